@@ -1,0 +1,223 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures under tests/golden/ from the REAL reference.
+
+Run in the build container only (it needs /root/reference, which does not exist on the
+GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+What it does
+  1. converts every MatrixMarket file of predict_and_recompute/matrices/ to a compressed
+     ``matrices/<name>.npz`` holding exactly the CSR arrays that
+     ``scipy.sparse.csr_matrix(scipy.io.mmread(...))`` produces (figure_gen.py:350);
+  2. imports the reference solvers and callbacks unmodified
+     (numerical_experiments/cg_variants, numerical_experiments/callbacks), runs the nine
+     ``*_pcg`` variants with the set-up of figure_gen.py:31-44 and the callbacks of
+     figure_gen.py:37 on the cases below, plus ``exact_pcg`` in longdouble
+     (figure_gen.py:53-56) to find the departure index k* (SURVEY.md section 8c);
+  3. asserts that oracle/cg_oracle.py reproduces every reference history BIT FOR BIT;
+  4. stores the reference histories, k*, and the published table metrics
+     (figures/convergence_table_data.tex) in ``histories.npz`` / ``table.json``;
+  5. runs the reference's mpi4py solvers on one rank through a 15-line fake ``mpi4py``
+     module and stores their final errors in ``mpi_kat.json``.
+"""
+import contextlib
+import io
+import json
+import os
+import re
+import sys
+import types
+import warnings
+
+import numpy as np
+import scipy.io
+import scipy.sparse as sps
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference/predict_and_recompute"
+sys.dont_write_bytecode = True
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(REF, "numerical_experiments"))
+warnings.filterwarnings("ignore")
+
+import cg_variants as ref_solvers            # noqa: E402  (the reference)
+import callbacks as ref_callbacks            # noqa: E402  (the reference)
+from oracle import cg_oracle as orc          # noqa: E402
+
+REF_FUN = {tag: getattr(ref_solvers, name) for tag, name in orc.VARIANTS.items()}
+
+# (case name, matrix source, max_iter, preconditioner) -- max_iter from figure_gen.py:247-315
+CASES = [
+    ("bcsstk03_jacobi", "bcsstk03", 250, "jacobi"),
+    ("bcsstk03_None", "bcsstk03", 1250, None),
+    ("nos4_jacobi", "nos4", 120, "jacobi"),
+    ("nos4_None", "nos4", 150, None),
+    ("model_48_8_3_None", "model_48_8_3", 110, None),
+    ("model_48_8_3_jacobi", "model_48_8_3", 200, "jacobi"),
+    ("494_bus_jacobi", "494_bus", 500, "jacobi"),
+    ("bcsstm22_None", "bcsstm22", 85, None),
+    ("nos6_jacobi", "nos6", 130, "jacobi"),
+    ("bcsstk15_jacobi", "bcsstk15", 830, "jacobi"),
+    ("poisson_ca_jacobi", "poisson_ca", 60, "jacobi"),
+    ("poisson2d_32_jacobi", ("poisson2d", 32), 120, "jacobi"),
+    ("poisson2d_128_jacobi", ("poisson2d", 128), 420, "jacobi"),
+    ("poisson3d_12_jacobi", ("poisson3d", 12), 60, "jacobi"),
+    ("poisson3d_32_None", ("poisson3d", 32), 130, None),
+]
+
+
+def load_mtx(name):
+    return sps.csr_matrix(scipy.io.mmread(os.path.join(REF, "matrices", name + ".mtx")))
+
+
+def get_matrix(src):
+    if isinstance(src, tuple):
+        return getattr(orc, src[0])(*src[1:])
+    return load_mtx(src)
+
+
+def convert_matrices():
+    out = os.path.join(HERE, "matrices")
+    os.makedirs(out, exist_ok=True)
+    for fn in sorted(os.listdir(os.path.join(REF, "matrices"))):
+        if not fn.endswith(".mtx"):
+            continue
+        A = load_mtx(fn[:-4])
+        assert A.has_canonical_format
+        # store the lower triangle only (the matrices are symmetric); the loader mirrors it
+        # and the assertion below guarantees the round trip is exact.
+        L = sps.tril(A, format="coo")
+        np.savez_compressed(os.path.join(out, fn[:-4] + ".npz"), n=A.shape[0],
+                            row=L.row.astype(np.int32), col=L.col.astype(np.int32), val=L.data)
+        B = load_npz_matrix(os.path.join(out, fn[:-4] + ".npz"))
+        assert (B.indptr == A.indptr).all() and (B.indices == A.indices).all()
+        assert (B.data == A.data).all(), fn
+        print(f"matrix {fn[:-4]:14s} n={A.shape[0]:6d} nnz={A.nnz:7d}")
+
+
+def load_npz_matrix(path):
+    z = np.load(path)
+    n = int(z["n"])
+    row, col, val = z["row"], z["col"], z["val"]
+    off = row != col
+    A = sps.coo_matrix((np.concatenate([val, val[off]]),
+                        (np.concatenate([row, col[off]]), np.concatenate([col, row[off]]))),
+                       shape=(n, n)).tocsr()
+    A.sort_indices()
+    return A
+
+
+def run_reference(A, max_iter, prec_name):
+    """figure_gen.py:31-60 without the file I/O."""
+    n = A.shape[0]
+    x_true = np.ones(n) / np.sqrt(n)
+    b = A @ x_true
+    x0 = np.zeros(n)
+    cbs = [ref_callbacks.error_A_norm, ref_callbacks.residual_2_norm,
+           ref_callbacks.error_2_norm, ref_callbacks.updated_residual_2_norm]
+    prec = lambda x: x
+    prec_long = lambda x: x
+    if prec_name == "jacobi":
+        prec = lambda x: (1 / A.diagonal()) * x
+        prec_long = lambda x: (1 / A.diagonal().astype(np.longdouble)) * x
+    res = {}
+    for tag, fun in REF_FUN.items():
+        res[tag] = fun(A, b, x0, max_iter, callbacks=cbs, x_true=x_true, preconditioner=prec)
+    with contextlib.redirect_stdout(io.StringIO()):
+        res["exact"] = ref_solvers.exact_pcg(
+            A.astype(np.longdouble), b.astype(np.longdouble), x0.astype(np.longdouble),
+            min(max_iter, n), callbacks=cbs, x_true=x_true.astype(np.longdouble),
+            preconditioner=prec_long)
+    return res
+
+
+def parse_table():
+    """figures/convergence_table_data.tex -> {case: {"iters": [...7], "acc": [...7]}}
+    column order figure_gen.py:360: hs cg m pr gv pipe_pr_m pipe_pr."""
+    rows = {}
+    path = os.path.join(REF, "numerical_experiments/figures/convergence_table_data.tex")
+    for line in open(path):
+        cells = [c.strip() for c in line.strip().rstrip("\\").split("&")]
+        if len(cells) < 18:
+            continue
+        name = re.sub(r"\\texttt\{(.*)\}", r"\1", cells[0]).replace("\\_", "_")
+        prec = "jacobi" if cells[1].startswith("Jac") else "None"
+        val = lambda c: re.sub(r"\\tableemph", "", c).strip("{} ")
+        iters = [0 if val(c) == "-" else int(val(c)) for c in cells[4:11]]
+        acc = [float(val(c)) for c in cells[11:18]]
+        rows[f"{name}_{prec}"] = {"n": int(cells[2]), "nnz": int(cells[3]), "iters": iters, "acc": acc}
+    return rows
+
+
+def mpi_kats():
+    """Reference mpi4py solvers on ONE rank through a fake mpi4py."""
+    class _Comm:
+        def Get_size(self): return 1
+        def Get_rank(self): return 0
+        def Barrier(self): pass
+        def Allreduce(self, send, recv, op=None): recv[0][...] = send[0]
+    fake = types.ModuleType("mpi4py")
+    fake.MPI = types.SimpleNamespace(COMM_WORLD=_Comm(), DOUBLE=None, SUM=None,
+                                     Wtime=lambda: 0.0)
+    sys.modules["mpi4py"] = fake
+    import importlib.util
+    out = {}
+    n, its = 1536, 1500
+    lam = orc.model_problem_spectrum(n)
+    b = lam / np.sqrt(n)
+    A = np.diag(lam)
+    for tag, fn in [("hs", "hs_cg"), ("cg", "cg_cg"), ("gv", "gv_cg"), ("pr", "pr_cg"),
+                    ("pipe_pr", "pipe_pr_cg")]:
+        spec = importlib.util.spec_from_file_location(
+            "ref_mpi_" + fn, os.path.join(REF, "scaling_experiments_mpi4py/cg_variants", fn + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        x, _ = getattr(mod, fn)(_Comm(), A.copy(), b.copy(), its)
+        err = float(np.linalg.norm(np.ones(n) / np.sqrt(n) - x))
+        xo = orc.solve_mpi_style(tag, lam, b.copy(), its)
+        erro = float(np.linalg.norm(np.ones(n) / np.sqrt(n) - xo))
+        print(f"mpi KAT {fn:11s} ref err {err:.6e}  oracle err {erro:.6e}")
+        # converged errors are rounding-noise dominated (strided ddot in the reference's
+        # pipe_pr_cg.py:60-63 sums in another order): same size, not same bits
+        assert 0.5 <= err / erro <= 2.0, (fn, err, erro)
+        out[tag] = {"n": n, "max_iter": its, "error": err}
+    return out
+
+
+def main():
+    convert_matrices()
+    hist = {}
+    meta = {}
+    for case, src, max_iter, prec in CASES:
+        A = get_matrix(src)
+        res = run_reference(A, max_iter, prec)
+        x_true, b, x0 = orc.setup_problem(A)
+        dinv = orc.jacobi_dinv(A) if prec == "jacobi" else None
+        kstar = {}
+        for tag in orc.VARIANTS:
+            o = orc.solve(tag, A, b, x0, max_iter, dinv=dinv, x_true=x_true)
+            assert o["name"] == res[tag]["name"]
+            for h in orc.HISTORIES:
+                ref_h = np.asarray(res[tag][h], dtype=np.float64)
+                if not np.array_equal(o[h], ref_h, equal_nan=True):
+                    bad = np.nonzero(o[h] != ref_h)[0]
+                    raise AssertionError(f"oracle != reference: {case} {tag} {h} first at k={bad[0]}")
+                hist[f"{case}/{tag}/{h}"] = ref_h
+            kstar[tag] = orc.departure_index(res[tag]["updated_residual_2_norm"],
+                                             res["exact"]["updated_residual_2_norm"])
+        for h in orc.HISTORIES:
+            hist[f"{case}/exact/{h}"] = np.asarray(res["exact"][h], dtype=np.float64)
+        meta[case] = {"matrix": src if isinstance(src, str) else list(src), "max_iter": max_iter,
+                      "preconditioner": prec, "n": int(A.shape[0]), "nnz": int(A.nnz), "kstar": kstar}
+        print(f"case {case:22s} oracle == reference bit-for-bit; k* = {kstar}")
+    np.savez_compressed(os.path.join(HERE, "histories.npz"), **hist)
+    json.dump(meta, open(os.path.join(HERE, "cases.json"), "w"), indent=1)
+    json.dump(parse_table(), open(os.path.join(HERE, "table.json"), "w"), indent=1)
+    json.dump(mpi_kats(), open(os.path.join(HERE, "mpi_kat.json"), "w"), indent=1)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
