@@ -1,0 +1,167 @@
+/* cgx.h -- C ABI of libcgx_b200.so: the B200 (sm_100a) implementation of the
+ * predict-and-recompute CG inner loop of tchen-research/new_cg_variants.
+ *
+ * The reference has NO native boundary (it is pure Python on numpy/scipy); this header is
+ * the boundary a binding for it would use.  Each entry point names the reference
+ * interface it replaces (paths relative to predict_and_recompute/ in the reference).
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns a cgx_status (0 = ok) except
+ *     the two getters; no exception crosses the ABI; the message of the last error of the
+ *     calling thread is available from cgx_last_error().
+ *   - "_host" pointers are ordinary host memory (numpy buffers); the library copies
+ *     them to/from the device.  "_dev" pointers are device pointers on the context's GPU
+ *     owned by the caller (e.g. torch tensors).
+ *   - a context is bound to one GPU and owns one stream; it is not re-entrant.  Distinct
+ *     contexts may be driven from distinct host threads/processes (one per GPU).
+ *   - all floating point is IEEE binary64; indices are int32 (scipy's CSR index type).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *     with CGX_ERR_CUDA.
+ */
+#ifndef CGX_H_
+#define CGX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGX_VERSION 100
+
+typedef enum {
+  CGX_OK = 0,
+  CGX_ERR_ARG = 1,        /* bad argument / call order */
+  CGX_ERR_CUDA = 2,       /* CUDA runtime error (see cgx_last_error) */
+  CGX_ERR_BREAKDOWN = 3,  /* a reduced scalar became non-finite at iteration
+                             info.breakdown_iter; histories are valid before it and hold
+                             what IEEE arithmetic produced after it (as the reference) */
+  CGX_ERR_UNSUPPORTED = 4
+} cgx_status;
+
+/* Variant ids.  Reference functions (numerical_experiments/cg_variants/):
+ *   HS        hs_pcg        hs_cg.py:70-131        Hestenes-Stiefel
+ *   CG        cg_pcg        cg_cg.py:77-146        Chronopoulos-Gear
+ *   GV        gv_pcg        gv_cg.py:89-176        Ghysels-Vanroose (w_replace = never)
+ *   PR        pr_pcg        pr_cg.py:93-171        predict-and-recompute
+ *   M         m_pcg         pr_cg.py:93-164,172    Meurant predictor
+ *   PIPE_PR   pipe_pr_pcg   pipe_pr_cg.py:109-205  pipelined predict-and-recompute
+ *   PIPE_P    pipe_p_pcg    pipe_pr_cg.py:195-199  pipelined predict (no recompute of w)
+ *   PIPE_PR_M pipe_pr_m_pcg pipe_pr_cg.py:213-217
+ *   PIPE_P_M  pipe_p_m_pcg  pipe_pr_cg.py:207-211
+ * The un-preconditioned twins (hs_cg, ...) are the same ids with no Jacobi vector set. */
+typedef enum {
+  CGX_HS = 0, CGX_CG = 1, CGX_GV = 2, CGX_PR = 3, CGX_M = 4,
+  CGX_PIPE_PR = 5, CGX_PIPE_P = 6, CGX_PIPE_PR_M = 7, CGX_PIPE_P_M = 8,
+  CGX_NUM_VARIANTS = 9
+} cgx_variant;
+
+/* History rows = the four standard callbacks (numerical_experiments/callbacks/):
+ *   error_A_norm.py:29-48, residual_2_norm.py:29-41, error_2_norm.py:29-48,
+ *   updated_residual_2_norm.py:29-40.  Row r of the history buffer is
+ *   hist[r*max_iter + k], k = 0 .. max_iter-1 (k = 0 is the initial state). */
+enum {
+  CGX_HIST_ERROR_A_NORM = 1u,
+  CGX_HIST_RESIDUAL_2_NORM = 2u,
+  CGX_HIST_ERROR_2_NORM = 4u,
+  CGX_HIST_UPDATED_RESIDUAL_2_NORM = 8u,
+  CGX_HIST_ALL = 15u
+};
+#define CGX_HIST_ROWS 4
+
+/* Execution path. AUTO picks PERSISTENT for latency-bound sizes. */
+typedef enum {
+  CGX_PATH_AUTO = 0,
+  CGX_PATH_STREAM = 1,     /* 2-3 fused kernels per iteration, bandwidth-tuned */
+  CGX_PATH_PERSISTENT = 2  /* one cooperative-grid launch runs every iteration */
+} cgx_path;
+
+typedef struct {
+  double loop_ms;          /* device time of the iteration loop (CUDA events) */
+  double setup_ms;         /* device time of the initialisation kernels */
+  double h2d_bytes;        /* bytes copied host->device by the call */
+  double d2h_bytes;        /* bytes copied device->host by the call */
+  int64_t kernel_launches; /* kernels of this library launched by the call */
+  int32_t iterations;      /* loop trips executed (max_iter - 1) */
+  int32_t breakdown_iter;  /* -1, or first k at which a reduced scalar was non-finite */
+  int32_t path;            /* cgx_path actually used */
+  int32_t reserved;
+} cgx_info;
+
+typedef struct cgx_ctx cgx_ctx;
+
+int cgx_version(void);
+const char* cgx_last_error(void);
+/* number of CUDA devices visible, or 0 (never fails). */
+int cgx_device_count(void);
+
+int cgx_ctx_create(int device, cgx_ctx** out);
+int cgx_ctx_destroy(cgx_ctx* ctx);
+
+/* ---- operator A.  Replaces the scipy CSR operand of every `A @ v` in the solvers
+ *      (e.g. hs_cg.py:123, pr_cg.py:152, pipe_pr_cg.py:179,181): canonical CSR, fp64
+ *      values, int32 indices.  Row sums are accumulated in stored order with separately
+ *      rounded multiply and add, as scipy's csr_matvec does. */
+int cgx_set_csr_host(cgx_ctx* ctx, int64_t n, int64_t nnz, const int32_t* indptr_host,
+                     const int32_t* indices_host, const double* data_host);
+/* Matrix-free Dirichlet Poisson stencil in natural ordering i = x + nx*(y + ny*z):
+ * dim = 2 (5-point, nz must be 1) or 3 (7-point); `diag` on the diagonal, `off` on the
+ * 2*dim neighbours.  Equivalent to the CSR matrix kron(I,T)+kron(T,I)[+...] scaled
+ * (matrices/poisson_ca.mtx is the 16x16 instance). */
+int cgx_set_stencil(cgx_ctx* ctx, int dim, int64_t nx, int64_t ny, int64_t nz, double diag,
+                    double off);
+
+/* ---- preconditioner.  Replaces the callable `preconditioner(v)` of the *_pcg solvers
+ *      (figure_gen.py:40-44): dinv_host == NULL -> identity, else z = dinv * v
+ *      elementwise (Jacobi: dinv = 1/A.diagonal(), computed by the caller). */
+int cgx_set_jacobi_host(cgx_ctx* ctx, const double* dinv_host, int64_t n);
+
+/* ---- problem vectors: b, x0 and (optional, may be NULL) x_true of
+ *      `solver(A, b, x0, max_iter, ..., x_true=...)` (figure_gen.py:31-34,59). */
+int cgx_load_problem_host(cgx_ctx* ctx, const double* b_host, const double* x0_host,
+                          const double* x_true_host, int64_t n);
+int cgx_load_problem_dev(cgx_ctx* ctx, const double* b_dev, const double* x0_dev,
+                         const double* x_true_dev, int64_t n);
+
+/* ---- run `max_iter - 1` iterations of `variant` on the loaded problem, recording the
+ *      history rows selected by hist_mask on the device.  Replaces the body of
+ *      hs_pcg / cg_pcg / gv_pcg / pr_master_pcg / pipe_pr_master_pcg.  Asynchronous work
+ *      is complete when the call returns. */
+int cgx_run(cgx_ctx* ctx, int variant, int max_iter, unsigned hist_mask, int path,
+            cgx_info* info);
+
+/* ---- the same solve, resumable: cgx_begin initialises (k = 0) and cgx_advance runs the
+ *      next `niter` iterations (clamped to max_iter - 1).  cgx_run == begin + advance(all).
+ *      This is what lets arbitrary Python callbacks (the reference's
+ *      `callback(**locals())` protocol, e.g. hs_cg.py:128-129) observe x_k, r_k and the
+ *      scalars between iterations without a CPU solve. */
+int cgx_begin(cgx_ctx* ctx, int variant, int max_iter, unsigned hist_mask, int path);
+int cgx_advance(cgx_ctx* ctx, int niter);
+int cgx_get_info(cgx_ctx* ctx, cgx_info* info);
+/* out9 = a_k, a_{k-1}, b_k, nu_k, nu_{k-1}, mu_k, eta_k, delta_k, gamma_k */
+int cgx_get_scalars(cgx_ctx* ctx, double* out9);
+
+/* ---- results: x_k of the last iteration and the history rows (CGX_HIST_ROWS*max_iter
+ *      doubles, rows not selected are zero).  Either pointer may be NULL. */
+int cgx_fetch_host(cgx_ctx* ctx, double* x_host, double* hist_host);
+int cgx_fetch_dev(cgx_ctx* ctx, double* x_dev, double* hist_dev);
+/* one named state vector ("x","r","rt","p","s","st","w","wt","u","ut","t") for tests */
+int cgx_fetch_vector_host(cgx_ctx* ctx, const char* name, double* out_host);
+
+/* ---- the whole reference call in one: load + run + fetch with HOST buffers
+ *      (this is what `trial = method(A,b,x0,max_iter,callbacks=...,x_true=...,
+ *      preconditioner=...)`, figure_gen.py:59, maps to once A and dinv are set). */
+int cgx_solve_host(cgx_ctx* ctx, int variant, const double* b_host, const double* x0_host,
+                   const double* x_true_host, int64_t n, int max_iter, unsigned hist_mask,
+                   int path, double* x_host, double* hist_host, cgx_info* info);
+
+/* ---- single primitives, exposed for the unit tests of SURVEY.md section 7:
+ *      y = A v (scipy `A @ v`) and the deterministic fp64 dot (numpy `u @ v`). */
+int cgx_spmv_host(cgx_ctx* ctx, const double* v_host, double* y_host, int64_t n);
+int cgx_dot_host(cgx_ctx* ctx, const double* u_host, const double* v_host, int64_t n,
+                 double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGX_H_ */

@@ -1,0 +1,72 @@
+"""In-tree build of libcgx_b200.so (sm_100a only) with plain nvcc.
+
+    python -m new_cg_variants_b200.build [--force]
+
+The shared library is written next to this file so that it travels to the GPU box with
+the repository snapshot; it links only the CUDA runtime (no torch, no cuBLAS/cuSPARSE).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libcgx_b200.so")
+STAMP = LIB_PATH + ".stamp"
+
+SOURCES = ["cgx.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared",
+    "--expt-relaxed-constexpr", "--extended-lambda",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libcgx_b200.so cannot be built")
+
+
+def _fingerprint() -> str:
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
+    files.append(os.path.join(ROOT, "include", "cgx.h"))
+    for path in files:
+        with open(path, "rb") as fh:
+            h.update(path.encode())
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    fp = _fingerprint()
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP):
+        if open(STAMP).read().strip() == fp:
+            return LIB_PATH
+    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", LIB_PATH,
+           *[os.path.join(CSRC, s) for s in SOURCES], "-lcuda"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    log = proc.stdout + proc.stderr
+    with open(os.path.join(PKG_DIR, "build.log"), "w") as fh:
+        fh.write(" ".join(cmd) + "\n" + log)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + log[-6000:])
+    if verbose:
+        print(log)
+    with open(STAMP, "w") as fh:
+        fh.write(fp)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -110,16 +110,50 @@ def _record(hist, k, A, b, x, r, x_true):
 # --------------------------------------------------------------------------------------
 # the solver: one stepper for all nine preconditioned variants
 # --------------------------------------------------------------------------------------
-def solve(variant, A, b, x0, max_iter, dinv=None, x_true=None, history=True, return_state=False):
+def _blas_dot(u, v):
+    return u @ v
+
+
+def _pairwise_dot(u, v):
+    return np.sum(u * v)                     # numpy pairwise summation, products rounded
+
+
+def _reversed_dot(u, v):
+    return u[::-1] @ v[::-1]                 # strided BLAS path, opposite order
+
+
+def _lanes8_dot(u, v):
+    t = u * v                                # 8 interleaved accumulators, like a SIMD ddot
+    m = (t.shape[0] // 8) * 8
+    return (t[:m].reshape(-1, 8).sum(axis=0).sum() + t[m:].sum()) if m else t.sum()
+
+
+def _extended_dot(u, v):
+    return float(u.astype(np.longdouble) @ v.astype(np.longdouble))   # nearly exact
+
+
+# alternative summation orders for the rounding-sensitivity ensemble
+DOT_ORDERS = {"blas": _blas_dot, "pairwise": _pairwise_dot, "reversed": _reversed_dot,
+              "lanes8": _lanes8_dot, "extended": _extended_dot}
+
+
+def solve(variant, A, b, x0, max_iter, dinv=None, x_true=None, history=True, return_state=False,
+          dot=None):
     """Run ``max_iter-1`` iterations of ``variant`` exactly as the reference does.
 
     dinv: None for the identity preconditioner, else the vector the Jacobi lambda
     multiplies by.  Returns the reference's ``output`` dict (name, max_iter and the four
     history arrays, index 0 = initial state); with ``return_state`` also the final
     vectors/scalars (used by the single-iteration kernel tests).
+
+    dot: inner-product implementation; the default is numpy's ``u @ v`` (what the reference
+    calls).  Other summation orders (``DOT_ORDERS``) are used ONLY to measure how sensitive
+    the reference's own curves are to rounding order (tests/golden/make_golden.py).
     """
     if variant not in VARIANTS:
         raise ValueError(f"unknown variant {variant!r}")
+    if dot is None:
+        dot = _blas_dot          # the reference's `u @ v`
     M = (lambda v: v) if dinv is None else (lambda v: dinv * v)
     pipe = variant.startswith("pipe")
     meurant = variant == "m" or variant.endswith("_m")
@@ -139,42 +173,42 @@ def solve(variant, A, b, x0, max_iter, dinv=None, x_true=None, history=True, ret
     w = wt = s = st = u = ut = None
     eta = dl = gam = None
     if variant == "hs":
-        nu = r @ rt
+        nu = dot(r, rt)
         s = A @ p
-        mu = p @ s
+        mu = dot(p, s)
     elif variant == "cg":
         w = A @ rt
-        nu = r @ rt
-        eta = w @ rt
+        nu = dot(r, rt)
+        eta = dot(w, rt)
         s = A @ p
-        mu = p @ s
+        mu = dot(p, s)
     elif variant == "gv":
         w = A @ rt
         wt = M(w)
         s = np.copy(w)
         st = np.copy(wt)
         u = A @ wt
-        nu = r @ rt
-        eta = w @ r            # gv_cg.py:115 (never consumed)
-        mu = p @ s
+        nu = dot(r, rt)
+        eta = dot(w, r)            # gv_cg.py:115 (never consumed)
+        mu = dot(p, s)
     elif not pipe:             # pr / m
-        nu = rt @ r
+        nu = dot(rt, r)
         s = A @ p
         st = M(s)
-        mu = p @ s
-        dl = r @ st
-        gam = st @ s
+        mu = dot(p, s)
+        dl = dot(r, st)
+        gam = dot(st, s)
     else:                      # pipe_* family
-        nu = rt @ r
+        nu = dot(rt, r)
         s = A @ p
         st = M(s)
         w = np.copy(s)
         wt = np.copy(st)
         u = A @ st
         ut = M(u)
-        mu = p @ s
-        dl = r @ st
-        gam = st @ s
+        mu = dot(p, s)
+        dl = dot(r, st)
+        gam = dot(st, s)
     a = nu / mu
     beta = 0
     _record(hist, 0, A, b, x, r, x_true)
@@ -185,18 +219,18 @@ def solve(variant, A, b, x0, max_iter, dinv=None, x_true=None, history=True, ret
             x = x + a1 * p
             r = r - a1 * s
             rt = M(r)
-            nu = r @ rt
+            nu = dot(r, rt)
             beta = nu / nu1
             p = rt + beta * p
             s = A @ p
-            mu = p @ s
+            mu = dot(p, s)
         elif variant == "cg":                                 # cg_cg.py:130-140
             x = x + a1 * p
             r = r - a1 * s
             rt = M(r)
             w = A @ rt
-            nu = r @ rt
-            eta = w @ rt
+            nu = dot(r, rt)
+            eta = dot(w, rt)
             beta = nu / nu1
             p = rt + beta * p
             s = w + beta * s
@@ -208,8 +242,8 @@ def solve(variant, A, b, x0, max_iter, dinv=None, x_true=None, history=True, ret
             w = w - a1 * u
             wt = M(w)
             t = A @ wt
-            nu = r @ rt
-            eta = w @ rt
+            nu = dot(r, rt)
+            eta = dot(w, rt)
             beta = nu / nu1
             p = rt + beta * p
             s = w + beta * s
@@ -226,10 +260,10 @@ def solve(variant, A, b, x0, max_iter, dinv=None, x_true=None, history=True, ret
             p = rt + beta * p
             s = A @ p
             st = M(s)
-            mu = p @ s
-            dl = r @ st
-            gam = st @ s
-            nu = rt @ r
+            mu = dot(p, s)
+            dl = dot(r, st)
+            gam = dot(st, s)
+            nu = dot(rt, r)
         else:                                                 # pipe_pr_cg.py:169-187
             dl1, gam1 = dl, gam
             x = x + a1 * p
@@ -247,10 +281,10 @@ def solve(variant, A, b, x0, max_iter, dinv=None, x_true=None, history=True, ret
             if recompute_w:
                 w = A @ rt
                 wt = M(w)
-            mu = p @ s
-            dl = r @ st
-            gam = st @ s
-            nu = rt @ r
+            mu = dot(p, s)
+            dl = dot(r, st)
+            gam = dot(st, s)
+            nu = dot(rt, r)
         a = nu / mu
         _record(hist, k, A, b, x, r, x_true)
 

@@ -1,0 +1,113 @@
+"""Shared test utilities: fixture loading and THE parity rule.
+
+Parity rule (BASELINE.json north_star + SURVEY.md section 8c, made precise in DESIGN.md
+section "Parity"):
+
+  P1  for k < window: |dev - ref| / |ref| <= 1e-10 on updated_residual_2_norm and
+      residual_2_norm, where ``window`` (tests/golden/cases.json) is the number of
+      iterations over which the reference's curve is still that of exact arithmetic: the
+      reference agrees with exact_pcg to 1e-12 AND with itself under four other
+      inner-product summation orders to 1e-10;
+  P2  attainable accuracy: log10(min_k rel. A-norm error) within log10(2) of the band the
+      reference itself spans under those summation orders, widened by the band's width;
+  P3  iterations to rel. A-norm error <= 1e-5 within max(1, 1 %) of that band, widened by
+      the band's width.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sps
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(HERE, "golden")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import cg_oracle as orc   # noqa: E402  (tests may use the oracle)
+
+RTOL = 1e-10
+RESIDUAL_HISTS = ("updated_residual_2_norm", "residual_2_norm")
+
+_cases = None
+_hist = None
+
+
+def cases():
+    global _cases
+    if _cases is None:
+        _cases = json.load(open(os.path.join(GOLDEN, "cases.json")))
+    return _cases
+
+
+def golden_history(case, tag, name):
+    global _hist
+    if _hist is None:
+        _hist = np.load(os.path.join(GOLDEN, "histories.npz"))
+    return _hist[f"{case}/{tag}/{name}"]
+
+
+def matrix_names():
+    return sorted(f[:-4] for f in os.listdir(os.path.join(GOLDEN, "matrices")) if f.endswith(".npz"))
+
+
+def load_matrix(name):
+    """The CSR matrix ``csr_matrix(mmread(matrices/<name>.mtx))`` of the reference."""
+    z = np.load(os.path.join(GOLDEN, "matrices", name + ".npz"))
+    n = int(z["n"])
+    row, col, val = z["row"], z["col"], z["val"]
+    off = row != col
+    A = sps.coo_matrix((np.concatenate([val, val[off]]),
+                        (np.concatenate([row, col[off]]), np.concatenate([col, row[off]]))),
+                       shape=(n, n)).tocsr()
+    A.sort_indices()
+    return A
+
+
+def case_matrix(case):
+    src = cases()[case]["matrix"]
+    if isinstance(src, list):
+        return getattr(orc, src[0])(*src[1:])
+    return load_matrix(src)
+
+
+def case_problem(case):
+    meta = cases()[case]
+    A = case_matrix(case)
+    x_true, b, x0 = orc.setup_problem(A)
+    dinv = orc.jacobi_dinv(A) if meta["preconditioner"] == "jacobi" else None
+    return A, b, x0, x_true, dinv, meta["max_iter"]
+
+
+def first_deviation(a, ref, tol=RTOL):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.abs(np.asarray(a) - ref) / np.abs(ref)
+    bad = np.nonzero(~(rel <= tol))[0]
+    return int(bad[0]) if len(bad) else int(len(ref))
+
+
+def check_parity(dev, ref, band, label=""):
+    """Assert P1-P3 for one (case, variant).  dev/ref: dicts of history arrays."""
+    w = band["window"]
+    for h in RESIDUAL_HISTS:
+        kd = first_deviation(dev[h][:w], ref[h][:w])
+        assert kd >= w, (f"{label} {h}: deviates from the reference by more than {RTOL} at k={kd} "
+                         f"(< window {w}); dev={dev[h][kd]!r} ref={ref[h][kd]!r}")
+    it, acc = orc.convergence_metrics(dev["error_A_norm"])
+    lo, hi = band["acc_band"]
+    width = hi - lo
+    assert lo - width - math.log10(2) <= acc <= hi + width + math.log10(2), \
+        f"{label}: attainable accuracy 1e{acc:.2f} outside reference band [{lo:.2f}, {hi:.2f}]"
+    ilo, ihi = band["iters_band"]
+    iw = ihi - ilo
+    slack = lambda v: max(1, math.ceil(0.01 * v))
+    if ilo == 0 or ihi == 0:      # "never reached" in (part of) the band: nothing to bound
+        return it, acc
+    assert ilo - iw - slack(ilo) <= it <= ihi + iw + slack(ihi), \
+        f"{label}: {it} iterations to 1e-5, reference band [{ilo}, {ihi}]"
+    return it, acc
