@@ -141,6 +141,18 @@ int cgx_get_info(cgx_ctx* ctx, cgx_info* info);
 /* out9 = a_k, a_{k-1}, b_k, nu_k, nu_{k-1}, mu_k, eta_k, delta_k, gamma_k */
 int cgx_get_scalars(cgx_ctx* ctx, double* out9);
 
+/* ---- tuning/testing switches.  "tma" = 0 forces the generic (non-TMA) stencil kernel so
+ *      the two SpMV implementations can be compared bit for bit. */
+int cgx_set_option(cgx_ctx* ctx, const char* name, int value);
+
+/* ---- optional per-kernel-class device timing of the iteration loop (CUDA event pair
+ *      around every launch; used by bench.py for the roofline of the dominant kernel,
+ *      never during a timed run).  Classes 0 .. cgx_profile_class_count()-1. */
+int cgx_set_profile(cgx_ctx* ctx, int on);
+int cgx_get_profile(cgx_ctx* ctx, int cls, double* ms, int64_t* launches);
+const char* cgx_profile_class_name(int cls);
+int cgx_profile_class_count(void);
+
 /* ---- results: x_k of the last iteration and the history rows (CGX_HIST_ROWS*max_iter
  *      doubles, rows not selected are zero).  Either pointer may be NULL. */
 int cgx_fetch_host(cgx_ctx* ctx, double* x_host, double* hist_host);

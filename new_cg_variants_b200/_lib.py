@@ -60,6 +60,11 @@ PROTOTYPES = {
     "cgx_advance": (C.c_int, [_P, C.c_int]),
     "cgx_get_info": (C.c_int, [_P, C.POINTER(CgxInfo)]),
     "cgx_get_scalars": (C.c_int, [_P, c_double_p]),
+    "cgx_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "cgx_set_profile": (C.c_int, [_P, C.c_int]),
+    "cgx_get_profile": (C.c_int, [_P, C.c_int, c_double_p, C.POINTER(C.c_int64)]),
+    "cgx_profile_class_name": (C.c_char_p, [C.c_int]),
+    "cgx_profile_class_count": (C.c_int, []),
     "cgx_fetch_host": (C.c_int, [_P, c_double_p, c_double_p]),
     "cgx_fetch_dev": (C.c_int, [_P, _P, _P]),
     "cgx_fetch_vector_host": (C.c_int, [_P, C.c_char_p, c_double_p]),

@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if open(STAMP).read().strip() == fp:
             return LIB_PATH
     cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", LIB_PATH,
-           *[os.path.join(CSRC, s) for s in SOURCES], "-lcuda"]
+           *[os.path.join(CSRC, s) for s in SOURCES]]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
     with open(os.path.join(PKG_DIR, "build.log"), "w") as fh:

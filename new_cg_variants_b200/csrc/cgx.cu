@@ -8,11 +8,31 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/cgx.h"
 #include "cgx_kernels.cuh"
+#include "cgx_stencil_tma.cuh"
 
 using namespace cgx;
+
+// cuTensorMapEncodeTiled is resolved through the runtime so the library has no link-time
+// dependency on libcuda (it must load on the GPU-less build box for the ABI tests).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
 
 // ---------------------------------------------------------------------------------------
 // error plumbing
@@ -56,8 +76,17 @@ struct cgx_ctx {
   int* d_idx = nullptr;
   double* d_val = nullptr;
   i64 n = 0, nnz = 0;
-  // preconditioner
+  // preconditioner: pm = 0 identity, 1 Jacobi vector, 2 Jacobi with a constant diagonal
   double* d_dinv = nullptr;
+  double dinv_s = 1.0;
+  int pm = 0;
+  // TMA-staged stencil path
+  bool use_tma = false;
+  bool no_tma = false;             // cgx_set_option("tma", 0): force the generic stencil kernel
+  TmaGeom geom{};
+  int tma_grid[2] = {0, 0};        // grid size for 1 / 2 right-hand sides
+  CUtensorMap tmap[10];
+  bool tmap_ok[10] = {};
   // problem
   double* d_b = nullptr;
   double* d_x0 = nullptr;
@@ -73,6 +102,13 @@ struct cgx_ctx {
   unsigned hist_mask = 0;
   bool ran = false;
   i64 launches = 0;
+  // per-kernel-class profiling
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<int> prof_cls;
+  size_t prof_used = 0;
+  double prof_ms[16] = {};
+  i64 prof_n[16] = {};
   // current run
   int variant = 0, max_iter = 0, cur_k = 0, path = CGX_PATH_STREAM;
   i64 launches_run = 0;
@@ -151,6 +187,7 @@ extern "C" int cgx_ctx_destroy(cgx_ctx* c) {
   free_state(c); free_problem(c); free_op(c);
   cudaFree(c->d_dinv); cudaFree(c->d_sc); cudaFree(c->d_partials); cudaFree(c->d_ticket);
   for (auto& e : c->ev) cudaEventDestroy(e);
+  for (auto& e : c->prof_events) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
   return CGX_OK;
@@ -204,13 +241,18 @@ extern "C" int cgx_set_stencil(cgx_ctx* c, int dim, int64_t nx, int64_t ny, int6
 extern "C" int cgx_set_jacobi_host(cgx_ctx* c, const double* dinv, int64_t n) {
   if (!c) return fail(CGX_ERR_ARG, "cgx_set_jacobi_host: ctx is NULL");
   CU(cudaSetDevice(c->device));
-  if (!dinv) { cudaFree(c->d_dinv); c->d_dinv = nullptr; return CGX_OK; }
+  if (!dinv) { cudaFree(c->d_dinv); c->d_dinv = nullptr; c->pm = 0; c->dinv_s = 1.0; return CGX_OK; }
   if (c->op_kind == 0 || n != c->n)
     return fail(CGX_ERR_ARG, "cgx_set_jacobi_host: set the operator first; n must match (%lld vs %lld)",
                 (long long)n, (long long)c->n);
   if (!c->d_dinv) CU(cudaMalloc(&c->d_dinv, sizeof(double) * n));
   CU(cudaMemcpyAsync(c->d_dinv, dinv, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  // constant diagonal (every Poisson stencil): the same products with one HBM stream less
+  bool constant = true;
+  for (i64 i = 1; i < n && constant; ++i) constant = (memcmp(&dinv[i], &dinv[0], sizeof(double)) == 0);
+  c->pm = constant ? 2 : 1;
+  c->dinv_s = dinv[0];
   return CGX_OK;
 }
 
@@ -251,23 +293,134 @@ extern "C" int cgx_load_problem_dev(cgx_ctx* c, const double* b, const double* x
 // ---------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------
-template <int MODE, bool PREC, bool MEUR>
+// Optional per-kernel-class timing (cgx_set_profile): an event pair around every launch of
+// the iteration loop, resolved after the stream has drained.  Off in timed runs.
+enum { PC_EW0 = 0, PC_SP0 = 7, PC_INSTR = 15, PC_COUNT = 16 };
+static const char* kClassNames[PC_COUNT] = {
+    "ew_hs1", "ew_hs2", "ew_cg", "ew_gv", "ew_pr", "ew_pipe_r", "ew_pipe_n",
+    "sp_plain", "sp_hs", "sp_cg", "sp_gv", "sp_pr", "sp_pipe_r", "sp_pipe_n", "sp_resid",
+    "instrument"};
+
+struct ProfScope {
+  cgx_ctx* c; int cls; size_t slot = 0; bool on;
+  ProfScope(cgx_ctx* c_, int cls_) : c(c_), cls(cls_), on(c_->profile) {
+    if (!on) return;
+    if (c->prof_used + 2 > c->prof_events.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); c->prof_events.push_back(e); }
+    }
+    slot = c->prof_used; c->prof_used += 2;
+    c->prof_cls.push_back(cls);
+    cudaEventRecord(c->prof_events[slot], c->stream);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(c->prof_events[slot + 1], c->stream); }
+};
+static void prof_resolve(cgx_ctx* c) {
+  for (size_t i = 0; i < c->prof_cls.size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->prof_events[2 * i], c->prof_events[2 * i + 1]) == cudaSuccess) {
+      c->prof_ms[c->prof_cls[i]] += ms; c->prof_n[c->prof_cls[i]]++;
+    }
+  }
+  c->prof_cls.clear(); c->prof_used = 0;
+}
+
+// which state vector a fused SpMV pass reads through TMA (second one for the 2-RHS pass)
+template <int MODE> struct SpInput { static constexpr int v0 = -1, v1 = -1; };
+template <> struct SpInput<SP_HS> { static constexpr int v0 = 3 /*V_P*/, v1 = -1; };
+template <> struct SpInput<SP_PR> { static constexpr int v0 = 3 /*V_P*/, v1 = -1; };
+template <> struct SpInput<SP_CG> { static constexpr int v0 = 2 /*V_RT*/, v1 = -1; };
+template <> struct SpInput<SP_GV> { static constexpr int v0 = 7 /*V_WT*/, v1 = -1; };
+template <> struct SpInput<SP_PIPE_R> { static constexpr int v0 = 5 /*V_ST*/, v1 = 2 /*V_RT*/; };
+template <> struct SpInput<SP_PIPE_N> { static constexpr int v0 = 5 /*V_ST*/, v1 = -1; };
+
+static size_t tma_smem_bytes(int nv) { return (size_t)kRing * nv * kPlaneStride * sizeof(double); }
+
+template <int MODE, int PM, bool MEUR>
 static void launch_spmv(cgx_ctx* c, const Args& g, const double* vin, double* vout) {
+  ProfScope ps(c, PC_SP0 + MODE);
+  constexpr int v0 = SpInput<MODE>::v0, v1 = SpInput<MODE>::v1;
+  if constexpr (v0 >= 0) {
+    if (c->op_kind == 2 && c->use_tma && c->tmap_ok[v0] && (v1 < 0 || c->tmap_ok[v1 < 0 ? 0 : v1])) {
+      constexpr int nv = (v1 >= 0) ? 2 : 1;
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaFuncSetAttribute(stencil_tma_kernel<MODE, PM, MEUR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)tma_smem_bytes(nv));
+        attr_set = true;
+      }
+      stencil_tma_kernel<MODE, PM, MEUR><<<c->tma_grid[nv - 1], kTmaThreads, tma_smem_bytes(nv), c->stream>>>(
+          c->tmap[v0], c->tmap[v1 < 0 ? v0 : v1], c->geom, g);
+      c->launches++;
+      return;
+    }
+  }
   const int grid = grid_for(c, c->n);
   if (c->op_kind == 1)
-    spmv_kernel<CsrOp, MODE, PREC, MEUR><<<grid, kBlock, 0, c->stream>>>(c->csr, g, vin, vout);
+    spmv_kernel<CsrOp, MODE, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(c->csr, g, vin, vout);
   else
-    spmv_kernel<StencilOp, MODE, PREC, MEUR><<<grid, kBlock, 0, c->stream>>>(c->sten, g, vin, vout);
+    spmv_kernel<StencilOp, MODE, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(c->sten, g, vin, vout);
   c->launches++;
 }
-template <int KID, bool PREC, bool MEUR>
+template <int KID, int PM, bool MEUR>
 static void launch_ew(cgx_ctx* c, const Args& g) {
   const int grid = grid_for(c, (c->n + 1) / 2);
-  ew_kernel<KID, PREC, MEUR><<<grid, kBlock, 0, c->stream>>>(g);
+  ProfScope ps(c, PC_EW0 + KID);
+  ew_kernel<KID, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(g);
   c->launches++;
+}
+
+// Tensor maps + work decomposition of the TMA stencil path for the current state vectors.
+static int setup_tma(cgx_ctx* c, unsigned need) {
+  c->use_tma = false;
+  for (auto& ok : c->tmap_ok) ok = false;
+  if (c->op_kind != 2 || c->no_tma) return CGX_OK;
+  const StencilOp& S = c->sten;
+  if (S.nx % 2 != 0 || S.nx < 2) return CGX_OK;        // TMA needs 16-byte global strides
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return CGX_OK;
+  for (int i = 0; i < V_COUNT; ++i) {
+    if (!(need & (1u << i)) || !c->vec[i]) continue;
+    cuuint64_t gdim[3] = {(cuuint64_t)S.nx, (cuuint64_t)S.ny, (cuuint64_t)S.nz};
+    cuuint64_t gstr[2] = {(cuuint64_t)S.nx * 8, (cuuint64_t)S.nx * S.ny * 8};
+    cuuint32_t box[3] = {(cuuint32_t)kPX, (cuuint32_t)kPY, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&c->tmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->vec[i], gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    c->tmap_ok[i] = (r == CUDA_SUCCESS);
+  }
+  TmaGeom& G = c->geom;
+  G.nx = S.nx; G.ny = S.ny; G.nz = S.nz;
+  G.ntx = (S.nx + kTX - 1) / kTX; G.nty = (S.ny + kTY - 1) / kTY;
+  G.zoff = 0; G.has_zlo = 0; G.has_zhi = 0;
+  G.diag = S.diag; G.off = S.off;
+  // resident CTAs: shared memory bound (227 KB/SM), 8 x 256 threads at most
+  const int cols = G.ntx * G.nty;
+  int per_sm1 = std::min(8, (int)(227 * 1024 / (tma_smem_bytes(1) + 1024)));
+  int per_sm2 = std::min(8, (int)(227 * 1024 / (tma_smem_bytes(2) + 1024)));
+  const int cap1 = c->sm_count * per_sm1, cap2 = c->sm_count * per_sm2;
+  // planes per chunk: balance (full waves) against z-halo re-reads (lz+2)/lz; fixed per
+  // problem so the summation order of the fused dots is reproducible
+  double best = -1.0; int best_lz = 1;
+  for (int lz : {1, 2, 4, 8, 16, 32, 64}) {
+    if (lz > S.nz && lz != 1) continue;
+    const int chunks = (S.nz + lz - 1) / lz;
+    const i64 items = (i64)cols * chunks;
+    const i64 grid = std::min<i64>(items, cap1);
+    const double waves = (double)((items + grid - 1) / grid);
+    const double eff = ((double)items / (waves * grid)) * ((double)lz / (lz + 2.0));
+    if (eff > best) { best = eff; best_lz = lz; }
+  }
+  G.lz = best_lz; G.nchunks = (S.nz + best_lz - 1) / best_lz;
+  const i64 items = (i64)cols * G.nchunks;
+  c->tma_grid[0] = (int)std::min<i64>(items, cap1);
+  c->tma_grid[1] = (int)std::min<i64>(items, cap2);
+  c->use_tma = true;
+  return CGX_OK;
 }
 static void launch_instrument(cgx_ctx* c, const Args& g) {
   const int grid = grid_for(c, c->n);
+  ProfScope ps(c, PC_INSTR);
   if (c->op_kind == 1) {
     if (c->has_xtrue) instrument_kernel<CsrOp, true><<<grid, kBlock, 0, c->stream>>>(c->csr, g);
     else instrument_kernel<CsrOp, false><<<grid, kBlock, 0, c->stream>>>(c->csr, g);
@@ -310,7 +463,7 @@ static VariantInfo variant_info(int v, bool prec) {
 }
 
 // one iteration of the streaming path --------------------------------------------------
-template <bool PREC>
+template <int PREC>
 static void iterate_stream(cgx_ctx* c, int variant, const VariantInfo& vi, Args& g) {
   switch (variant) {
     case CGX_HS:
@@ -361,16 +514,16 @@ static int init_state(cgx_ctx* c, int variant, const VariantInfo& vi, Args& g) {
   const double* dinv = c->d_dinv;
   double** v = c->vec;
   CU(cudaMemcpyAsync(v[V_X], c->d_x0, bytes, cudaMemcpyDeviceToDevice, c->stream));
-  launch_spmv<SP_RESID, false, false>(c, g, v[V_X], v[V_R]);            // r = b - A x0
+  launch_spmv<SP_RESID, 0, false>(c, g, v[V_X], v[V_R]);            // r = b - A x0
   launch_scale(c, dinv, v[V_R], v[V_RT]);                               // rt = M r
   CU(cudaMemcpyAsync(v[V_P], v[V_RT], bytes, cudaMemcpyDeviceToDevice, c->stream));  // p = rt
   launch_dot(c, v[V_R], v[V_RT], nullptr, 0);                           // nu = r.rt
   if (variant == CGX_HS || variant == CGX_PR || variant == CGX_M || vi.pipe) {
-    launch_spmv<SP_PLAIN, false, false>(c, g, v[V_P], v[V_S]);          // s = A p
+    launch_spmv<SP_PLAIN, 0, false>(c, g, v[V_P], v[V_S]);          // s = A p
     launch_dot(c, v[V_P], v[V_S], nullptr, 1);                          // mu = p.s
   }
   if (variant == CGX_CG || variant == CGX_GV) {
-    launch_spmv<SP_PLAIN, false, false>(c, g, v[V_RT], v[V_W]);         // w = A rt
+    launch_spmv<SP_PLAIN, 0, false>(c, g, v[V_RT], v[V_W]);         // w = A rt
     CU(cudaMemcpyAsync(v[V_S], v[V_W], bytes, cudaMemcpyDeviceToDevice, c->stream));  // s = A p = w
     launch_dot(c, v[V_P], v[V_S], nullptr, 1);                          // mu = p.s
     launch_dot(c, v[V_W], v[V_RT], nullptr, 2);                         // eta = w.rt
@@ -378,7 +531,7 @@ static int init_state(cgx_ctx* c, int variant, const VariantInfo& vi, Args& g) {
   if (variant == CGX_GV) {
     launch_scale(c, dinv, v[V_W], v[V_WT]);                             // wt = M w
     CU(cudaMemcpyAsync(v[V_ST], v[V_WT], bytes, cudaMemcpyDeviceToDevice, c->stream));
-    launch_spmv<SP_PLAIN, false, false>(c, g, v[V_WT], v[V_T]);         // t = A wt
+    launch_spmv<SP_PLAIN, 0, false>(c, g, v[V_WT], v[V_T]);         // t = A wt
     CU(cudaMemcpyAsync(v[V_U], v[V_T], bytes, cudaMemcpyDeviceToDevice, c->stream));  // u = A wt
   }
   if (vi.cls == 2) {
@@ -389,7 +542,7 @@ static int init_state(cgx_ctx* c, int variant, const VariantInfo& vi, Args& g) {
     launch_scale(c, dinv, v[V_S], v[V_ST]);                             // st = M s
     CU(cudaMemcpyAsync(v[V_W], v[V_S], bytes, cudaMemcpyDeviceToDevice, c->stream));   // w = s
     if (v[V_WT]) CU(cudaMemcpyAsync(v[V_WT], v[V_ST], bytes, cudaMemcpyDeviceToDevice, c->stream));
-    launch_spmv<SP_PLAIN, false, false>(c, g, v[V_ST], v[V_U]);         // u = A st
+    launch_spmv<SP_PLAIN, 0, false>(c, g, v[V_ST], v[V_U]);         // u = A st
   }
   init_scalars_kernel<<<1, 1, 0, c->stream>>>(c->d_sc, vi.cls, vi.meurant ? 1 : 0);
   c->launches++;
@@ -401,7 +554,7 @@ static Args make_args(cgx_ctx* c) {
   g.x = c->vec[V_X]; g.r = c->vec[V_R]; g.rt = c->vec[V_RT]; g.p = c->vec[V_P];
   g.s = c->vec[V_S]; g.st = c->vec[V_ST]; g.w = c->vec[V_W]; g.wt = c->vec[V_WT];
   g.u = c->vec[V_U]; g.t = c->vec[V_T];
-  g.dinv = c->d_dinv; g.b = c->d_b; g.xtrue = c->d_xtrue;
+  g.dinv = c->d_dinv; g.dinv_s = c->dinv_s; g.b = c->d_b; g.xtrue = c->d_xtrue;
   g.sc = c->d_sc; g.partials = c->d_partials; g.ticket = c->d_ticket;
   g.hist = c->d_hist; g.hist_len = c->hist_len; g.hist_mask = c->hist_mask;
   g.n = c->n; g.k = c->cur_k;
@@ -431,6 +584,7 @@ extern "C" int cgx_begin(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
   }
   CU(cudaMemsetAsync(c->d_hist, 0, sizeof(double) * CGX_HIST_ROWS * (size_t)max_iter, c->stream));
   c->hist_mask = hist_mask;
+  { int trc = setup_tma(c, vi.need); if (trc) return trc; }
   c->variant = variant; c->max_iter = max_iter; c->cur_k = 0;
   c->path = CGX_PATH_STREAM;
   c->launches_run = 0; c->loop_ms = 0.0;
@@ -447,6 +601,7 @@ extern "C" int cgx_begin(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
   float ms0 = 0.f;
   CU(cudaEventElapsedTime(&ms0, c->ev[0], c->ev[1]));
   c->setup_ms = ms0;
+  if (c->profile) { c->prof_cls.clear(); c->prof_used = 0; }   // initialisation is not profiled
   c->launches_run = c->launches - launches0;
   c->ran = true;
   return CGX_OK;
@@ -464,8 +619,9 @@ extern "C" int cgx_advance(cgx_ctx* c, int niter) {
   CU(cudaEventRecord(c->ev[1], c->stream));
   for (int k = c->cur_k + 1; k <= last; ++k) {
     g.k = k;
-    if (prec) iterate_stream<true>(c, c->variant, vi, g);
-    else iterate_stream<false>(c, c->variant, vi, g);
+    if (c->pm == 2) iterate_stream<2>(c, c->variant, vi, g);
+    else if (c->pm == 1) iterate_stream<1>(c, c->variant, vi, g);
+    else iterate_stream<0>(c, c->variant, vi, g);
     if (c->hist_mask) launch_instrument(c, g);
   }
   CU(cudaEventRecord(c->ev[2], c->stream));
@@ -474,6 +630,7 @@ extern "C" int cgx_advance(cgx_ctx* c, int niter) {
   float ms1 = 0.f;
   CU(cudaEventElapsedTime(&ms1, c->ev[1], c->ev[2]));
   c->loop_ms += ms1;
+  if (c->profile) prof_resolve(c);
   c->launches_run += c->launches - launches0;
   c->cur_k = std::max(c->cur_k, last);
   return CGX_OK;
@@ -493,6 +650,30 @@ extern "C" int cgx_get_info(cgx_ctx* c, cgx_info* info) {
   info->reserved = 0;
   return CGX_OK;
 }
+
+extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
+  if (!c || !name) return fail(CGX_ERR_ARG, "cgx_set_option: bad arguments");
+  if (!strcmp(name, "tma")) { c->no_tma = (value == 0); return CGX_OK; }
+  return fail(CGX_ERR_ARG, "cgx_set_option: unknown option '%s'", name);
+}
+
+extern "C" int cgx_set_profile(cgx_ctx* c, int on) {
+  if (!c) return fail(CGX_ERR_ARG, "cgx_set_profile: ctx is NULL");
+  c->profile = on != 0;
+  for (int i = 0; i < PC_COUNT; ++i) { c->prof_ms[i] = 0.0; c->prof_n[i] = 0; }
+  c->prof_cls.clear(); c->prof_used = 0;
+  return CGX_OK;
+}
+extern "C" int cgx_get_profile(cgx_ctx* c, int cls, double* ms, int64_t* launches) {
+  if (!c || cls < 0 || cls >= PC_COUNT) return fail(CGX_ERR_ARG, "cgx_get_profile: bad arguments");
+  if (ms) *ms = c->prof_ms[cls];
+  if (launches) *launches = c->prof_n[cls];
+  return CGX_OK;
+}
+extern "C" const char* cgx_profile_class_name(int cls) {
+  return (cls >= 0 && cls < PC_COUNT) ? kClassNames[cls] : "";
+}
+extern "C" int cgx_profile_class_count(void) { return PC_COUNT; }
 
 // scalars of the recurrences after the last completed iteration:
 // out[0..8] = a_k, a_{k-1}, b_k, nu_k, nu_{k-1}, mu_k, eta_k, delta_k, gamma_k
@@ -570,7 +751,7 @@ extern "C" int cgx_spmv_host(cgx_ctx* c, const double* v, double* y, int64_t n) 
   CU(cudaMemcpyAsync(dv, v, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
   Args g{};
   g.n = n;
-  launch_spmv<SP_PLAIN, false, false>(c, g, dv, dy);
+  launch_spmv<SP_PLAIN, 0, false>(c, g, dv, dy);
   CU(cudaMemcpyAsync(y, dy, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());

@@ -72,7 +72,7 @@ struct StencilOp {
 struct Args {
   double* x; double* r; double* rt; double* p; double* s; double* st;
   double* w; double* wt; double* u; double* t;
-  const double* dinv;
+  const double* dinv; double dinv_s;
   const double* b; const double* xtrue;
   Scal* sc; double* partials; unsigned* ticket;
   double* hist; int hist_len; unsigned hist_mask;
@@ -110,12 +110,16 @@ __device__ __forceinline__ double predict_beta(bool meurant, double nu, double a
 // -------------------------------------------------------------------------------------
 // Fused vector pass: one HBM sweep over the state vectors of stage KID.
 // -------------------------------------------------------------------------------------
-template <int KID, bool PREC, int W>
+// PM: preconditioner mode -- 0 identity, 1 Jacobi vector g.dinv, 2 Jacobi scalar g.dinv_s
+// (a constant diagonal, e.g. every Poisson stencil: same products, one HBM stream less).
+template <int KID, int PM, int W>
 __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b,
                                         double (&red)[kNRed]) {
+  constexpr bool PREC = PM != 0;
   Pk<W> dv{};
-  if constexpr (PREC) dv = ldp<W>(g.dinv, i);
-  auto M = [&](double v, int l) { return PREC ? mul_(dv.v[l], v) : v; };
+  if constexpr (PM == 1) dv = ldp<W>(g.dinv, i);
+  const double ds = g.dinv_s;
+  auto M = [&](double v, int l) { return PM == 1 ? mul_(dv.v[l], v) : (PM == 2 ? mul_(ds, v) : v); };
 
   if constexpr (KID == EW_HS1) {             // hs_cg.py:118-120
     Pk<W> r = ldp<W>(g.r, i), s = ldp<W>(g.s, i);
@@ -215,16 +219,16 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
   }
 }
 
-template <int KID, bool PREC, bool MEURANT>
+template <int KID, int PM, bool MEURANT>
 __global__ void __launch_bounds__(kBlock) ew_kernel(const Args g) {
   const double a = g.sc->a, b = g.sc->b;
   double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
   const i64 nv = g.n >> 1;
   const i64 stride = (i64)gridDim.x * kBlock;
   for (i64 i = (i64)blockIdx.x * kBlock + threadIdx.x; i < nv; i += stride)
-    ew_body<KID, PREC, 2>(g, 2 * i, a, b, red);
+    ew_body<KID, PM, 2>(g, 2 * i, a, b, red);
   if ((g.n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
-    ew_body<KID, PREC, 1>(g, g.n - 1, a, b, red);
+    ew_body<KID, PM, 1>(g, g.n - 1, a, b, red);
 
   constexpr int NR = EwTraits<KID>::NR;
   if constexpr (NR > 0) {
@@ -268,7 +272,31 @@ template <> struct SpTraits<SP_HS> { static constexpr int NR = 1; };
 template <> struct SpTraits<SP_CG> { static constexpr int NR = 2; };
 template <> struct SpTraits<SP_PR> { static constexpr int NR = 3; };
 
-template <class Op, int MODE, bool PREC, bool MEURANT>
+// Scalar recurrences that close a fused SpMV pass (run by one thread with the grid totals).
+template <int MODE, bool MEURANT>
+__device__ __forceinline__ void spmv_finalize(Scal* sc, int k, const double* acc) {
+  if constexpr (MODE == SP_HS) {             // hs_cg.py:124-125
+    sc->mu = acc[0];
+    sc->a1 = sc->a; sc->a = div_(sc->nu, acc[0]);
+    note_breakdown(sc, k, sc->a, sc->b);
+  } else if constexpr (MODE == SP_CG) {      // cg_cg.py:134-136,139-140
+    const double nu1 = sc->nu, a1 = sc->a, nu = acc[0], eta = acc[1];
+    const double bb = div_(nu, nu1);
+    const double mu = sub_(eta, mul_(div_(bb, a1), nu));
+    sc->nu1 = nu1; sc->nu = nu; sc->eta = eta; sc->b = bb; sc->mu = mu;
+    sc->a1 = a1; sc->a = div_(nu, mu);
+    note_breakdown(sc, k, sc->a, bb);
+  } else if constexpr (MODE == SP_PR) {      // pr_cg.py:154-158 then :149-150
+    const double mu = acc[0], del = acc[1], gam = acc[2], nu = sc->nu;
+    sc->mu = mu; sc->del = del; sc->gam = gam;
+    const double an = div_(nu, mu);
+    sc->a1 = sc->a; sc->a = an;
+    sc->b = predict_beta(MEURANT, nu, an, del, gam);
+    note_breakdown(sc, k, an, sc->b);
+  }
+}
+
+template <class Op, int MODE, int PM, bool MEURANT>
 __global__ void __launch_bounds__(kBlock) spmv_kernel(const Op A, const Args g, const double* vin,
                                                      double* vout) {
   double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
@@ -302,7 +330,7 @@ __global__ void __launch_bounds__(kBlock) spmv_kernel(const Op A, const Args g, 
       double y[1];
       A.template row<1>(i, [&](i64 j, double (&v)[1]) { v[0] = g.p[j]; }, y);
       g.s[i] = y[0];
-      const double sti = PREC ? mul_(g.dinv[i], y[0]) : y[0];
+      const double sti = PM == 1 ? mul_(g.dinv[i], y[0]) : (PM == 2 ? mul_(g.dinv_s, y[0]) : y[0]);
       red[0] = fma(g.p[i], y[0], red[0]);
       red[1] = fma(g.r[i], sti, red[1]);
       red[2] = fma(sti, y[0], red[2]);
@@ -325,25 +353,7 @@ __global__ void __launch_bounds__(kBlock) spmv_kernel(const Op A, const Args g, 
     Scal* sc = g.sc;
     const int k = g.k;
     grid_sum_finalize<NR>(v, g.partials, g.ticket, [=](const double* acc) {
-      if constexpr (MODE == SP_HS) {             // hs_cg.py:124-125
-        sc->mu = acc[0];
-        sc->a1 = sc->a; sc->a = div_(sc->nu, acc[0]);
-        note_breakdown(sc, k, sc->a, sc->b);
-      } else if constexpr (MODE == SP_CG) {      // cg_cg.py:134-136,139-140
-        const double nu1 = sc->nu, a1 = sc->a, nu = acc[0], eta = acc[1];
-        const double bb = div_(nu, nu1);
-        const double mu = sub_(eta, mul_(div_(bb, a1), nu));
-        sc->nu1 = nu1; sc->nu = nu; sc->eta = eta; sc->b = bb; sc->mu = mu;
-        sc->a1 = a1; sc->a = div_(nu, mu);
-        note_breakdown(sc, k, sc->a, bb);
-      } else {                                   // SP_PR: pr_cg.py:154-158 then :149-150
-        const double mu = acc[0], del = acc[1], gam = acc[2], nu = sc->nu;
-        sc->mu = mu; sc->del = del; sc->gam = gam;
-        const double an = div_(nu, mu);
-        sc->a1 = sc->a; sc->a = an;
-        sc->b = predict_beta(MEURANT, nu, an, del, gam);
-        note_breakdown(sc, k, an, sc->b);
-      }
+      spmv_finalize<MODE, MEURANT>(sc, k, acc);
     });
   }
 }

@@ -1,0 +1,247 @@
+// cgx_stencil_tma.cuh -- TMA-staged matrix-free stencil SpMV with fused epilogues (sm_100a).
+//
+// One CTA owns a BX x BY column of the grid and marches through a chunk of z-planes.  Each
+// plane (with its one-point x/y halo) is brought into shared memory by ONE bulk-tensor copy
+// (cp.async.bulk.tensor.3d, SASS UTMALDG) that completes on an mbarrier; out-of-range
+// coordinates are zero-filled by the TMA unit, which is exactly the Dirichlet boundary, so
+// the load path has no boundary branches.  A ring of kRing planes keeps the copy of plane
+// z+2 in flight while plane z is computed from planes z-1, z, z+1, so every input value
+// is read from L2/HBM once per CTA column (+ halo) instead of seven times.
+//
+// The row sum is still evaluated in canonical-CSR term order with separately rounded
+// multiply and add (absent neighbours are skipped by a select, not by adding a zero), so
+// results stay bit-identical to scipy's `A @ v` on the equivalent CSR matrix.
+#pragma once
+#include <cuda.h>
+
+#include "cgx_kernels.cuh"
+
+namespace cgx {
+
+constexpr int kTX = 128;              // tile extent in x (points)
+constexpr int kTY = 8;                // tile extent in y
+constexpr int kPX = kTX + 2;          // box extent incl. halo
+constexpr int kPY = kTY + 2;
+constexpr int kPlane = kPX * kPY;     // doubles per staged plane
+constexpr int kPlaneStride = ((kPlane * 8 + 127) / 128) * 128 / 8;   // 128-B aligned slots
+constexpr int kRing = 4;
+constexpr int kTmaThreads = 256;
+constexpr int kPtsPerThread = kTX * kTY / kTmaThreads;               // 4
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a copy that never lands (bad descriptor) must fail loudly, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    if (global_ns() - t0 > 2000000000ull) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Geometry of one launch.  zlo/zhi: does a plane exist below z=0 / above z=nz-1 of THIS
+// slab (ghost planes of a multi-GPU partition; the tensor map then covers them and
+// zoff = 1 shifts local plane z to tensor coordinate z + 1).
+struct TmaGeom {
+  int nx, ny, nz;
+  int ntx, nty, nchunks, lz;     // tiles in x, y; z-chunks; planes per chunk
+  int zoff;                      // tensor z coordinate of local plane 0
+  int has_zlo, has_zhi;
+  double diag, off;
+};
+
+// MODE: SP_* of cgx_kernels.cuh.  PM: 0 identity, 1 Jacobi vector, 2 Jacobi scalar.
+template <int MODE, int PM, bool MEUR>
+__global__ void __launch_bounds__(kTmaThreads)
+stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                   const TmaGeom G, const Args g) {
+  constexpr int NV = (MODE == SP_PIPE_R) ? 2 : 1;
+  extern __shared__ __align__(128) double smem[];        // [kRing][NV][kPlaneStride]
+  __shared__ __align__(8) uint64_t bar[kRing];
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kRing; ++s) mbar_init(&bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int ly = tid >> 5;              // 0..7   row of the tile
+  const int lx = tid & 31;              // lane: points lx, lx+32, lx+64, lx+96
+  const i64 plane_pts = (i64)G.nx * G.ny;
+  const int work_items = G.ntx * G.nty * G.nchunks;
+  constexpr uint32_t kBytes = (uint32_t)(kPlane * 8 * NV);
+
+  double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
+  uint32_t L = 0;                        // loads issued so far by this CTA (ring position)
+
+  for (int wi = blockIdx.x; wi < work_items; wi += gridDim.x) {
+    const int tx = wi % G.ntx;
+    const int ty = (wi / G.ntx) % G.nty;
+    const int tc = wi / (G.ntx * G.nty);
+    const int x0 = tx * kTX, y0 = ty * kTY;
+    const int z0 = tc * G.lz;
+    const int z1 = min(z0 + G.lz, G.nz);
+    const uint32_t Lbase = L;            // load index of plane z0-1
+
+    auto issue = [&](int z, uint32_t li) {          // one thread: plane z -> slot li % kRing
+      const int slot = li % kRing;
+      const bool exists = (z >= 0 || G.has_zlo) && (z < G.nz || G.has_zhi);
+      if (!exists) {                                // beyond the domain: never read (selects)
+        mbar_arrive(&bar[slot]);
+        return;
+      }
+      double* dst = smem + (size_t)slot * NV * kPlaneStride;
+      mbar_arrive_expect_tx(&bar[slot], kBytes);
+      tma_load_3d(dst, &tm0, x0 - 1, y0 - 1, z + G.zoff, &bar[slot]);
+      if constexpr (NV == 2) tma_load_3d(dst + kPlaneStride, &tm1, x0 - 1, y0 - 1, z + G.zoff, &bar[slot]);
+    };
+    auto wait_load = [&](uint32_t li) { mbar_wait(&bar[li % kRing], (li / kRing) & 1u); };
+
+    if (tid == 0) {
+      issue(z0 - 1, Lbase);
+      issue(z0, Lbase + 1);
+      issue(z0 + 1, Lbase + 2);
+    }
+    wait_load(Lbase);
+    wait_load(Lbase + 1);
+
+    const int gy = y0 + ly;
+    const bool row_ok = gy < G.ny;
+    const bool has_ym = gy > 0, has_yp = gy < G.ny - 1;
+
+    for (int z = z0; z < z1; ++z) {
+      const uint32_t j = (uint32_t)(z - z0);
+      if (tid == 0 && z + 2 <= z1) issue(z + 2, Lbase + j + 3);    // slot of plane z-2: free
+      // operands that do not go through shared memory: fetch them before blocking on the
+      // plane so their latency overlaps the wait
+      constexpr bool kNeedR = (MODE == SP_CG || MODE == SP_PR);
+      constexpr bool kNeedD = (MODE == SP_PR && PM == 1);
+      double rv[kPtsPerThread], dvv[kPtsPerThread];
+      const i64 ibase = (i64)z * plane_pts + (i64)gy * G.nx + x0 + lx;
+#pragma unroll
+      for (int m = 0; m < kPtsPerThread; ++m) {
+        const bool ok = row_ok && (x0 + lx + 32 * m) < G.nx;
+        rv[m] = (kNeedR && ok) ? g.r[ibase + 32 * m] : 0.0;
+        dvv[m] = (kNeedD && ok) ? g.dinv[ibase + 32 * m] : 0.0;
+      }
+      wait_load(Lbase + j + 2);                                     // plane z+1 has landed
+      const double* pm = smem + (size_t)((Lbase + j) % kRing) * NV * kPlaneStride;
+      const double* pc = smem + (size_t)((Lbase + j + 1) % kRing) * NV * kPlaneStride;
+      const double* pp = smem + (size_t)((Lbase + j + 2) % kRing) * NV * kPlaneStride;
+      const bool has_zm = (z > 0) || G.has_zlo;
+      const bool has_zp = (z < G.nz - 1) || G.has_zhi;
+
+      if (row_ok) {
+#pragma unroll
+        for (int m = 0; m < kPtsPerThread; ++m) {
+          const int px = lx + 32 * m;              // 0..127 within the tile
+          const int gx = x0 + px;
+          if (gx < G.nx) {
+            const int c = (ly + 1) * kPX + (px + 1);
+            const bool has_xm = gx > 0, has_xp = gx < G.nx - 1;
+            double y[NV], ctr[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              const double* qm = pm + v * kPlaneStride;
+              const double* qc = pc + v * kPlaneStride;
+              const double* qp = pp + v * kPlaneStride;
+              double acc = 0.0, t;
+              t = add_(acc, mul_(G.off, qm[c]));        acc = has_zm ? t : acc;
+              t = add_(acc, mul_(G.off, qc[c - kPX]));  acc = has_ym ? t : acc;
+              t = add_(acc, mul_(G.off, qc[c - 1]));    acc = has_xm ? t : acc;
+              ctr[v] = qc[c];
+              acc = add_(acc, mul_(G.diag, ctr[v]));
+              t = add_(acc, mul_(G.off, qc[c + 1]));    acc = has_xp ? t : acc;
+              t = add_(acc, mul_(G.off, qc[c + kPX]));  acc = has_yp ? t : acc;
+              t = add_(acc, mul_(G.off, qp[c]));        acc = has_zp ? t : acc;
+              y[v] = acc;
+            }
+            const i64 i = ibase + 32 * m;
+            auto M = [&](double v) {
+              if constexpr (PM == 1) return mul_(dvv[m], v);
+              else if constexpr (PM == 2) return mul_(g.dinv_s, v);
+              else return v;
+            };
+            if constexpr (MODE == SP_HS) {                 // hs_cg.py:123-124
+              g.s[i] = y[0];
+              red[0] = fma(ctr[0], y[0], red[0]);
+            } else if constexpr (MODE == SP_CG) {          // cg_cg.py:133-135
+              g.w[i] = y[0];
+              red[0] = fma(rv[m], ctr[0], red[0]);
+              red[1] = fma(y[0], ctr[0], red[1]);
+            } else if constexpr (MODE == SP_GV) {          // gv_cg.py:161
+              g.t[i] = y[0];
+            } else if constexpr (MODE == SP_PR) {          // pr_cg.py:152-156
+              g.s[i] = y[0];
+              const double sti = M(y[0]);
+              red[0] = fma(ctr[0], y[0], red[0]);
+              red[1] = fma(rv[m], sti, red[1]);
+              red[2] = fma(sti, y[0], red[2]);
+            } else if constexpr (MODE == SP_PIPE_R) {      // pipe_pr_cg.py:179-182
+              g.u[i] = y[0];
+              g.w[i] = y[NV - 1];
+            } else {                                       // SP_PIPE_N
+              g.u[i] = y[0];
+            }
+          }
+        }
+      }
+      __syncthreads();       // everyone is done with plane z-1 before its slot is refilled
+    }
+    L = Lbase + (uint32_t)(z1 - z0) + 2;   // planes z0-1 .. z1 were issued
+  }
+
+  constexpr int NR = SpTraits<MODE>::NR;
+  if constexpr (NR > 0) {
+    double v[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) v[j] = red[j];
+    Scal* sc = g.sc;
+    const int k = g.k;
+    grid_sum_finalize<NR>(v, g.partials, g.ticket, [=](const double* acc) {
+      spmv_finalize<MODE, MEUR>(sc, k, acc);
+    });
+  }
+}
+
+}  // namespace cgx

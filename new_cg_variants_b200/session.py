@@ -119,6 +119,24 @@ class Session:
         self.info = info.as_dict()
         return self.info
 
+    def set_option(self, name, value):
+        """Library switches, e.g. ("tma", 0) forces the generic stencil kernel."""
+        _lib.check(self._lib.cgx_set_option(self._ctx, name.encode(), int(value)))
+
+    def set_profile(self, on=True):
+        """Per-kernel-class device timing of the iteration loop (event pair per launch)."""
+        _lib.check(self._lib.cgx_set_profile(self._ctx, 1 if on else 0))
+
+    def get_profile(self):
+        """{class name: (total ms, launches)} accumulated since set_profile(True)."""
+        out = {}
+        for cls in range(self._lib.cgx_profile_class_count()):
+            ms, cnt = C.c_double(), C.c_int64()
+            _lib.check(self._lib.cgx_get_profile(self._ctx, cls, C.byref(ms), C.byref(cnt)))
+            if cnt.value:
+                out[self._lib.cgx_profile_class_name(cls).decode()] = (ms.value, cnt.value)
+        return out
+
     def scalars(self):
         out = np.zeros(9)
         _lib.check(self._lib.cgx_get_scalars(self._ctx, _lib.dptr(out)))
