@@ -333,7 +333,7 @@ template <> struct SpInput<SP_GV> { static constexpr int v0 = 7 /*V_WT*/, v1 = -
 template <> struct SpInput<SP_PIPE_R> { static constexpr int v0 = 5 /*V_ST*/, v1 = 2 /*V_RT*/; };
 template <> struct SpInput<SP_PIPE_N> { static constexpr int v0 = 5 /*V_ST*/, v1 = -1; };
 
-static size_t tma_smem_bytes(int nv) { return (size_t)kRing * nv * kPlaneStride * sizeof(double); }
+static size_t tma_smem_bytes(int nv) { return (size_t)kRing * nv * kPlaneStride * sizeof(double) + 128; }
 
 template <int MODE, int PM, bool MEUR>
 static void launch_spmv(cgx_ctx* c, const Args& g, const double* vin, double* vout) {
@@ -369,26 +369,25 @@ static void launch_ew(cgx_ctx* c, const Args& g) {
   c->launches++;
 }
 
-// Tensor maps + work decomposition of the TMA stencil path for the current state vectors.
-static int setup_tma(cgx_ctx* c, unsigned need) {
-  c->use_tma = false;
-  for (auto& ok : c->tmap_ok) ok = false;
-  if (c->op_kind != 2 || c->no_tma) return CGX_OK;
-  const StencilOp& S = c->sten;
-  if (S.nx % 2 != 0 || S.nx < 2) return CGX_OK;        // TMA needs 16-byte global strides
+// ---- TMA stencil path: descriptors and work decomposition -------------------------------
+static bool tma_encode(cgx_ctx* c, double* ptr, CUtensorMap* out) {
   EncodeTiledFn enc = get_encode_tiled();
-  if (!enc) return CGX_OK;
-  for (int i = 0; i < V_COUNT; ++i) {
-    if (!(need & (1u << i)) || !c->vec[i]) continue;
-    cuuint64_t gdim[3] = {(cuuint64_t)S.nx, (cuuint64_t)S.ny, (cuuint64_t)S.nz};
-    cuuint64_t gstr[2] = {(cuuint64_t)S.nx * 8, (cuuint64_t)S.nx * S.ny * 8};
-    cuuint32_t box[3] = {(cuuint32_t)kPX, (cuuint32_t)kPY, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&c->tmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->vec[i], gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    c->tmap_ok[i] = (r == CUDA_SUCCESS);
-  }
+  if (!enc || !ptr) return false;
+  const StencilOp& S = c->sten;
+  cuuint64_t gdim[3] = {(cuuint64_t)S.nx, (cuuint64_t)S.ny, (cuuint64_t)S.nz};
+  cuuint64_t gstr[2] = {(cuuint64_t)S.nx * 8, (cuuint64_t)S.nx * S.ny * 8};
+  cuuint32_t box[3] = {(cuuint32_t)kPX, (cuuint32_t)kPY, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ptr, gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool tma_prepare_geom(cgx_ctx* c) {
+  if (c->op_kind != 2 || c->no_tma) return false;
+  const StencilOp& S = c->sten;
+  if (S.nx % 2 != 0 || S.nx < 2) return false;         // TMA needs 16-byte global strides
+  if (!get_encode_tiled()) return false;
   TmaGeom& G = c->geom;
   G.nx = S.nx; G.ny = S.ny; G.nz = S.nz;
   G.ntx = (S.nx + kTX - 1) / kTX; G.nty = (S.ny + kTY - 1) / kTY;
@@ -415,9 +414,19 @@ static int setup_tma(cgx_ctx* c, unsigned need) {
   const i64 items = (i64)cols * G.nchunks;
   c->tma_grid[0] = (int)std::min<i64>(items, cap1);
   c->tma_grid[1] = (int)std::min<i64>(items, cap2);
+  return true;
+}
+
+static int setup_tma(cgx_ctx* c, unsigned need) {
+  c->use_tma = false;
+  for (auto& ok : c->tmap_ok) ok = false;
+  if (!tma_prepare_geom(c)) return CGX_OK;
+  for (int i = 0; i < V_COUNT; ++i)
+    if ((need & (1u << i)) && c->vec[i]) c->tmap_ok[i] = tma_encode(c, c->vec[i], &c->tmap[i]);
   c->use_tma = true;
   return CGX_OK;
 }
+
 static void launch_instrument(cgx_ctx* c, const Args& g) {
   const int grid = grid_for(c, c->n);
   ProfScope ps(c, PC_INSTR);
@@ -631,6 +640,11 @@ extern "C" int cgx_advance(cgx_ctx* c, int niter) {
   CU(cudaEventElapsedTime(&ms1, c->ev[1], c->ev[2]));
   c->loop_ms += ms1;
   if (c->profile) prof_resolve(c);
+  if (c->use_tma) {
+    int flag = 0;
+    CU(cudaMemcpyFromSymbol(&flag, g_tma_timeout, sizeof(int)));
+    if (flag) return fail(CGX_ERR_CUDA, "cgx_advance: a TMA plane copy did not complete within 1 s");
+  }
   c->launches_run += c->launches - launches0;
   c->cur_k = std::max(c->cur_k, last);
   return CGX_OK;

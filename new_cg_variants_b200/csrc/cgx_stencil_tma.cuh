@@ -20,7 +20,7 @@ namespace cgx {
 
 constexpr int kTX = 128;              // tile extent in x (points)
 constexpr int kTY = 8;                // tile extent in y
-constexpr int kPX = kTX + 2;          // box extent incl. halo
+constexpr int kPX = kTX + 4;          // box extent incl. halo: starts at x0-2 (TMA needs 16-B aligned starts)
 constexpr int kPY = kTY + 2;
 constexpr int kPlane = kPX * kPY;     // doubles per staged plane
 constexpr int kPlaneStride = ((kPlane * 8 + 127) / 128) * 128 / 8;   // 128-B aligned slots
@@ -60,11 +60,13 @@ __device__ __forceinline__ uint64_t global_ns() {
   return t;
 }
 // Bounded wait: a copy that never lands (bad descriptor) must fail loudly, not hang the GPU.
+// The flag is checked by the host after every synchronisation (CGX_ERR_CUDA).
+__device__ int g_tma_timeout = 0;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = global_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (global_ns() - t0 > 2000000000ull) __trap();
+    if (global_ns() - t0 > 1000000000ull) { atomicExch(&g_tma_timeout, 1); return; }
   }
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2,
@@ -94,7 +96,10 @@ __global__ void __launch_bounds__(kTmaThreads)
 stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                    const TmaGeom G, const Args g) {
   constexpr int NV = (MODE == SP_PIPE_R) ? 2 : 1;
-  extern __shared__ __align__(128) double smem[];        // [kRing][NV][kPlaneStride]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // [kRing][NV][kPlaneStride], 128-byte aligned whatever static shared memory precedes it
+  double* smem = reinterpret_cast<double*>(
+      smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
   __shared__ __align__(8) uint64_t bar[kRing];
 
   const int tid = threadIdx.x;
@@ -132,8 +137,8 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
       }
       double* dst = smem + (size_t)slot * NV * kPlaneStride;
       mbar_arrive_expect_tx(&bar[slot], kBytes);
-      tma_load_3d(dst, &tm0, x0 - 1, y0 - 1, z + G.zoff, &bar[slot]);
-      if constexpr (NV == 2) tma_load_3d(dst + kPlaneStride, &tm1, x0 - 1, y0 - 1, z + G.zoff, &bar[slot]);
+      tma_load_3d(dst, &tm0, x0 - 2, y0 - 1, z + G.zoff, &bar[slot]);
+      if constexpr (NV == 2) tma_load_3d(dst + kPlaneStride, &tm1, x0 - 2, y0 - 1, z + G.zoff, &bar[slot]);
     };
     auto wait_load = [&](uint32_t li) { mbar_wait(&bar[li % kRing], (li / kRing) & 1u); };
 
@@ -177,7 +182,7 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
           const int px = lx + 32 * m;              // 0..127 within the tile
           const int gx = x0 + px;
           if (gx < G.nx) {
-            const int c = (ly + 1) * kPX + (px + 1);
+            const int c = (ly + 1) * kPX + (px + 2);
             const bool has_xm = gx > 0, has_xp = gx < G.nx - 1;
             double y[NV], ctr[NV];
 #pragma unroll
