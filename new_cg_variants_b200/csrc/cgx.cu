@@ -398,22 +398,13 @@ static bool tma_prepare_geom(cgx_ctx* c) {
   int per_sm1 = std::min(8, (int)(227 * 1024 / (tma_smem_bytes(1) + 1024)));
   int per_sm2 = std::min(8, (int)(227 * 1024 / (tma_smem_bytes(2) + 1024)));
   const int cap1 = c->sm_count * per_sm1, cap2 = c->sm_count * per_sm2;
-  // planes per chunk: balance (full waves) against z-halo re-reads (lz+2)/lz; fixed per
-  // problem so the summation order of the fused dots is reproducible
-  double best = -1.0; int best_lz = 1;
-  for (int lz : {1, 2, 4, 8, 16, 32, 64}) {
-    if (lz > S.nz && lz != 1) continue;
-    const int chunks = (S.nz + lz - 1) / lz;
-    const i64 items = (i64)cols * chunks;
-    const i64 grid = std::min<i64>(items, cap1);
-    const double waves = (double)((items + grid - 1) / grid);
-    const double eff = ((double)items / (waves * grid)) * ((double)lz / (lz + 2.0));
-    if (eff > best) { best = eff; best_lz = lz; }
-  }
-  G.lz = best_lz; G.nchunks = (S.nz + best_lz - 1) / best_lz;
-  const i64 items = (i64)cols * G.nchunks;
-  c->tma_grid[0] = (int)std::min<i64>(items, cap1);
-  c->tma_grid[1] = (int)std::min<i64>(items, cap2);
+  // one CTA per resident slot; the kernel cuts the (column, plane) sequence evenly between
+  // them (>= 4 planes per CTA when the problem is large enough to keep the z-halo small)
+  G.lz = 0; G.nchunks = 0;
+  const i64 total = (i64)cols * S.nz;
+  const i64 want = std::max<i64>(1, (total + 3) / 4);
+  c->tma_grid[0] = (int)std::min<i64>(want, cap1);
+  c->tma_grid[1] = (int)std::min<i64>(want, cap2);
   return true;
 }
 

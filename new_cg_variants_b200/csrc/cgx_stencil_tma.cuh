@@ -113,19 +113,26 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
   const int ly = tid >> 5;              // 0..7   row of the tile
   const int lx = tid & 31;              // lane: points lx, lx+32, lx+64, lx+96
   const i64 plane_pts = (i64)G.nx * G.ny;
-  const int work_items = G.ntx * G.nty * G.nchunks;
   constexpr uint32_t kBytes = (uint32_t)(kPlane * 8 * NV);
 
   double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
   uint32_t L = 0;                        // loads issued so far by this CTA (ring position)
 
-  for (int wi = blockIdx.x; wi < work_items; wi += gridDim.x) {
-    const int tx = wi % G.ntx;
-    const int ty = (wi / G.ntx) % G.nty;
-    const int tc = wi / (G.ntx * G.nty);
+  // Static even split: the (column, plane) pairs, column-major, are cut into gridDim.x
+  // contiguous ranges, so every CTA streams the same number of planes (+-1) whatever the
+  // grid shape, and the assignment (hence the summation order of the fused dots) is a
+  // function of the problem size only.  A range that crosses a column end is processed as
+  // two z-segments.
+  const i64 total = (i64)G.ntx * G.nty * G.nz;
+  const i64 range_end = ((i64)blockIdx.x + 1) * total / gridDim.x;
+  for (i64 pos = (i64)blockIdx.x * total / gridDim.x; pos < range_end;) {
+    const int col = (int)(pos / G.nz);
+    const int z0 = (int)(pos - (i64)col * G.nz);
+    const int z1 = (int)min((i64)G.nz, (i64)z0 + (range_end - pos));
+    pos += z1 - z0;
+    const int tx = col % G.ntx;
+    const int ty = col / G.ntx;
     const int x0 = tx * kTX, y0 = ty * kTY;
-    const int z0 = tc * G.lz;
-    const int z1 = min(z0 + G.lz, G.nz);
     const uint32_t Lbase = L;            // load index of plane z0-1
 
     auto issue = [&](int z, uint32_t li) {          // one thread: plane z -> slot li % kRing

@@ -105,7 +105,8 @@ def test_stencil_solve_equals_csr_solve():
             d_s = _device_solve(tag, S, b, x0, 40, dinv, x_true)
             d_c = _device_solve(tag, A, b, x0, 40, dinv, x_true)
             for h in orc.HISTORIES:
-                np.testing.assert_allclose(d_s[h], d_c[h], rtol=1e-9, err_msg=f"{tag}/{h}")
+                np.testing.assert_allclose(d_s[h][:12], d_c[h][:12], rtol=1e-10, err_msg=f"{tag}/{h}")
+                np.testing.assert_allclose(d_s[h], d_c[h], rtol=1e-6, err_msg=f"{tag}/{h}")
 
 
 def test_runs_are_bitwise_repeatable():
