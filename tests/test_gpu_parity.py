@@ -106,7 +106,9 @@ def test_stencil_solve_equals_csr_solve():
             d_c = _device_solve(tag, A, b, x0, 40, dinv, x_true)
             for h in orc.HISTORIES:
                 np.testing.assert_allclose(d_s[h][:12], d_c[h][:12], rtol=1e-10, err_msg=f"{tag}/{h}")
-                np.testing.assert_allclose(d_s[h], d_c[h], rtol=1e-6, err_msg=f"{tag}/{h}")
+                # the tail is converged to rounding level: absolute floor relative to k = 0
+                np.testing.assert_allclose(d_s[h], d_c[h], rtol=1e-6, atol=1e-11 * d_c[h][0],
+                                           err_msg=f"{tag}/{h}")
 
 
 def test_runs_are_bitwise_repeatable():
