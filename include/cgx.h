@@ -141,8 +141,11 @@ int cgx_get_info(cgx_ctx* ctx, cgx_info* info);
 /* out9 = a_k, a_{k-1}, b_k, nu_k, nu_{k-1}, mu_k, eta_k, delta_k, gamma_k */
 int cgx_get_scalars(cgx_ctx* ctx, double* out9);
 
-/* ---- tuning/testing switches.  "tma" = 0 forces the generic (non-TMA) stencil kernel so
- *      the two SpMV implementations can be compared bit for bit. */
+/* ---- tuning/testing switches.  "tma" = 0 forces the generic (non-TMA) stencil kernel and
+ *      "csr_stream" = 0 the thread-per-row CSR kernel, so that two SpMV implementations can
+ *      be compared bit for bit; "persistent_threshold" = rows below which CGX_PATH_AUTO
+ *      takes the persistent kernel; "stub_allreduce" = 1 replaces the multi-GPU scalar
+ *      exchange by a local stand-in (timing experiment: exposed allreduce time). */
 int cgx_set_option(cgx_ctx* ctx, const char* name, int value);
 
 /* ---- optional per-kernel-class device timing of the iteration loop (CUDA event pair
@@ -166,6 +169,41 @@ int cgx_fetch_vector_host(cgx_ctx* ctx, const char* name, double* out_host);
 int cgx_solve_host(cgx_ctx* ctx, int variant, const double* b_host, const double* x0_host,
                    const double* x_true_host, int64_t n, int max_iter, unsigned hist_mask,
                    int path, double* x_host, double* hist_host, cgx_info* info);
+
+/* ---- row-partitioned multi-GPU runs (one rank per GPU).  The
+ *      reference's distributed solvers (scaling_experiments_mpi4py/cg_variants/*.py,
+ *      `f(comm, A, b, max_iter)`) partition the unknowns over MPI ranks and Allreduce every
+ *      iteration; here rank `rank` of `world` owns the z-slab of nz_local planes of the
+ *      nx x ny x (sum of nz_local) Dirichlet 7-point grid (2-D grids: ny = 1, planes = grid
+ *      rows), neighbours exchange one boundary plane per SpMV input by peer-to-peer stores
+ *      over NVLink, and the <= 4 fused scalars per iteration are summed in rank order on
+ *      every GPU (bit-identical everywhere).
+ *      Set-up order on each rank: cgx_set_stencil_slab -> exchange the 64-byte window
+ *      handles (cgx_dist_ipc_handle / cgx_dist_attach_ipc between processes, or
+ *      cgx_dist_attach_ctx inside one process) -> cgx_dist_commit -> a barrier of the
+ *      caller's -> cgx_set_jacobi_host / cgx_load_problem_* with the LOCAL slices ->
+ *      cgx_run / cgx_begin / cgx_advance as on one GPU (collective: every rank calls them
+ *      with the same arguments).  Histories are the global ones on every rank. */
+int cgx_set_stencil_slab(cgx_ctx* ctx, int64_t nx, int64_t ny, int64_t nz_local, int world,
+                         int rank, double diag, double off);
+int cgx_dist_ipc_handle(cgx_ctx* ctx, void* handle64);
+int cgx_dist_attach_ipc(cgx_ctx* ctx, int peer_rank, const void* handle64);
+int cgx_dist_attach_ctx(cgx_ctx* ctx, int peer_rank, cgx_ctx* peer);
+/* scalar exchange mode: 1 = one-hop peer-to-peer flag exchange fused into the producing
+ * kernel; 2 = ncclAllReduce (the comm.Allreduce of e.g. mpi4py pr_cg.py:61-69) on a side
+ * stream, overlapped with the SpMV for the pipelined variants (pipeprcg.c:154-173).
+ * Mode 2 needs the path of libnccl.so.2 and the 128-byte id from cgx_dist_nccl_unique_id
+ * (made on rank 0, broadcast by the caller). */
+int cgx_dist_nccl_unique_id(const char* nccl_libpath, void* id128);
+int cgx_dist_commit(cgx_ctx* ctx, int mode, const char* nccl_libpath, const void* nccl_id128);
+/* The same partition driven from ONE host thread: ctxs[r] is rank r (all on one GPU --
+ * the ranks then share a stream and run interleaved, which is how the protocol is tested
+ * on a single GPU -- or one context per GPU).  b/x0/x_true are the GLOBAL vectors. */
+int cgx_group_load_problem_host(cgx_ctx** ctxs, int count, const double* b_host,
+                                const double* x0_host, const double* x_true_host,
+                                int64_t n_total);
+int cgx_group_begin(cgx_ctx** ctxs, int count, int variant, int max_iter, unsigned hist_mask);
+int cgx_group_advance(cgx_ctx** ctxs, int count, int niter);
 
 /* ---- single primitives, exposed for the unit tests of SURVEY.md section 7:
  *      y = A v (scipy `A @ v`) and the deterministic fp64 dot (numpy `u @ v`). */

@@ -168,7 +168,7 @@ def _solve_stepwise(sess, tag, A, b, x0, max_iter, x_true, dev_hist, generic, ou
     reference's keyword set (hs_cg.py:97-98,128-129).  Slow (a device round trip per
     iteration) but still no CPU arithmetic on the solve itself."""
     sess.load_problem(b, x0, x_true)
-    sess.begin(tag, max_iter, histories=tuple(dev_hist), path="stream")
+    sess.begin(tag, max_iter, histories=tuple(dev_hist), path=path)
     predicted = tag in ("pr", "m") or tag.startswith("pipe")
     b_arr = np.asarray(b, dtype=np.float64)
     a_k1 = a_k2 = 0.0

@@ -2,17 +2,21 @@
 // loop and the C ABI of include/cgx.h.  No torch, no cuBLAS/cuSPARSE, no CPU fallback.
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
 #include "../../include/cgx.h"
 #include "cgx_kernels.cuh"
 #include "cgx_stencil_tma.cuh"
+#include "cgx_persistent.cuh"
 
 using namespace cgx;
 
@@ -58,6 +62,35 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 // ---------------------------------------------------------------------------------------
+// NCCL (mode 2 of the scalar exchange) -- resolved with dlopen from the library the caller
+// names (torch's bundled libnccl.so.2); the .so itself does not link NCCL.
+// ---------------------------------------------------------------------------------------
+struct Nid { char b[128]; };        // ncclUniqueId (passed by value)
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Nid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load(const char* path) {
+  if (g_nccl.h) return CGX_OK;
+  void* h = dlopen(path && *path ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(CGX_ERR_UNSUPPORTED, "cannot load NCCL (%s): %s", path ? path : "libnccl.so.2", dlerror());
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    return fail(CGX_ERR_UNSUPPORTED, "NCCL symbols missing in %s", path ? path : "libnccl.so.2");
+  g_nccl.h = h;
+  return CGX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------
 enum { V_X = 0, V_R, V_RT, V_P, V_S, V_ST, V_W, V_WT, V_U, V_T, V_COUNT };
@@ -75,6 +108,8 @@ struct cgx_ctx {
   int* d_ptr = nullptr;
   int* d_idx = nullptr;
   double* d_val = nullptr;
+  int* d_rowblk = nullptr;         // CSR-stream row blocks (cgx_kernels.cuh)
+  int n_rowblk = 0;
   i64 n = 0, nnz = 0;
   // preconditioner: pm = 0 identity, 1 Jacobi vector, 2 Jacobi with a constant diagonal
   double* d_dinv = nullptr;
@@ -83,6 +118,7 @@ struct cgx_ctx {
   // TMA-staged stencil path
   bool use_tma = false;
   bool no_tma = false;             // cgx_set_option("tma", 0): force the generic stencil kernel
+  bool no_csr_stream = false;      // cgx_set_option("csr_stream", 0): one thread per row
   TmaGeom geom{};
   int tma_grid[2] = {0, 0};        // grid size for 1 / 2 right-hand sides
   CUtensorMap tmap[10];
@@ -94,7 +130,7 @@ struct cgx_ctx {
   bool own_problem = false, has_xtrue = false, problem_loaded = false;
   // state
   double* vec[V_COUNT] = {};
-  Scal* d_sc = nullptr;
+  Scal* d_sc = nullptr;            // [2]: multi-GPU runs alternate (Args::scpar)
   double* d_partials = nullptr;
   unsigned* d_ticket = nullptr;
   double* d_hist = nullptr;
@@ -109,6 +145,30 @@ struct cgx_ctx {
   size_t prof_used = 0;
   double prof_ms[16] = {};
   i64 prof_n[16] = {};
+  // multi-GPU (dist.world > 1): window, peers, epochs (cgx_common.cuh "Row-partitioned ...")
+  Dist dist{};
+  unsigned char* d_win = nullptr;
+  size_t win_bytes = 0;
+  unsigned char* peer_base[kMaxWorld] = {};
+  bool peer_ipc[kMaxWorld] = {};
+  bool dist_ready = false;
+  cudaStream_t own_stream = nullptr;      // c->stream may be a group's shared stream
+  u64 epoch = 0;                           // last scalar-exchange epoch produced
+  u64 hepoch[kChan] = {};                  // last halo epoch produced per channel
+  int scpar = 0;
+  struct Pend { u64 e; int kind; int k; };
+  std::vector<Pend> pend;
+  CUtensorMap gmap[kChan];
+  bool gmap_ok[kChan] = {};
+  // mode 2: NCCL allreduce of the records on a side stream
+  void* nccl_comm = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_prod[kSlots] = {}, ev_red[kSlots] = {};
+  double* d_nccl = nullptr;                // [2][kSlots][kSumW]: in, out
+  // persistent path
+  double* d_ppart = nullptr;               // [2][grid][kPersRed]
+  u64* d_pbar = nullptr;                   // [0] grid barrier counter, [1] error flag
+  int pers_threshold = 1 << 19;            // AUTO: rows below which the persistent kernel runs
   // current run
   int variant = 0, max_iter = 0, cur_k = 0, path = CGX_PATH_STREAM;
   i64 launches_run = 0;
@@ -125,8 +185,9 @@ static int grid_for(const cgx_ctx* c, i64 work_items) {
 }
 
 static void free_op(cgx_ctx* c) {
-  cudaFree(c->d_ptr); cudaFree(c->d_idx); cudaFree(c->d_val);
-  c->d_ptr = c->d_idx = nullptr; c->d_val = nullptr;
+  cudaFree(c->d_ptr); cudaFree(c->d_idx); cudaFree(c->d_val); cudaFree(c->d_rowblk);
+  c->d_ptr = c->d_idx = c->d_rowblk = nullptr; c->d_val = nullptr;
+  c->n_rowblk = 0;
   c->op_kind = 0;
 }
 static void free_problem(cgx_ctx* c) {
@@ -142,7 +203,7 @@ static void free_state(cgx_ctx* c) {
 static void reset_size(cgx_ctx* c, i64 n) {
   if (c->n != n) {
     free_state(c); free_problem(c);
-    cudaFree(c->d_dinv); c->d_dinv = nullptr;
+    cudaFree(c->d_dinv); c->d_dinv = nullptr; c->pm = 0; c->dinv_s = 1.0;
     c->n = n;
   }
 }
@@ -169,26 +230,50 @@ extern "C" int cgx_ctx_create(int device, cgx_ctx** out) {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
-  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
   for (auto& e : c->ev) CU(cudaEventCreate(&e));
-  CU(cudaMalloc(&c->d_sc, sizeof(Scal)));
-  CU(cudaMemset(c->d_sc, 0, sizeof(Scal)));
+  CU(cudaMalloc(&c->d_sc, 2 * sizeof(Scal)));
+  CU(cudaMemset(c->d_sc, 0, 2 * sizeof(Scal)));
   CU(cudaMalloc(&c->d_partials, sizeof(double) * kMaxGrid * kNRed));
   CU(cudaMalloc(&c->d_ticket, sizeof(unsigned)));
   CU(cudaMemset(c->d_ticket, 0, sizeof(unsigned)));
+  CU(cudaMalloc(&c->d_ppart, sizeof(double) * 2 * kPersMaxGrid * kPersRed));
+  CU(cudaMalloc(&c->d_pbar, sizeof(u64) * 2));
+  CU(cudaMemset(c->d_pbar, 0, sizeof(u64) * 2));
+  c->dist.world = 1;
   *out = c;
   return CGX_OK;
+}
+
+static void dist_release(cgx_ctx* c) {
+  if (c->nccl_comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(c->nccl_comm); c->nccl_comm = nullptr; }
+  for (int r = 0; r < kMaxWorld; ++r) {
+    if (c->peer_ipc[r] && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+    c->peer_base[r] = nullptr; c->peer_ipc[r] = false;
+  }
+  cudaFree(c->d_win); c->d_win = nullptr; c->win_bytes = 0;
+  cudaFree(c->d_nccl); c->d_nccl = nullptr;
+  if (c->comm_stream) { cudaStreamDestroy(c->comm_stream); c->comm_stream = nullptr; }
+  for (int s = 0; s < kSlots; ++s) {
+    if (c->ev_prod[s]) { cudaEventDestroy(c->ev_prod[s]); c->ev_prod[s] = nullptr; }
+    if (c->ev_red[s]) { cudaEventDestroy(c->ev_red[s]); c->ev_red[s] = nullptr; }
+  }
+  c->dist = Dist{}; c->dist.world = 1;
+  c->dist_ready = false;
 }
 
 extern "C" int cgx_ctx_destroy(cgx_ctx* c) {
   if (!c) return CGX_OK;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->own_stream);
+  dist_release(c);
   free_state(c); free_problem(c); free_op(c);
   cudaFree(c->d_dinv); cudaFree(c->d_sc); cudaFree(c->d_partials); cudaFree(c->d_ticket);
+  cudaFree(c->d_ppart); cudaFree(c->d_pbar);
   for (auto& e : c->ev) cudaEventDestroy(e);
   for (auto& e : c->prof_events) cudaEventDestroy(e);
-  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->own_stream);
   delete c;
   return CGX_OK;
 }
@@ -196,6 +281,20 @@ extern "C" int cgx_ctx_destroy(cgx_ctx* c) {
 // ---------------------------------------------------------------------------------------
 // operator / preconditioner / problem
 // ---------------------------------------------------------------------------------------
+// CSR-stream row blocks: consecutive rows, at most kBlock of them and kCsrCap non-zeros
+// (a single longer row is a block of its own).
+static void build_row_blocks(const int32_t* ptr, i64 n, std::vector<int>& blk) {
+  blk.clear();
+  blk.push_back(0);
+  i64 r = 0;
+  while (r < n) {
+    i64 e = r + 1;
+    while (e < n && e - r < kBlock && (i64)ptr[e + 1] - ptr[r] <= kCsrCap) ++e;
+    blk.push_back((int)e);
+    r = e;
+  }
+}
+
 extern "C" int cgx_set_csr_host(cgx_ctx* c, int64_t n, int64_t nnz, const int32_t* indptr,
                                 const int32_t* indices, const double* data) {
   if (!c || n <= 0 || nnz < 0 || !indptr || (nnz > 0 && (!indices || !data)))
@@ -204,38 +303,53 @@ extern "C" int cgx_set_csr_host(cgx_ctx* c, int64_t n, int64_t nnz, const int32_
     return fail(CGX_ERR_UNSUPPORTED, "cgx_set_csr_host: int32 index range exceeded");
   if (indptr[0] != 0 || indptr[n] != nnz)
     return fail(CGX_ERR_ARG, "cgx_set_csr_host: indptr[0] != 0 or indptr[n] != nnz");
+  if (c->dist.world > 1)
+    return fail(CGX_ERR_UNSUPPORTED, "cgx_set_csr_host: row-partitioned runs take the stencil operator "
+                "(cgx_set_stencil_slab); CSR matrices are single-GPU");
   CU(cudaSetDevice(c->device));
   free_op(c);
   reset_size(c, n);
   c->nnz = nnz;
+  std::vector<int> blk;
+  build_row_blocks(indptr, n, blk);
   CU(cudaMalloc(&c->d_ptr, sizeof(int) * (n + 1)));
   CU(cudaMalloc(&c->d_idx, sizeof(int) * std::max<i64>(nnz, 1)));
   CU(cudaMalloc(&c->d_val, sizeof(double) * std::max<i64>(nnz, 1)));
+  CU(cudaMalloc(&c->d_rowblk, sizeof(int) * blk.size()));
   CU(cudaMemcpyAsync(c->d_ptr, indptr, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_rowblk, blk.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice, c->stream));
   if (nnz) {
     CU(cudaMemcpyAsync(c->d_idx, indices, sizeof(int) * nnz, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_val, data, sizeof(double) * nnz, cudaMemcpyHostToDevice, c->stream));
   }
   CU(cudaStreamSynchronize(c->stream));
+  c->n_rowblk = (int)blk.size() - 1;
   c->csr = CsrOp{c->d_ptr, c->d_idx, c->d_val, n};
   c->op_kind = 1;
   return CGX_OK;
 }
 
-extern "C" int cgx_set_stencil(cgx_ctx* c, int dim, int64_t nx, int64_t ny, int64_t nz,
-                               double diag, double off) {
+static int set_stencil(cgx_ctx* c, int dim, i64 nx, i64 ny, i64 nz, double diag, double off, int has_lo,
+                       int has_hi) {
   if (!c || (dim != 2 && dim != 3) || nx < 1 || ny < 1 || nz < 1 || (dim == 2 && nz != 1))
     return fail(CGX_ERR_ARG, "cgx_set_stencil: bad arguments");
   const i64 n = nx * ny * nz;
-  if (n + nx * ny >= (1ll << 31))
+  if (n + 2 * nx * ny >= (1ll << 31))
     return fail(CGX_ERR_UNSUPPORTED, "cgx_set_stencil: grid too large for int32 indexing");
   CU(cudaSetDevice(c->device));
   free_op(c);
   reset_size(c, n);
-  c->sten = StencilOp{(int)nx, (int)ny, (int)nz, diag, off, n};
+  c->sten = StencilOp{(int)nx, (int)ny, (int)nz, diag, off, n, has_lo, has_hi};
   c->nnz = 0;
   c->op_kind = 2;
   return CGX_OK;
+}
+
+extern "C" int cgx_set_stencil(cgx_ctx* c, int dim, int64_t nx, int64_t ny, int64_t nz,
+                               double diag, double off) {
+  if (c && c->dist.world > 1)
+    return fail(CGX_ERR_ARG, "cgx_set_stencil: this context is a rank of a partitioned run; use cgx_set_stencil_slab");
+  return set_stencil(c, dim, nx, ny, nz, diag, off, 0, 0);
 }
 
 extern "C" int cgx_set_jacobi_host(cgx_ctx* c, const double* dinv, int64_t n) {
@@ -256,42 +370,8 @@ extern "C" int cgx_set_jacobi_host(cgx_ctx* c, const double* dinv, int64_t n) {
   return CGX_OK;
 }
 
-static int load_problem(cgx_ctx* c, const double* b, const double* x0, const double* xt, i64 n,
-                        cudaMemcpyKind kind) {
-  if (!c || !b || !x0) return fail(CGX_ERR_ARG, "cgx_load_problem: b and x0 are required");
-  if (c->op_kind == 0 || n != c->n)
-    return fail(CGX_ERR_ARG, "cgx_load_problem: set the operator first; n must match (%lld vs %lld)",
-                (long long)n, (long long)c->n);
-  CU(cudaSetDevice(c->device));
-  if (!c->own_problem) {
-    c->d_b = c->d_x0 = c->d_xtrue = nullptr;
-    CU(cudaMalloc(&c->d_b, sizeof(double) * n));
-    CU(cudaMalloc(&c->d_x0, sizeof(double) * n));
-    CU(cudaMalloc(&c->d_xtrue, sizeof(double) * n));
-    c->own_problem = true;
-  }
-  CU(cudaMemcpyAsync(c->d_b, b, sizeof(double) * n, kind, c->stream));
-  CU(cudaMemcpyAsync(c->d_x0, x0, sizeof(double) * n, kind, c->stream));
-  if (xt) CU(cudaMemcpyAsync(c->d_xtrue, xt, sizeof(double) * n, kind, c->stream));
-  c->has_xtrue = xt != nullptr;
-  c->problem_loaded = true;
-  return CGX_OK;
-}
-
-extern "C" int cgx_load_problem_host(cgx_ctx* c, const double* b, const double* x0,
-                                     const double* xt, int64_t n) {
-  int rc = load_problem(c, b, x0, xt, n, cudaMemcpyHostToDevice);
-  if (rc) return rc;
-  CU(cudaStreamSynchronize(c->stream));   // pageable host buffers may be reused by the caller
-  return CGX_OK;
-}
-extern "C" int cgx_load_problem_dev(cgx_ctx* c, const double* b, const double* x0,
-                                    const double* xt, int64_t n) {
-  return load_problem(c, b, x0, xt, n, cudaMemcpyDeviceToDevice);
-}
-
 // ---------------------------------------------------------------------------------------
-// launch helpers
+// launch bookkeeping
 // ---------------------------------------------------------------------------------------
 // Optional per-kernel-class timing (cgx_set_profile): an event pair around every launch of
 // the iteration loop, resolved after the stream has drained.  Off in timed runs.
@@ -324,58 +404,176 @@ static void prof_resolve(cgx_ctx* c) {
   c->prof_cls.clear(); c->prof_used = 0;
 }
 
-// which state vector a fused SpMV pass reads through TMA (second one for the 2-RHS pass)
+static Args make_args(cgx_ctx* c) {
+  Args g{};
+  g.x = c->vec[V_X]; g.r = c->vec[V_R]; g.rt = c->vec[V_RT]; g.p = c->vec[V_P];
+  g.s = c->vec[V_S]; g.st = c->vec[V_ST]; g.w = c->vec[V_W]; g.wt = c->vec[V_WT];
+  g.u = c->vec[V_U]; g.t = c->vec[V_T];
+  g.dinv = c->d_dinv; g.dinv_s = c->dinv_s; g.b = c->d_b; g.xtrue = c->d_xtrue;
+  g.sc = c->d_sc; g.partials = c->d_partials; g.ticket = c->d_ticket;
+  g.hist = c->d_hist; g.hist_len = c->hist_len; g.hist_mask = c->hist_mask;
+  g.n = c->n; g.k = c->cur_k;
+  g.d = c->dist;
+  return g;
+}
+
+// What one launch does in the multi-GPU protocol (cgx_common.cuh "Row-partitioned ..."):
+struct Plan {
+  bool consume = false;      // needs alpha/beta: folds every pending reduction into the scalars
+  int produce = FK_NONE;     // publishes a reduction record of this kind (FK_*; -1: instrumentation)
+  int hout_n = 0, hout_ch = 0;   // writes boundary planes of `hout_n` SpMV inputs into the neighbours
+  int hin_n = 0, hin_ch = 0;     // reads ghost planes
+};
+enum { FK_INSTR = 100 };
+
+// before the launch: fill the per-launch fields of g; mode 2: make the stream wait for the
+// NCCL reductions this kernel folds
+static void plan_apply(cgx_ctx* c, Args& g, const Plan& p) {
+  if (c->dist.world <= 1) return;
+  g.d = c->dist;
+  g.scpar = c->scpar;
+  g.npend = 0;
+  if (p.consume) {
+    g.npend = (int)c->pend.size();
+    for (int q = 0; q < g.npend; ++q) {
+      g.pend_kind[q] = c->pend[q].kind; g.pend_k[q] = c->pend[q].k; g.pend_e[q] = c->pend[q].e;
+      if (c->dist.mode == 2) cudaStreamWaitEvent(c->stream, c->ev_red[c->pend[q].e % kSlots], 0);
+    }
+  }
+  if (p.produce != FK_NONE) g.sepoch = c->epoch + 1;
+  g.hout_n = p.hout_n; g.hout_ch = p.hout_ch;
+  if (p.hout_n) {
+    g.hout_epoch = c->hepoch[p.hout_ch] + 1;
+    g.hout_par = (int)(g.hout_epoch & 1);
+  }
+  g.hin_ch = p.hin_ch;
+  if (p.hin_n) {
+    g.hin_epoch = c->hepoch[p.hin_ch];
+    g.hin_par = (int)(g.hin_epoch & 1);
+  }
+  g.xt_epoch = c->hepoch[3];
+  g.xt_par = (int)(g.xt_epoch & 1);
+}
+// after the launch: advance the epochs; mode 2: enqueue the allreduce of the new record
+static void plan_commit(cgx_ctx* c, const Args& g, const Plan& p) {
+  if (c->dist.world <= 1) return;
+  if (p.consume && !c->pend.empty()) { c->scpar ^= 1; c->pend.clear(); }
+  if (p.produce != FK_NONE) {
+    c->epoch++;
+    if (p.produce != FK_INSTR) c->pend.push_back({c->epoch, p.produce, g.k});
+    if (c->dist.mode == 2) {
+      const int slot = (int)(c->epoch % kSlots);
+      cudaEventRecord(c->ev_prod[slot], c->stream);
+      cudaStreamWaitEvent(c->comm_stream, c->ev_prod[slot], 0);
+      g_nccl.AllReduce(c->dist.nccl_in + (size_t)slot * kSumW, c->dist.nccl_out + (size_t)slot * kSumW, kSumW,
+                       /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl_comm, c->comm_stream);
+      cudaEventRecord(c->ev_red[slot], c->comm_stream);
+    }
+  }
+  for (int i = 0; i < p.hout_n; ++i) c->hepoch[p.hout_ch + i]++;
+}
+
+static VecIn vec_in(cgx_ctx* c, const double* v, int ch, const Args& g) {
+  VecIn a{v, nullptr, nullptr};
+  if (c->dist.world > 1 && c->dist.ghost) {
+    a.lo = c->dist.ghost + ghost_off(c->dist, ch, g.hin_par, 0);
+    a.hi = c->dist.ghost + ghost_off(c->dist, ch, g.hin_par, 1);
+  }
+  return a;
+}
+
+// which state vector a fused SpMV pass reads (second one for the 2-RHS pass)
 template <int MODE> struct SpInput { static constexpr int v0 = -1, v1 = -1; };
-template <> struct SpInput<SP_HS> { static constexpr int v0 = 3 /*V_P*/, v1 = -1; };
-template <> struct SpInput<SP_PR> { static constexpr int v0 = 3 /*V_P*/, v1 = -1; };
-template <> struct SpInput<SP_CG> { static constexpr int v0 = 2 /*V_RT*/, v1 = -1; };
-template <> struct SpInput<SP_GV> { static constexpr int v0 = 7 /*V_WT*/, v1 = -1; };
-template <> struct SpInput<SP_PIPE_R> { static constexpr int v0 = 5 /*V_ST*/, v1 = 2 /*V_RT*/; };
-template <> struct SpInput<SP_PIPE_N> { static constexpr int v0 = 5 /*V_ST*/, v1 = -1; };
+template <> struct SpInput<SP_HS> { static constexpr int v0 = V_P, v1 = -1; };
+template <> struct SpInput<SP_PR> { static constexpr int v0 = V_P, v1 = -1; };
+template <> struct SpInput<SP_CG> { static constexpr int v0 = V_RT, v1 = -1; };
+template <> struct SpInput<SP_GV> { static constexpr int v0 = V_WT, v1 = -1; };
+template <> struct SpInput<SP_PIPE_R> { static constexpr int v0 = V_ST, v1 = V_RT; };
+template <> struct SpInput<SP_PIPE_N> { static constexpr int v0 = V_ST, v1 = -1; };
 
 static size_t tma_smem_bytes(int nv) { return (size_t)kRing * nv * kPlaneStride * sizeof(double) + 128; }
 
+// Fused SpMV pass of stage MODE (vin/vout only for SP_PLAIN / SP_RESID).
 template <int MODE, int PM, bool MEUR>
-static void launch_spmv(cgx_ctx* c, const Args& g, const double* vin, double* vout) {
-  ProfScope ps(c, PC_SP0 + MODE);
+static void launch_spmv(cgx_ctx* c, Args g, const double* vin, double* vout) {
   constexpr int v0 = SpInput<MODE>::v0, v1 = SpInput<MODE>::v1;
-  if constexpr (v0 >= 0) {
-    if (c->op_kind == 2 && c->use_tma && c->tmap_ok[v0] && (v1 < 0 || c->tmap_ok[v1 < 0 ? 0 : v1])) {
-      constexpr int nv = (v1 >= 0) ? 2 : 1;
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaFuncSetAttribute(stencil_tma_kernel<MODE, PM, MEUR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)tma_smem_bytes(nv));
-        attr_set = true;
+  constexpr int nv = (v1 >= 0) ? 2 : 1;
+  Plan p;
+  p.produce = SpTraits<MODE>::FK;
+  p.hin_n = nv; p.hin_ch = 0;
+  plan_apply(c, g, p);
+  {
+    ProfScope ps(c, PC_SP0 + MODE);
+    bool done = false;
+    if constexpr (v0 >= 0) {
+      const bool ghosts_ok = c->dist.world <= 1 || (c->gmap_ok[0] && (nv == 1 || c->gmap_ok[1]));
+      if (c->op_kind == 2 && c->use_tma && c->tmap_ok[v0] && (v1 < 0 || c->tmap_ok[v1 < 0 ? 0 : v1]) && ghosts_ok) {
+        static bool attr_set = false;
+        if (!attr_set) {
+          cudaFuncSetAttribute(stencil_tma_kernel<MODE, PM, MEUR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)tma_smem_bytes(nv));
+          attr_set = true;
+        }
+        stencil_tma_kernel<MODE, PM, MEUR><<<c->tma_grid[nv - 1], kTmaThreads, tma_smem_bytes(nv), c->stream>>>(
+            c->tmap[v0], c->tmap[v1 < 0 ? v0 : v1], c->gmap[0], c->gmap[nv - 1], c->geom, g);
+        done = true;
       }
-      stencil_tma_kernel<MODE, PM, MEUR><<<c->tma_grid[nv - 1], kTmaThreads, tma_smem_bytes(nv), c->stream>>>(
-          c->tmap[v0], c->tmap[v1 < 0 ? v0 : v1], c->geom, g);
-      c->launches++;
-      return;
     }
+    if (!done) {
+      const double* a0 = v0 >= 0 ? c->vec[v0 < 0 ? 0 : v0] : vin;
+      const double* a1 = v1 >= 0 ? c->vec[v1 < 0 ? 0 : v1] : nullptr;
+      const VecIn in0 = vec_in(c, a0, 0, g), in1 = vec_in(c, a1, 1, g);
+      if (c->op_kind == 1) {
+        if (!c->no_csr_stream) {
+          const int grid = std::max(1, std::min(c->n_rowblk, c->sm_count * 8));
+          csr_stream_kernel<MODE, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(c->csr, c->d_rowblk, c->n_rowblk, g,
+                                                                           in0, in1, vout);
+        } else {
+          spmv_kernel<CsrOp, MODE, PM, MEUR><<<grid_for(c, c->n), kBlock, 0, c->stream>>>(c->csr, g, in0, in1, vout);
+        }
+      } else {
+        spmv_kernel<StencilOp, MODE, PM, MEUR><<<grid_for(c, c->n), kBlock, 0, c->stream>>>(c->sten, g, in0, in1, vout);
+      }
+    }
+    c->launches++;
   }
-  const int grid = grid_for(c, c->n);
-  if (c->op_kind == 1)
-    spmv_kernel<CsrOp, MODE, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(c->csr, g, vin, vout);
-  else
-    spmv_kernel<StencilOp, MODE, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(c->sten, g, vin, vout);
-  c->launches++;
+  plan_commit(c, g, p);
 }
+
 template <int KID, int PM, bool MEUR>
-static void launch_ew(cgx_ctx* c, const Args& g) {
-  const int grid = grid_for(c, (c->n + 1) / 2);
-  ProfScope ps(c, PC_EW0 + KID);
-  ew_kernel<KID, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(g);
+static void launch_ew(cgx_ctx* c, Args g) {
+  Plan p;
+  p.consume = true;
+  p.produce = EwKind<KID>::FK;
+  p.hout_ch = 0;
+  p.hout_n = (KID == EW_HS1) ? 0 : (KID == EW_PIPE_R ? 2 : 1);
+  plan_apply(c, g, p);
+  {
+    const int grid = grid_for(c, (c->n + 1) / 2);
+    ProfScope ps(c, PC_EW0 + KID);
+    ew_kernel<KID, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(g);
+    c->launches++;
+  }
+  plan_commit(c, g, p);
+}
+
+// multi-GPU: push the boundary planes of v into the neighbours' ghost planes of channel ch
+static void launch_halo_push(cgx_ctx* c, Args g, const double* v, int ch) {
+  if (c->dist.world <= 1) return;
+  Plan p;
+  p.hout_n = 1; p.hout_ch = ch;
+  plan_apply(c, g, p);
+  halo_push_kernel<<<grid_for(c, c->dist.plane), kBlock, 0, c->stream>>>(g, v);
   c->launches++;
+  plan_commit(c, g, p);
 }
 
 // ---- TMA stencil path: descriptors and work decomposition -------------------------------
-static bool tma_encode(cgx_ctx* c, double* ptr, CUtensorMap* out) {
+static bool tma_encode_dims(double* ptr, i64 nx, i64 ny, i64 nz, CUtensorMap* out) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc || !ptr) return false;
-  const StencilOp& S = c->sten;
-  cuuint64_t gdim[3] = {(cuuint64_t)S.nx, (cuuint64_t)S.ny, (cuuint64_t)S.nz};
-  cuuint64_t gstr[2] = {(cuuint64_t)S.nx * 8, (cuuint64_t)S.nx * S.ny * 8};
+  cuuint64_t gdim[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
+  cuuint64_t gstr[2] = {(cuuint64_t)nx * 8, (cuuint64_t)nx * ny * 8};
   cuuint32_t box[3] = {(cuuint32_t)kPX, (cuuint32_t)kPY, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ptr, gdim, gstr, box, estr,
@@ -387,11 +585,12 @@ static bool tma_prepare_geom(cgx_ctx* c) {
   if (c->op_kind != 2 || c->no_tma) return false;
   const StencilOp& S = c->sten;
   if (S.nx % 2 != 0 || S.nx < 2) return false;         // TMA needs 16-byte global strides
+  if (S.ny < 4 && S.nz > 1) return false;              // 2-D grid viewed as nx x 1 x ny slabs: tiles would idle
   if (!get_encode_tiled()) return false;
   TmaGeom& G = c->geom;
   G.nx = S.nx; G.ny = S.ny; G.nz = S.nz;
   G.ntx = (S.nx + kTX - 1) / kTX; G.nty = (S.ny + kTY - 1) / kTY;
-  G.zoff = 0; G.has_zlo = 0; G.has_zhi = 0;
+  G.has_zlo = S.has_zlo; G.has_zhi = S.has_zhi;
   G.diag = S.diag; G.off = S.off;
   // resident CTAs: shared memory bound (227 KB/SM), 8 x 256 threads at most
   const int cols = G.ntx * G.nty;
@@ -411,27 +610,56 @@ static bool tma_prepare_geom(cgx_ctx* c) {
 static int setup_tma(cgx_ctx* c, unsigned need) {
   c->use_tma = false;
   for (auto& ok : c->tmap_ok) ok = false;
+  for (auto& ok : c->gmap_ok) ok = false;
   if (!tma_prepare_geom(c)) return CGX_OK;
+  const StencilOp& S = c->sten;
   for (int i = 0; i < V_COUNT; ++i)
-    if ((need & (1u << i)) && c->vec[i]) c->tmap_ok[i] = tma_encode(c, c->vec[i], &c->tmap[i]);
+    if ((need & (1u << i)) && c->vec[i]) c->tmap_ok[i] = tma_encode_dims(c->vec[i], S.nx, S.ny, S.nz, &c->tmap[i]);
+  if (c->dist.world > 1 && c->dist.ghost)
+    for (int ch = 0; ch < 2; ++ch)       // ghost planes of channel ch: z = parity*2 + side
+      c->gmap_ok[ch] = tma_encode_dims(c->dist.ghost + ghost_off(c->dist, ch, 0, 0), S.nx, S.ny, 4, &c->gmap[ch]);
+  else
+    for (int ch = 0; ch < 2; ++ch) { c->gmap[ch] = c->tmap[V_X]; }   // never dereferenced
   c->use_tma = true;
   return CGX_OK;
 }
 
-static void launch_instrument(cgx_ctx* c, const Args& g) {
+static void launch_instrument(cgx_ctx* c, Args g) {
   const int grid = grid_for(c, c->n);
-  ProfScope ps(c, PC_INSTR);
-  if (c->op_kind == 1) {
-    if (c->has_xtrue) instrument_kernel<CsrOp, true><<<grid, kBlock, 0, c->stream>>>(c->csr, g);
-    else instrument_kernel<CsrOp, false><<<grid, kBlock, 0, c->stream>>>(c->csr, g);
-  } else {
-    if (c->has_xtrue) instrument_kernel<StencilOp, true><<<grid, kBlock, 0, c->stream>>>(c->sten, g);
-    else instrument_kernel<StencilOp, false><<<grid, kBlock, 0, c->stream>>>(c->sten, g);
+  Plan p;
+  p.produce = FK_INSTR;
+  p.hin_n = 1; p.hin_ch = 2;
+  plan_apply(c, g, p);
+  {
+    ProfScope ps(c, PC_INSTR);
+    const VecIn xin = vec_in(c, c->vec[V_X], 2, g);
+    VecIn xtin{c->d_xtrue, nullptr, nullptr};
+    if (c->dist.world > 1 && c->dist.ghost) {
+      xtin.lo = c->dist.ghost + ghost_off(c->dist, 3, g.xt_par, 0);
+      xtin.hi = c->dist.ghost + ghost_off(c->dist, 3, g.xt_par, 1);
+    }
+    if (c->op_kind == 1) {
+      if (c->has_xtrue) instrument_kernel<CsrOp, true><<<grid, kBlock, 0, c->stream>>>(c->csr, g, xin, xtin);
+      else instrument_kernel<CsrOp, false><<<grid, kBlock, 0, c->stream>>>(c->csr, g, xin, xtin);
+    } else {
+      if (c->has_xtrue) instrument_kernel<StencilOp, true><<<grid, kBlock, 0, c->stream>>>(c->sten, g, xin, xtin);
+      else instrument_kernel<StencilOp, false><<<grid, kBlock, 0, c->stream>>>(c->sten, g, xin, xtin);
+    }
+    c->launches++;
   }
+  plan_commit(c, g, p);
+}
+// multi-GPU: the history entry of the instrumentation record just produced
+static void launch_hist_consume(cgx_ctx* c, Args g) {
+  if (c->dist.world <= 1) return;
+  g.d = c->dist;
+  g.pend_e[0] = c->epoch;
+  if (c->dist.mode == 2) cudaStreamWaitEvent(c->stream, c->ev_red[c->epoch % kSlots], 0);
+  hist_consume_kernel<<<1, 32, 0, c->stream>>>(g);
   c->launches++;
 }
 static void launch_dot(cgx_ctx* c, const double* u, const double* v, const double* dinv, int slot) {
-  dot_kernel<<<grid_for(c, c->n), kBlock, 0, c->stream>>>(u, v, dinv, c->n, c->d_sc, slot,
+  dot_kernel<<<grid_for(c, c->n), kBlock, 0, c->stream>>>(u, v, dinv, c->n, c->d_sc + c->scpar, slot,
                                                           c->d_partials, c->d_ticket);
   c->launches++;
 }
@@ -462,112 +690,265 @@ static VariantInfo variant_info(int v, bool prec) {
   return {false, false, false, -1, 0};
 }
 
-// one iteration of the streaming path --------------------------------------------------
-template <int PREC>
-static void iterate_stream(cgx_ctx* c, int variant, const VariantInfo& vi, Args& g) {
-  switch (variant) {
-    case CGX_HS:
-      launch_ew<EW_HS1, PREC, false>(c, g);
-      launch_ew<EW_HS2, PREC, false>(c, g);
-      launch_spmv<SP_HS, PREC, false>(c, g, nullptr, nullptr);
-      break;
-    case CGX_CG:
-      launch_ew<EW_CG, PREC, false>(c, g);
-      launch_spmv<SP_CG, PREC, false>(c, g, nullptr, nullptr);
-      break;
-    case CGX_GV:
-      launch_ew<EW_GV, PREC, false>(c, g);
-      launch_spmv<SP_GV, PREC, false>(c, g, nullptr, nullptr);
-      break;
-    case CGX_PR:
-      launch_ew<EW_PR, PREC, false>(c, g);
-      launch_spmv<SP_PR, PREC, false>(c, g, nullptr, nullptr);
-      break;
-    case CGX_M:
-      launch_ew<EW_PR, PREC, true>(c, g);
-      launch_spmv<SP_PR, PREC, true>(c, g, nullptr, nullptr);
-      break;
-    case CGX_PIPE_PR:
-      launch_ew<EW_PIPE_R, PREC, false>(c, g);
-      launch_spmv<SP_PIPE_R, PREC, false>(c, g, nullptr, nullptr);
-      break;
-    case CGX_PIPE_PR_M:
-      launch_ew<EW_PIPE_R, PREC, true>(c, g);
-      launch_spmv<SP_PIPE_R, PREC, true>(c, g, nullptr, nullptr);
-      break;
-    case CGX_PIPE_P:
-      launch_ew<EW_PIPE_N, PREC, false>(c, g);
-      launch_spmv<SP_PIPE_N, PREC, false>(c, g, nullptr, nullptr);
-      break;
-    case CGX_PIPE_P_M:
-      launch_ew<EW_PIPE_N, PREC, true>(c, g);
-      launch_spmv<SP_PIPE_N, PREC, true>(c, g, nullptr, nullptr);
-      break;
-  }
-  (void)vi;
+// ---------------------------------------------------------------------------------------
+// The iteration as a list of stages.  A stage is one kernel launch; stage s of rank A only
+// ever waits for stages < s of other ranks, so a group of ranks may be driven in lockstep
+// from one host thread (cgx_group_*), or every rank from its own process.
+// ---------------------------------------------------------------------------------------
+static int iter_stage_count(const cgx_ctx* c) {
+  int ns = (c->variant == CGX_HS) ? 3 : 2;
+  if (c->hist_mask) ns += (c->dist.world > 1) ? 3 : 1;
+  return ns;
 }
 
-// initial state: hs_cg.py:83-94, cg_cg.py:90-104, gv_cg.py:105-121, pr_cg.py:106-120,
-// pipe_pr_cg.py:122-140.  Built from plain kernels; not part of the timed loop.
-static int init_state(cgx_ctx* c, int variant, const VariantInfo& vi, Args& g) {
+template <int PM>
+static void iter_stage_pm(cgx_ctx* c, int s, const Args& g) {
+  const int core = (c->variant == CGX_HS) ? 3 : 2;
+  if (s >= core) {
+    const int t = s - core;
+    if (c->dist.world > 1) {
+      if (t == 0) launch_halo_push(c, g, c->vec[V_X], 2);
+      else if (t == 1) launch_instrument(c, g);
+      else launch_hist_consume(c, g);
+    } else {
+      launch_instrument(c, g);
+    }
+    return;
+  }
+  switch (c->variant) {
+    case CGX_HS:
+      if (s == 0) launch_ew<EW_HS1, PM, false>(c, g);
+      else if (s == 1) launch_ew<EW_HS2, PM, false>(c, g);
+      else launch_spmv<SP_HS, PM, false>(c, g, nullptr, nullptr);
+      break;
+    case CGX_CG:
+      if (s == 0) launch_ew<EW_CG, PM, false>(c, g); else launch_spmv<SP_CG, PM, false>(c, g, nullptr, nullptr);
+      break;
+    case CGX_GV:
+      if (s == 0) launch_ew<EW_GV, PM, false>(c, g); else launch_spmv<SP_GV, PM, false>(c, g, nullptr, nullptr);
+      break;
+    case CGX_PR:
+      if (s == 0) launch_ew<EW_PR, PM, false>(c, g); else launch_spmv<SP_PR, PM, false>(c, g, nullptr, nullptr);
+      break;
+    case CGX_M:
+      if (s == 0) launch_ew<EW_PR, PM, true>(c, g); else launch_spmv<SP_PR, PM, true>(c, g, nullptr, nullptr);
+      break;
+    case CGX_PIPE_PR:
+      if (s == 0) launch_ew<EW_PIPE_R, PM, false>(c, g); else launch_spmv<SP_PIPE_R, PM, false>(c, g, nullptr, nullptr);
+      break;
+    case CGX_PIPE_PR_M:
+      if (s == 0) launch_ew<EW_PIPE_R, PM, true>(c, g); else launch_spmv<SP_PIPE_R, PM, true>(c, g, nullptr, nullptr);
+      break;
+    case CGX_PIPE_P:
+      if (s == 0) launch_ew<EW_PIPE_N, PM, false>(c, g); else launch_spmv<SP_PIPE_N, PM, false>(c, g, nullptr, nullptr);
+      break;
+    case CGX_PIPE_P_M:
+      if (s == 0) launch_ew<EW_PIPE_N, PM, true>(c, g); else launch_spmv<SP_PIPE_N, PM, true>(c, g, nullptr, nullptr);
+      break;
+  }
+}
+static void iter_stage(cgx_ctx* c, int s, const Args& g) {
+  if (c->pm == 2) iter_stage_pm<2>(c, s, g);
+  else if (c->pm == 1) iter_stage_pm<1>(c, s, g);
+  else iter_stage_pm<0>(c, s, g);
+}
+
+// multi-GPU: fold what is still pending into the persisted scalars (end of an advance)
+static void launch_flush(cgx_ctx* c, Args g, bool meurant) {
+  if (c->dist.world <= 1 || c->pend.empty()) return;
+  Plan p; p.consume = true;
+  plan_apply(c, g, p);
+  g.meur = meurant ? 1 : 0;
+  flush_scalars_kernel<<<1, 32, 0, c->stream>>>(g);
+  c->launches++;
+  plan_commit(c, g, p);
+}
+
+// Initial state: hs_cg.py:83-94, cg_cg.py:90-104, gv_cg.py:105-121, pr_cg.py:106-120,
+// pipe_pr_cg.py:122-140.  Built from plain kernels; not part of the timed loop.  Returned
+// as a list of steps (one launch or copy each) with the same length on every rank.
+typedef std::vector<std::function<void()>> Steps;
+
+static void build_init_steps(cgx_ctx* c, int variant, const VariantInfo& vi, Steps& st) {
   const size_t bytes = sizeof(double) * c->n;
   const double* dinv = c->d_dinv;
   double** v = c->vec;
-  CU(cudaMemcpyAsync(v[V_X], c->d_x0, bytes, cudaMemcpyDeviceToDevice, c->stream));
-  launch_spmv<SP_RESID, 0, false>(c, g, v[V_X], v[V_R]);            // r = b - A x0
-  launch_scale(c, dinv, v[V_R], v[V_RT]);                               // rt = M r
-  CU(cudaMemcpyAsync(v[V_P], v[V_RT], bytes, cudaMemcpyDeviceToDevice, c->stream));  // p = rt
-  launch_dot(c, v[V_R], v[V_RT], nullptr, 0);                           // nu = r.rt
+  const bool dist = c->dist.world > 1;
+  auto copy = [=](double* dst, const double* src) {
+    return [=]() { cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream); };
+  };
+  auto spmv = [=, &st](int mode, const double* in, double* out) {     // y = A in  /  r = b - A in
+    if (dist) st.push_back([=]() { launch_halo_push(c, make_args(c), in, 0); });
+    st.push_back([=]() {
+      Args g = make_args(c);
+      if (mode == SP_RESID) launch_spmv<SP_RESID, 0, false>(c, g, in, out);
+      else launch_spmv<SP_PLAIN, 0, false>(c, g, in, out);
+    });
+  };
+  auto dot = [=, &st](const double* a, const double* b, const double* dv, int slot) {
+    st.push_back([=]() { launch_dot(c, a, b, dv, slot); });
+  };
+  auto scale = [=, &st](const double* in, double* out) { st.push_back([=]() { launch_scale(c, dinv, in, out); }); };
+
+  st.push_back(copy(v[V_X], c->d_x0));
+  spmv(SP_RESID, v[V_X], v[V_R]);                                       // r = b - A x0
+  scale(v[V_R], v[V_RT]);                                               // rt = M r
+  st.push_back(copy(v[V_P], v[V_RT]));                                  // p = rt
+  dot(v[V_R], v[V_RT], nullptr, 0);                                     // nu = r.rt
   if (variant == CGX_HS || variant == CGX_PR || variant == CGX_M || vi.pipe) {
-    launch_spmv<SP_PLAIN, 0, false>(c, g, v[V_P], v[V_S]);          // s = A p
-    launch_dot(c, v[V_P], v[V_S], nullptr, 1);                          // mu = p.s
+    spmv(SP_PLAIN, v[V_P], v[V_S]);                                     // s = A p
+    dot(v[V_P], v[V_S], nullptr, 1);                                    // mu = p.s
   }
   if (variant == CGX_CG || variant == CGX_GV) {
-    launch_spmv<SP_PLAIN, 0, false>(c, g, v[V_RT], v[V_W]);         // w = A rt
-    CU(cudaMemcpyAsync(v[V_S], v[V_W], bytes, cudaMemcpyDeviceToDevice, c->stream));  // s = A p = w
-    launch_dot(c, v[V_P], v[V_S], nullptr, 1);                          // mu = p.s
-    launch_dot(c, v[V_W], v[V_RT], nullptr, 2);                         // eta = w.rt
+    spmv(SP_PLAIN, v[V_RT], v[V_W]);                                    // w = A rt
+    st.push_back(copy(v[V_S], v[V_W]));                                 // s = A p = w
+    dot(v[V_P], v[V_S], nullptr, 1);                                    // mu = p.s
+    dot(v[V_W], v[V_RT], nullptr, 2);                                   // eta = w.rt
   }
   if (variant == CGX_GV) {
-    launch_scale(c, dinv, v[V_W], v[V_WT]);                             // wt = M w
-    CU(cudaMemcpyAsync(v[V_ST], v[V_WT], bytes, cudaMemcpyDeviceToDevice, c->stream));
-    launch_spmv<SP_PLAIN, 0, false>(c, g, v[V_WT], v[V_T]);         // t = A wt
-    CU(cudaMemcpyAsync(v[V_U], v[V_T], bytes, cudaMemcpyDeviceToDevice, c->stream));  // u = A wt
+    scale(v[V_W], v[V_WT]);                                             // wt = M w
+    st.push_back(copy(v[V_ST], v[V_WT]));
+    spmv(SP_PLAIN, v[V_WT], v[V_T]);                                    // t = A wt
+    st.push_back(copy(v[V_U], v[V_T]));                                 // u = A wt
   }
   if (vi.cls == 2) {
-    launch_dot(c, v[V_R], v[V_S], dinv, 3);                             // delta = r.(M s)
-    launch_dot(c, v[V_S], v[V_S], dinv, 4);                             // gamma = (M s).s
+    dot(v[V_R], v[V_S], dinv, 3);                                       // delta = r.(M s)
+    dot(v[V_S], v[V_S], dinv, 4);                                       // gamma = (M s).s
   }
   if (vi.pipe) {
-    launch_scale(c, dinv, v[V_S], v[V_ST]);                             // st = M s
-    CU(cudaMemcpyAsync(v[V_W], v[V_S], bytes, cudaMemcpyDeviceToDevice, c->stream));   // w = s
-    if (v[V_WT]) CU(cudaMemcpyAsync(v[V_WT], v[V_ST], bytes, cudaMemcpyDeviceToDevice, c->stream));
-    launch_spmv<SP_PLAIN, 0, false>(c, g, v[V_ST], v[V_U]);         // u = A st
+    scale(v[V_S], v[V_ST]);                                             // st = M s
+    st.push_back(copy(v[V_W], v[V_S]));                                 // w = s
+    if (v[V_WT]) st.push_back(copy(v[V_WT], v[V_ST]));
+    spmv(SP_PLAIN, v[V_ST], v[V_U]);                                    // u = A st
   }
-  init_scalars_kernel<<<1, 1, 0, c->stream>>>(c->d_sc, vi.cls, vi.meurant ? 1 : 0);
-  c->launches++;
+  if (dist) {
+    st.push_back([=]() {                                                // publish the rank's partial dots
+      Args g = make_args(c);
+      Plan p; p.produce = FK_INIT;
+      plan_apply(c, g, p);
+      push_tmp_kernel<<<1, 32, 0, c->stream>>>(g);
+      c->launches++;
+      // not a pending recurrence: init_scalars consumes it directly
+      c->epoch++;
+      if (c->dist.mode == 2) {
+        const int slot = (int)(c->epoch % kSlots);
+        cudaEventRecord(c->ev_prod[slot], c->stream);
+        cudaStreamWaitEvent(c->comm_stream, c->ev_prod[slot], 0);
+        g_nccl.AllReduce(c->dist.nccl_in + (size_t)slot * kSumW, c->dist.nccl_out + (size_t)slot * kSumW, kSumW, 8, 0,
+                         c->nccl_comm, c->comm_stream);
+        cudaEventRecord(c->ev_red[slot], c->comm_stream);
+      }
+    });
+  }
+  const int cls = vi.cls, meur = vi.meurant ? 1 : 0;
+  st.push_back([=]() {
+    Args g = make_args(c);
+    g.scpar = c->scpar;
+    if (dist) {
+      g.pend_e[0] = c->epoch;
+      if (c->dist.mode == 2) cudaStreamWaitEvent(c->stream, c->ev_red[c->epoch % kSlots], 0);
+    }
+    init_scalars_kernel<<<1, 32, 0, c->stream>>>(g, cls, meur);
+    c->launches++;
+  });
+}
+
+// ---------------------------------------------------------------------------------------
+// problem vectors
+// ---------------------------------------------------------------------------------------
+static int load_problem(cgx_ctx* c, const double* b, const double* x0, const double* xt, i64 n,
+                        cudaMemcpyKind kind) {
+  if (!c || !b || !x0) return fail(CGX_ERR_ARG, "cgx_load_problem: b and x0 are required");
+  if (c->op_kind == 0 || n != c->n)
+    return fail(CGX_ERR_ARG, "cgx_load_problem: set the operator first; n must match (%lld vs %lld)",
+                (long long)n, (long long)c->n);
+  CU(cudaSetDevice(c->device));
+  if (!c->own_problem) {
+    c->d_b = c->d_x0 = c->d_xtrue = nullptr;
+    CU(cudaMalloc(&c->d_b, sizeof(double) * n));
+    CU(cudaMalloc(&c->d_x0, sizeof(double) * n));
+    CU(cudaMalloc(&c->d_xtrue, sizeof(double) * n));
+    c->own_problem = true;
+  }
+  CU(cudaMemcpyAsync(c->d_b, b, sizeof(double) * n, kind, c->stream));
+  CU(cudaMemcpyAsync(c->d_x0, x0, sizeof(double) * n, kind, c->stream));
+  if (xt) CU(cudaMemcpyAsync(c->d_xtrue, xt, sizeof(double) * n, kind, c->stream));
+  c->has_xtrue = xt != nullptr;
+  c->problem_loaded = true;
+  // multi-GPU: the neighbours need the boundary planes of x_true for e = x - x_true
+  if (c->dist.world > 1 && c->dist_ready) {
+    if (xt) launch_halo_push(c, make_args(c), c->d_xtrue, 3);
+    else c->hepoch[3]++;      // keep the epoch counters of all ranks in step
+  }
   return CGX_OK;
 }
 
-static Args make_args(cgx_ctx* c) {
-  Args g{};
-  g.x = c->vec[V_X]; g.r = c->vec[V_R]; g.rt = c->vec[V_RT]; g.p = c->vec[V_P];
-  g.s = c->vec[V_S]; g.st = c->vec[V_ST]; g.w = c->vec[V_W]; g.wt = c->vec[V_WT];
-  g.u = c->vec[V_U]; g.t = c->vec[V_T];
-  g.dinv = c->d_dinv; g.dinv_s = c->dinv_s; g.b = c->d_b; g.xtrue = c->d_xtrue;
-  g.sc = c->d_sc; g.partials = c->d_partials; g.ticket = c->d_ticket;
-  g.hist = c->d_hist; g.hist_len = c->hist_len; g.hist_mask = c->hist_mask;
-  g.n = c->n; g.k = c->cur_k;
-  return g;
+extern "C" int cgx_load_problem_host(cgx_ctx* c, const double* b, const double* x0,
+                                     const double* xt, int64_t n) {
+  int rc = load_problem(c, b, x0, xt, n, cudaMemcpyHostToDevice);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));   // pageable host buffers may be reused by the caller
+  return CGX_OK;
+}
+extern "C" int cgx_load_problem_dev(cgx_ctx* c, const double* b, const double* x0,
+                                    const double* xt, int64_t n) {
+  return load_problem(c, b, x0, xt, n, cudaMemcpyDeviceToDevice);
 }
 
-extern "C" int cgx_begin(cgx_ctx* c, int variant, int max_iter, unsigned hist_mask, int path) {
+// ---------------------------------------------------------------------------------------
+// persistent path (cgx_persistent.cuh): one cooperative launch runs every iteration
+// ---------------------------------------------------------------------------------------
+static int pers_grid(const cgx_ctx* c) {
+  i64 g = (c->n + kBlock - 1) / kBlock;
+  g = std::min<i64>(g, (i64)c->sm_count * 2);
+  g = std::min<i64>(g, kPersMaxGrid);
+  return (int)std::max<i64>(g, 1);
+}
+
+template <class Op, int PM>
+static int pers_launch_pm(cgx_ctx* c, const Op& A, PersArgs pa) {
+  void* params[] = {(void*)&A, (void*)&pa};
+  const void* fn = nullptr;
+#define CGX_PV(V) case V: fn = (const void*)persistent_kernel<Op, V, PM>; break;
+  switch (c->variant) {
+    CGX_PV(CGX_HS) CGX_PV(CGX_CG) CGX_PV(CGX_GV) CGX_PV(CGX_PR) CGX_PV(CGX_M) CGX_PV(CGX_PIPE_PR)
+    CGX_PV(CGX_PIPE_P) CGX_PV(CGX_PIPE_PR_M) CGX_PV(CGX_PIPE_P_M)
+  }
+#undef CGX_PV
+  if (!fn) return fail(CGX_ERR_ARG, "persistent path: unknown variant");
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0));
+  int grid = std::min(pers_grid(c), std::max(1, per_sm) * c->sm_count);
+  pa.nblocks = grid;
+  CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), params, 0, c->stream));
+  c->launches++;
+  return CGX_OK;
+}
+static int pers_launch(cgx_ctx* c, const PersArgs& pa) {
+  if (c->op_kind == 1) {
+    if (c->pm == 2) return pers_launch_pm<CsrOp, 2>(c, c->csr, pa);
+    if (c->pm == 1) return pers_launch_pm<CsrOp, 1>(c, c->csr, pa);
+    return pers_launch_pm<CsrOp, 0>(c, c->csr, pa);
+  }
+  if (c->pm == 2) return pers_launch_pm<StencilOp, 2>(c, c->sten, pa);
+  if (c->pm == 1) return pers_launch_pm<StencilOp, 1>(c, c->sten, pa);
+  return pers_launch_pm<StencilOp, 0>(c, c->sten, pa);
+}
+
+// ---------------------------------------------------------------------------------------
+// begin / advance, for one context or a lockstep group of ranks
+// ---------------------------------------------------------------------------------------
+static int begin_prepare(cgx_ctx* c, int variant, int max_iter, unsigned hist_mask, int path) {
   if (!c) return fail(CGX_ERR_ARG, "cgx_begin: ctx is NULL");
   if (variant < 0 || variant >= CGX_NUM_VARIANTS) return fail(CGX_ERR_ARG, "cgx_begin: unknown variant %d", variant);
   if (max_iter < 1) return fail(CGX_ERR_ARG, "cgx_begin: max_iter must be >= 1");
   if (c->op_kind == 0 || !c->problem_loaded) return fail(CGX_ERR_ARG, "cgx_begin: operator and problem must be set first");
-  if (path == CGX_PATH_PERSISTENT)
-    return fail(CGX_ERR_UNSUPPORTED, "cgx_begin: persistent path not built in this version");
+  if (path != CGX_PATH_AUTO && path != CGX_PATH_STREAM && path != CGX_PATH_PERSISTENT)
+    return fail(CGX_ERR_ARG, "cgx_begin: unknown path %d", path);
+  if (c->dist.world > 1 && !c->dist_ready)
+    return fail(CGX_ERR_ARG, "cgx_begin: cgx_dist_commit has not been called on this rank");
+  if (c->dist.world > 1 && path == CGX_PATH_PERSISTENT)
+    return fail(CGX_ERR_UNSUPPORTED, "cgx_begin: the persistent path is single-GPU in this version");
   CU(cudaSetDevice(c->device));
   const bool prec = c->d_dinv != nullptr;
   const VariantInfo vi = variant_info(variant, prec);
@@ -586,16 +967,16 @@ extern "C" int cgx_begin(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
   c->hist_mask = hist_mask;
   { int trc = setup_tma(c, vi.need); if (trc) return trc; }
   c->variant = variant; c->max_iter = max_iter; c->cur_k = 0;
-  c->path = CGX_PATH_STREAM;
+  if (path == CGX_PATH_AUTO)
+    path = (c->dist.world <= 1 && c->n < c->pers_threshold) ? CGX_PATH_PERSISTENT : CGX_PATH_STREAM;
+  c->path = path;
   c->launches_run = 0; c->loop_ms = 0.0;
+  c->pend.clear();
+  return CGX_OK;
+}
 
-  Args g = make_args(c);
-  const i64 launches0 = c->launches;
-  CU(cudaEventRecord(c->ev[0], c->stream));
-  int rc = init_state(c, variant, vi, g);
-  if (rc) return rc;
-  if (hist_mask) launch_instrument(c, g);
-  CU(cudaEventRecord(c->ev[1], c->stream));
+static int begin_finish(cgx_ctx* c, i64 launches0) {
+  CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   float ms0 = 0.f;
@@ -607,45 +988,193 @@ extern "C" int cgx_begin(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
   return CGX_OK;
 }
 
-extern "C" int cgx_advance(cgx_ctx* c, int niter) {
-  if (!c || !c->ran) return fail(CGX_ERR_ARG, "cgx_advance: call cgx_begin first");
-  if (niter < 0) return fail(CGX_ERR_ARG, "cgx_advance: niter must be >= 0");
-  CU(cudaSetDevice(c->device));
-  const bool prec = c->d_dinv != nullptr;
-  const VariantInfo vi = variant_info(c->variant, prec);
-  Args g = make_args(c);
-  const int last = std::min(c->max_iter - 1, c->cur_k + niter);
-  const i64 launches0 = c->launches;
-  CU(cudaEventRecord(c->ev[1], c->stream));
-  for (int k = c->cur_k + 1; k <= last; ++k) {
-    g.k = k;
-    if (c->pm == 2) iterate_stream<2>(c, c->variant, vi, g);
-    else if (c->pm == 1) iterate_stream<1>(c, c->variant, vi, g);
-    else iterate_stream<0>(c, c->variant, vi, g);
-    if (c->hist_mask) launch_instrument(c, g);
-  }
-  CU(cudaEventRecord(c->ev[2], c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  CU(cudaGetLastError());
-  float ms1 = 0.f;
-  CU(cudaEventElapsedTime(&ms1, c->ev[1], c->ev[2]));
-  c->loop_ms += ms1;
-  if (c->profile) prof_resolve(c);
+static int check_device_flags(cgx_ctx* c, const char* who) {
   if (c->use_tma) {
     int flag = 0;
     CU(cudaMemcpyFromSymbol(&flag, g_tma_timeout, sizeof(int)));
-    if (flag) return fail(CGX_ERR_CUDA, "cgx_advance: a TMA plane copy did not complete within 1 s");
+    if (flag) return fail(CGX_ERR_CUDA, "%s: a TMA plane copy did not complete within 1 s", who);
   }
-  c->launches_run += c->launches - launches0;
-  c->cur_k = std::max(c->cur_k, last);
+  if (c->path == CGX_PATH_PERSISTENT) {
+    int err = 0;
+    CU(cudaMemcpy(&err, c->d_pbar + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) return fail(CGX_ERR_CUDA, "%s: the persistent kernel's grid barrier timed out", who);
+  }
+  if (c->dist.world > 1 && c->d_win) {
+    int err = 0;
+    CU(cudaMemcpy(&err, c->d_win + offsetof(WinHdr, error), sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) return fail(CGX_ERR_CUDA, "%s: rank %d waited more than 10 s for a peer (halo or scalar exchange)",
+                         who, c->dist.rank);
+  }
   return CGX_OK;
+}
+
+// Lockstep driver: `count` contexts (ranks of one partitioned problem, or a single context).
+static int group_begin(cgx_ctx** cs, int count, int variant, int max_iter, unsigned hist_mask, int path) {
+  for (int i = 0; i < count; ++i) {
+    int rc = begin_prepare(cs[i], variant, max_iter, hist_mask, path);
+    if (rc) return rc;
+  }
+  std::vector<Steps> steps(count);
+  std::vector<i64> l0(count);
+  for (int i = 0; i < count; ++i) {
+    cgx_ctx* c = cs[i];
+    l0[i] = c->launches;
+    const VariantInfo vi = variant_info(variant, c->d_dinv != nullptr);
+    build_init_steps(c, variant, vi, steps[i]);
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->ev[0], c->stream));
+  }
+  for (size_t s = 0; s < steps[0].size(); ++s)
+    for (int i = 0; i < count; ++i) {
+      if (count > 1) cudaSetDevice(cs[i]->device);
+      steps[i][s]();
+    }
+  // k = 0 entry of the histories (the reference's callbacks fire on the initial state)
+  for (int i = 0; i < count; ++i) cs[i]->cur_k = 0;
+  if (cs[0]->hist_mask) {
+    const int core = (variant == CGX_HS) ? 3 : 2;
+    for (int s = core; s < iter_stage_count(cs[0]); ++s)
+      for (int i = 0; i < count; ++i) {
+        if (count > 1) cudaSetDevice(cs[i]->device);
+        Args g = make_args(cs[i]);
+        g.k = 0;
+        iter_stage(cs[i], s, g);
+      }
+  }
+  for (int i = 0; i < count; ++i) {
+    cudaSetDevice(cs[i]->device);
+    CU(cudaEventRecord(cs[i]->ev[1], cs[i]->stream));
+  }
+  for (int i = 0; i < count; ++i) {
+    int rc = begin_finish(cs[i], l0[i]);
+    if (rc) return rc;
+    rc = check_device_flags(cs[i], "cgx_begin");
+    if (rc) return rc;
+  }
+  return CGX_OK;
+}
+
+static int group_advance(cgx_ctx** cs, int count, int niter) {
+  for (int i = 0; i < count; ++i)
+    if (!cs[i] || !cs[i]->ran) return fail(CGX_ERR_ARG, "cgx_advance: call cgx_begin first");
+  if (niter < 0) return fail(CGX_ERR_ARG, "cgx_advance: niter must be >= 0");
+  cgx_ctx* c0 = cs[0];
+  const int last = std::min(c0->max_iter - 1, c0->cur_k + niter);
+  std::vector<i64> l0(count);
+  std::vector<Args> gs(count);
+  for (int i = 0; i < count; ++i) {
+    CU(cudaSetDevice(cs[i]->device));
+    l0[i] = cs[i]->launches;
+    gs[i] = make_args(cs[i]);
+    CU(cudaEventRecord(cs[i]->ev[1], cs[i]->stream));
+  }
+  if (c0->path == CGX_PATH_PERSISTENT) {
+    if (last > c0->cur_k) {
+      PersArgs pa{};
+      pa.g = gs[0];
+      pa.k0 = c0->cur_k + 1; pa.k1 = last;
+      pa.part = c0->d_ppart; pa.bar = c0->d_pbar; pa.err = reinterpret_cast<int*>(c0->d_pbar + 1);
+      CU(cudaMemsetAsync(c0->d_pbar, 0, sizeof(u64) * 2, c0->stream));
+      int rc = pers_launch(c0, pa);
+      if (rc) return rc;
+    }
+  } else {
+    const int ns = iter_stage_count(c0);
+    for (int k = c0->cur_k + 1; k <= last; ++k)
+      for (int s = 0; s < ns; ++s)
+        for (int i = 0; i < count; ++i) {
+          if (count > 1) cudaSetDevice(cs[i]->device);
+          gs[i].k = k;
+          iter_stage(cs[i], s, gs[i]);
+        }
+    for (int i = 0; i < count; ++i) {
+      if (count > 1) cudaSetDevice(cs[i]->device);
+      const VariantInfo vi = variant_info(cs[i]->variant, cs[i]->d_dinv != nullptr);
+      launch_flush(cs[i], gs[i], vi.meurant);
+    }
+  }
+  for (int i = 0; i < count; ++i) {
+    cudaSetDevice(cs[i]->device);
+    CU(cudaEventRecord(cs[i]->ev[2], cs[i]->stream));
+  }
+  for (int i = 0; i < count; ++i) {
+    cgx_ctx* c = cs[i];
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->comm_stream) CU(cudaStreamSynchronize(c->comm_stream));
+    CU(cudaGetLastError());
+    float ms1 = 0.f;
+    CU(cudaEventElapsedTime(&ms1, c->ev[1], c->ev[2]));
+    c->loop_ms += ms1;
+    if (c->profile) prof_resolve(c);
+    int rc = check_device_flags(c, "cgx_advance");
+    if (rc) return rc;
+    c->launches_run += c->launches - l0[i];
+    c->cur_k = std::max(c->cur_k, last);
+  }
+  return CGX_OK;
+}
+
+extern "C" int cgx_begin(cgx_ctx* c, int variant, int max_iter, unsigned hist_mask, int path) {
+  return group_begin(&c, 1, variant, max_iter, hist_mask, path);
+}
+extern "C" int cgx_advance(cgx_ctx* c, int niter) {
+  if (!c) return fail(CGX_ERR_ARG, "cgx_advance: ctx is NULL");
+  return group_advance(&c, 1, niter);
+}
+
+// Ranks emulated inside one process (all on one GPU -> they share rank 0's stream, or one
+// context per GPU): same kernels, same protocol, launched stage by stage in rank order.
+static int group_check(cgx_ctx** cs, int count) {
+  if (!cs || count < 1 || count > kMaxWorld) return fail(CGX_ERR_ARG, "cgx_group: bad arguments");
+  for (int i = 0; i < count; ++i)
+    if (!cs[i] || cs[i]->dist.world != count || cs[i]->dist.rank != i)
+      return fail(CGX_ERR_ARG, "cgx_group: contexts must be ranks 0..%d of one partition, in order", count - 1);
+  return CGX_OK;
+}
+static void group_share_stream(cgx_ctx** cs, int count, bool on) {
+  for (int i = 1; i < count; ++i)
+    if (cs[i]->device == cs[0]->device) cs[i]->stream = on ? cs[0]->own_stream : cs[i]->own_stream;
+}
+extern "C" int cgx_group_begin(cgx_ctx** cs, int count, int variant, int max_iter, unsigned hist_mask) {
+  int rc = group_check(cs, count);
+  if (rc) return rc;
+  group_share_stream(cs, count, true);
+  rc = group_begin(cs, count, variant, max_iter, hist_mask, CGX_PATH_STREAM);
+  group_share_stream(cs, count, false);
+  return rc;
+}
+extern "C" int cgx_group_advance(cgx_ctx** cs, int count, int niter) {
+  int rc = group_check(cs, count);
+  if (rc) return rc;
+  group_share_stream(cs, count, true);
+  rc = group_advance(cs, count, niter);
+  group_share_stream(cs, count, false);
+  return rc;
+}
+extern "C" int cgx_group_load_problem_host(cgx_ctx** cs, int count, const double* b, const double* x0,
+                                           const double* xt, int64_t n_total) {
+  int rc = group_check(cs, count);
+  if (rc) return rc;
+  if (!b || !x0) return fail(CGX_ERR_ARG, "cgx_group_load_problem_host: b and x0 are required");
+  i64 off = 0;
+  group_share_stream(cs, count, true);
+  for (int i = 0; i < count && !rc; ++i) {
+    rc = load_problem(cs[i], b + off, x0 + off, xt ? xt + off : nullptr, cs[i]->n, cudaMemcpyHostToDevice);
+    off += cs[i]->n;
+  }
+  for (int i = 0; i < count; ++i) { cudaSetDevice(cs[i]->device); cudaStreamSynchronize(cs[i]->stream); }
+  group_share_stream(cs, count, false);
+  if (!rc && off != n_total) return fail(CGX_ERR_ARG, "cgx_group_load_problem_host: slabs cover %lld rows, n = %lld",
+                                         (long long)off, (long long)n_total);
+  return rc;
 }
 
 extern "C" int cgx_get_info(cgx_ctx* c, cgx_info* info) {
   if (!c || !c->ran || !info) return fail(CGX_ERR_ARG, "cgx_get_info: bad arguments");
   CU(cudaSetDevice(c->device));
   Scal h;
-  CU(cudaMemcpy(&h, c->d_sc, sizeof(Scal), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&h, c->d_sc + c->scpar, sizeof(Scal), cudaMemcpyDeviceToHost));
   info->setup_ms = c->setup_ms; info->loop_ms = c->loop_ms;
   info->h2d_bytes = 0; info->d2h_bytes = 0;
   info->kernel_launches = c->launches_run;
@@ -659,6 +1188,16 @@ extern "C" int cgx_get_info(cgx_ctx* c, cgx_info* info) {
 extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
   if (!c || !name) return fail(CGX_ERR_ARG, "cgx_set_option: bad arguments");
   if (!strcmp(name, "tma")) { c->no_tma = (value == 0); return CGX_OK; }
+  if (!strcmp(name, "csr_stream")) { c->no_csr_stream = (value == 0); return CGX_OK; }
+  if (!strcmp(name, "persistent_threshold")) { c->pers_threshold = value; return CGX_OK; }
+  if (!strcmp(name, "stub_allreduce")) {
+    // timing experiment (SURVEY.md section 8d "allreduce-hiding metric"): value != 0 replaces the
+    // scalar exchange by a local stand-in; value == 0 restores the mode chosen at commit
+    if (c->dist.world <= 1) return fail(CGX_ERR_ARG, "cgx_set_option: stub_allreduce needs a partitioned run");
+    if (value) { if (c->dist.mode != 3) { c->dist.saved_mode = c->dist.mode; c->dist.mode = 3; } }
+    else if (c->dist.mode == 3) c->dist.mode = c->dist.saved_mode;
+    return CGX_OK;
+  }
   return fail(CGX_ERR_ARG, "cgx_set_option: unknown option '%s'", name);
 }
 
@@ -686,7 +1225,7 @@ extern "C" int cgx_get_scalars(cgx_ctx* c, double* out9) {
   if (!c || !c->ran || !out9) return fail(CGX_ERR_ARG, "cgx_get_scalars: bad arguments");
   CU(cudaSetDevice(c->device));
   Scal h;
-  CU(cudaMemcpy(&h, c->d_sc, sizeof(Scal), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&h, c->d_sc + c->scpar, sizeof(Scal), cudaMemcpyDeviceToHost));
   const double v[9] = {h.a, h.a1, h.b, h.nu, h.nu1, h.mu, h.eta, h.del, h.gam};
   memcpy(out9, v, sizeof v);
   return CGX_OK;
@@ -745,10 +1284,122 @@ extern "C" int cgx_solve_host(cgx_ctx* c, int variant, const double* b, const do
 }
 
 // ---------------------------------------------------------------------------------------
+// multi-GPU set-up (include/cgx.h "row-partitioned runs")
+// ---------------------------------------------------------------------------------------
+extern "C" int cgx_set_stencil_slab(cgx_ctx* c, int64_t nx, int64_t ny, int64_t nz_local, int world, int rank,
+                                    double diag, double off) {
+  if (!c || world < 1 || world > kMaxWorld || rank < 0 || rank >= world)
+    return fail(CGX_ERR_ARG, "cgx_set_stencil_slab: bad arguments (world <= %d)", kMaxWorld);
+  if ((nx * ny) % 2 != 0 && world > 1)
+    return fail(CGX_ERR_UNSUPPORTED, "cgx_set_stencil_slab: nx*ny must be even (16-byte halo stores)");
+  CU(cudaSetDevice(c->device));
+  dist_release(c);
+  int rc = set_stencil(c, 3, nx, ny, nz_local, diag, off, rank > 0, rank < world - 1);
+  if (rc) return rc;
+  if (world == 1) return CGX_OK;
+  Dist& d = c->dist;
+  d.world = world; d.rank = rank; d.mode = 1; d.saved_mode = 1;
+  d.has_lo = rank > 0; d.has_hi = rank < world - 1;
+  d.plane = nx * ny;
+  c->win_bytes = kWinHdrBytes + sizeof(double) * (size_t)kChan * 4 * (size_t)d.plane;
+  CU(cudaMalloc(&c->d_win, c->win_bytes));
+  CU(cudaMemset(c->d_win, 0, c->win_bytes));
+  CU(cudaDeviceSynchronize());
+  c->peer_base[rank] = c->d_win;
+  c->epoch = 0; c->scpar = 0; c->pend.clear();
+  for (auto& h : c->hepoch) h = 0;
+  return CGX_OK;
+}
+
+extern "C" int cgx_dist_ipc_handle(cgx_ctx* c, void* handle64) {
+  if (!c || !c->d_win || !handle64) return fail(CGX_ERR_ARG, "cgx_dist_ipc_handle: no window (cgx_set_stencil_slab first)");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  CU(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, c->d_win));
+  memcpy(handle64, &h, 64);
+  return CGX_OK;
+}
+extern "C" int cgx_dist_attach_ipc(cgx_ctx* c, int peer, const void* handle64) {
+  if (!c || !c->d_win || !handle64 || peer < 0 || peer >= c->dist.world || peer == c->dist.rank)
+    return fail(CGX_ERR_ARG, "cgx_dist_attach_ipc: bad arguments");
+  CU(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  c->peer_base[peer] = (unsigned char*)p;
+  c->peer_ipc[peer] = true;
+  return CGX_OK;
+}
+extern "C" int cgx_dist_attach_ctx(cgx_ctx* c, int peer, cgx_ctx* other) {
+  if (!c || !other || !c->d_win || !other->d_win || peer < 0 || peer >= c->dist.world || peer == c->dist.rank ||
+      other->dist.rank != peer || other->dist.world != c->dist.world)
+    return fail(CGX_ERR_ARG, "cgx_dist_attach_ctx: bad arguments");
+  if (other->device != c->device) {
+    CU(cudaSetDevice(c->device));
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, c->device, other->device));
+    if (!can) return fail(CGX_ERR_UNSUPPORTED, "cgx_dist_attach_ctx: device %d cannot access device %d", c->device, other->device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(other->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+      return fail(CGX_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+  }
+  c->peer_base[peer] = other->d_win;
+  c->peer_ipc[peer] = false;
+  return CGX_OK;
+}
+extern "C" int cgx_dist_nccl_unique_id(const char* libpath, void* id128) {
+  if (!id128) return fail(CGX_ERR_ARG, "cgx_dist_nccl_unique_id: id is NULL");
+  int rc = nccl_load(libpath);
+  if (rc) return rc;
+  int e = g_nccl.GetUniqueId(id128);
+  if (e) return fail(CGX_ERR_CUDA, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+  return CGX_OK;
+}
+// mode: 1 = peer-to-peer flag exchange of the fused scalars, 2 = ncclAllReduce on a side stream
+extern "C" int cgx_dist_commit(cgx_ctx* c, int mode, const char* nccl_libpath, const void* nccl_id128) {
+  if (!c || !c->d_win || (mode != 1 && mode != 2)) return fail(CGX_ERR_ARG, "cgx_dist_commit: bad arguments");
+  CU(cudaSetDevice(c->device));
+  Dist& d = c->dist;
+  for (int r = 0; r < d.world; ++r) {
+    if (!c->peer_base[r]) return fail(CGX_ERR_ARG, "cgx_dist_commit: rank %d's window is not attached", r);
+    d.win[r] = reinterpret_cast<WinHdr*>(c->peer_base[r]);
+  }
+  d.ghost = reinterpret_cast<double*>(c->d_win + kWinHdrBytes);
+  d.ghost_lo = d.has_lo ? reinterpret_cast<double*>(c->peer_base[d.rank - 1] + kWinHdrBytes) : nullptr;
+  d.ghost_hi = d.has_hi ? reinterpret_cast<double*>(c->peer_base[d.rank + 1] + kWinHdrBytes) : nullptr;
+  d.mode = mode; d.saved_mode = mode;
+  if (mode == 2) {
+    if (!nccl_id128) return fail(CGX_ERR_ARG, "cgx_dist_commit: mode 2 needs the NCCL unique id");
+    int rc = nccl_load(nccl_libpath);
+    if (rc) return rc;
+    Nid id;
+    memcpy(&id, nccl_id128, 128);
+    int e = g_nccl.CommInitRank(&c->nccl_comm, d.world, id, d.rank);
+    if (e) return fail(CGX_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+    CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    for (int s = 0; s < kSlots; ++s) {
+      CU(cudaEventCreateWithFlags(&c->ev_prod[s], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c->ev_red[s], cudaEventDisableTiming));
+    }
+    CU(cudaMalloc(&c->d_nccl, sizeof(double) * 2 * kSlots * kSumW));
+    CU(cudaMemset(c->d_nccl, 0, sizeof(double) * 2 * kSlots * kSumW));
+    d.nccl_in = c->d_nccl;
+    d.nccl_out = c->d_nccl + kSlots * kSumW;
+  }
+  CU(cudaDeviceSynchronize());
+  c->dist_ready = true;
+  return CGX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // primitives for unit tests
 // ---------------------------------------------------------------------------------------
 extern "C" int cgx_spmv_host(cgx_ctx* c, const double* v, double* y, int64_t n) {
   if (!c || !v || !y || c->op_kind == 0 || n != c->n) return fail(CGX_ERR_ARG, "cgx_spmv_host: bad arguments");
+  if (c->dist.world > 1) return fail(CGX_ERR_UNSUPPORTED, "cgx_spmv_host: single-GPU primitive");
   CU(cudaSetDevice(c->device));
   double *dv = nullptr, *dy = nullptr;
   CU(cudaMalloc(&dv, sizeof(double) * n));
@@ -756,7 +1407,19 @@ extern "C" int cgx_spmv_host(cgx_ctx* c, const double* v, double* y, int64_t n) 
   CU(cudaMemcpyAsync(dv, v, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
   Args g{};
   g.n = n;
-  launch_spmv<SP_PLAIN, 0, false>(c, g, dv, dy);
+  g.d.world = 1;
+  CUtensorMap tm;
+  if (c->op_kind == 2 && tma_prepare_geom(c) && tma_encode_dims(dv, c->sten.nx, c->sten.ny, c->sten.nz, &tm)) {
+    // the TMA-staged stencil kernel in its plainest mode (SP_PIPE_N: u = A v, no epilogue)
+    g.u = dy;
+    CU(cudaFuncSetAttribute(stencil_tma_kernel<SP_PIPE_N, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)tma_smem_bytes(1)));
+    stencil_tma_kernel<SP_PIPE_N, 0, false><<<c->tma_grid[0], kTmaThreads, tma_smem_bytes(1), c->stream>>>(
+        tm, tm, tm, tm, c->geom, g);
+    c->launches++;
+  } else {
+    launch_spmv<SP_PLAIN, 0, false>(c, g, dv, dy);
+  }
   CU(cudaMemcpyAsync(y, dy, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
@@ -777,7 +1440,7 @@ extern "C" int cgx_dot_host(cgx_ctx* c, const double* u, const double* v, int64_
   launch_dot(c, du, dv, nullptr, 7);
   c->n = keep;
   Scal h;
-  CU(cudaMemcpyAsync(&h, c->d_sc, sizeof(Scal), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&h, c->d_sc + c->scpar, sizeof(Scal), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   *out = h.tmp[7];

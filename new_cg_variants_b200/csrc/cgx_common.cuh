@@ -94,16 +94,19 @@ __device__ __forceinline__ void block_sum(double (&v)[NR], double* sh) {
 // Grid-wide sum of NR values with a fixed summation order, finished by whichever CTA
 // arrives last (ticket counter); `fin(acc)` runs in ONE thread with the totals.
 // partials: [gridDim.x][NR].  The order in which CTAs arrive does not influence the bits.
+// `sys`: the CTAs also stored into peer memory (halo planes); make those stores visible
+// system-wide before the ticket so that the finishing CTA may publish them.
 template <int NR, class Fin>
 __device__ __forceinline__ void grid_sum_finalize(double (&v)[NR], double* __restrict__ partials,
-                                                  unsigned* __restrict__ ticket, Fin fin) {
+                                                  unsigned* __restrict__ ticket, Fin fin,
+                                                  bool sys = false) {
   __shared__ double sh[NR * (kBlock / 32)];
   __shared__ bool is_last;
   block_sum<NR>(v, sh);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int j = 0; j < NR; ++j) __stcg(&partials[(i64)blockIdx.x * NR + j], v[j]);
-    __threadfence();
+    if (sys) __threadfence_system(); else __threadfence();
     unsigned t = atomicAdd(ticket, 1u);
     is_last = (t == gridDim.x - 1);
   }
@@ -124,8 +127,98 @@ __device__ __forceinline__ void grid_sum_finalize(double (&v)[NR], double* __res
   }
 }
 
+// For kernels without a reduction that still have something to publish when the whole grid
+// is done (halo epochs): `fin()` runs in one thread of the CTA that arrives last.
+template <class Fin>
+__device__ __forceinline__ void grid_last_finalize(unsigned* __restrict__ ticket, Fin fin) {
+  __shared__ bool is_last0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    unsigned t = atomicAdd(ticket, 1u);
+    is_last0 = (t == gridDim.x - 1);
+    if (is_last0) { *ticket = 0u; fin(); }
+  }
+}
+
 __device__ __forceinline__ void note_breakdown(Scal* sc, int k, double a, double b) {
   if (sc->breakdown < 0 && !(isfinite(a) && isfinite(b))) sc->breakdown = k;
+}
+
+// =====================================================================================
+// Row-partitioned multi-GPU runs (one rank per GPU, z-slabs of the stencil grid).
+//
+// Every rank owns a "window": a device allocation that its peers map (CUDA IPC between
+// processes, plain pointers inside one process) and write into directly over NVLink.
+//   * scalar exchange: the CTA that finishes a fused reduction stores the rank's partial
+//     sums into slot (epoch % kSlots) of EVERY rank's window, then the epoch number into
+//     the matching flag (release, system scope).  The next kernel that needs alpha/beta
+//     waits for all ranks' flags, adds the partials in rank order (bit-identical on every
+//     GPU) and evaluates the scalar recurrences redundantly -- a one-hop all-to-all
+//     "allreduce" with no extra launch.  (mode 2 swaps this for ncclAllReduce on a side
+//     stream; the flags are then not used.)
+//   * halo exchange: the vector pass that produces the SpMV input also stores its first
+//     and last plane into the neighbours' ghost planes (double-buffered by parity), and
+//     its last CTA publishes the halo epoch; the stencil kernel waits for that epoch only
+//     before it touches a ghost plane.
+// A kernel never waits for something produced by the same stage of another rank, so the
+// ranks may also be emulated as contexts sharing one stream on one GPU (tests).
+// =====================================================================================
+constexpr int kMaxWorld = 8;
+constexpr int kSumW = 8;     // doubles per exchanged record
+constexpr int kSlots = 8;    // ring depth of the scalar exchange (see DESIGN.md "Epochs")
+constexpr int kChan = 4;     // halo channels: 0,1 SpMV inputs, 2 x (instrumentation), 3 x_true
+
+typedef unsigned long long u64;
+
+struct WinHdr {
+  double sums[kSlots][kMaxWorld][kSumW];
+  u64 sflag[kSlots][kMaxWorld];
+  u64 hflag[kChan][2][2];          // [channel][parity][side]; side 0 = plane below, 1 = above
+  int error;                       // set when a bounded wait expired
+  int pad;
+};
+constexpr size_t kWinHdrBytes = (sizeof(WinHdr) + 1023) / 1024 * 1024;   // ghost planes follow
+
+enum { FK_NONE = 0, FK_HS_NU, FK_HS_MU, FK_CGGV, FK_PR_NU, FK_PR_SP, FK_PIPE, FK_INIT };
+
+struct Dist {
+  int world, rank, mode;           // mode: 1 peer-to-peer scalars, 2 NCCL scalars, 3 timing stub (local only)
+  int saved_mode;
+  int has_lo, has_hi;              // a neighbour slab exists below / above
+  WinHdr* win[kMaxWorld];          // every rank's window header (win[rank] is local)
+  double* ghost;                   // local ghost planes [kChan][2 parity][2 side][plane]
+  double* ghost_lo;                // ghost planes of the rank below (peer mapped) or null
+  double* ghost_hi;
+  double* nccl_in;                 // mode 2: [kSlots][kSumW] local partials / reduced totals
+  double* nccl_out;
+  i64 plane;                       // points per exchanged plane
+};
+
+__device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {
+  u64 v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(u64* p, u64 v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 timer_ns() {
+  u64 t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait for *flag >= epoch.  A peer that never arrives must surface as an error
+// (CGX_ERR_CUDA after the next synchronisation), not as a hung GPU.
+__device__ __forceinline__ void wait_epoch(const u64* flag, u64 epoch, int* err) {
+  if (ld_acquire_sys(flag) >= epoch) return;
+  const u64 t0 = timer_ns();
+  while (ld_acquire_sys(flag) < epoch) {
+    if (timer_ns() - t0 > 10000000000ull) { atomicExch(err, 1); return; }
+  }
+}
+__host__ __device__ __forceinline__ size_t ghost_off(const Dist& d, int ch, int par, int side) {
+  return ((size_t)(ch * 2 + par) * 2 + side) * (size_t)d.plane;
 }
 
 }  // namespace cgx

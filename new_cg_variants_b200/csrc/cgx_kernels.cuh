@@ -13,6 +13,7 @@ namespace cgx {
 // (sum = 0; sum += a*v, stored order, multiply and add rounded separately).
 // =====================================================================================
 struct CsrOp {
+  static constexpr bool kSlab = false;
   const int* __restrict__ ptr;
   const int* __restrict__ idx;
   const double* __restrict__ val;
@@ -35,10 +36,15 @@ struct CsrOp {
 // Matrix-free Dirichlet Poisson stencil, natural ordering.  Visits the neighbours in
 // ascending column order (z-1, y-1, x-1, centre, x+1, y+1, z+1), i.e. exactly the order
 // of the canonical CSR matrix, so the result is bit-identical to scipy on that matrix.
+// In a multi-GPU run the operator is the z-slab [z_begin, z_begin + nz) of the global grid:
+// has_zlo / has_zhi say that a plane exists below local z = 0 / above local z = nz-1; the
+// loader is then called with j < 0 or j >= n for those neighbours (see VecIn).
 struct StencilOp {
+  static constexpr bool kSlab = true;
   int nx, ny, nz;
   double diag, off;
   i64 n;
+  int has_zlo, has_zhi;
   template <int NV, class Ld>
   __device__ __forceinline__ void row(i64 i, Ld ld, double (&y)[NV]) const {
     const int plane = nx * ny;
@@ -55,13 +61,13 @@ struct StencilOp {
       ld((i64)(j), v);                                                     \
       _Pragma("unroll") for (int c = 0; c < NV; ++c) y[c] = add_(y[c], mul_((coef), v[c])); \
     }
-    CGX_ST_TERM(z > 0, ii - plane, off)
+    CGX_ST_TERM(z > 0 || has_zlo, ii - plane, off)
     CGX_ST_TERM(yy > 0, ii - nx, off)
     CGX_ST_TERM(xx > 0, ii - 1, off)
     CGX_ST_TERM(true, ii, diag)
     CGX_ST_TERM(xx < nx - 1, ii + 1, off)
     CGX_ST_TERM(yy < ny - 1, ii + nx, off)
-    CGX_ST_TERM(z < nz - 1, ii + plane, off)
+    CGX_ST_TERM(z < nz - 1 || has_zhi, ii + plane, off)
 #undef CGX_ST_TERM
   }
 };
@@ -77,7 +83,32 @@ struct Args {
   Scal* sc; double* partials; unsigned* ticket;
   double* hist; int hist_len; unsigned hist_mask;
   i64 n; int k;
+  // ---- multi-GPU (d.world > 1), filled per launch by the host ----
+  Dist d;
+  int scpar;                 // which of sc[0], sc[1] holds the scalars this kernel starts from
+  int npend;                 // reductions of earlier kernels still to be folded into them
+  int pend_kind[3], pend_k[3];
+  u64 pend_e[3];             // their epochs
+  u64 sepoch;                // epoch of the reduction this kernel produces
+  int hout_n, hout_ch, hout_par;   // halo planes this kernel produces: channels hout_ch ..
+  u64 hout_epoch;
+  int hin_ch, hin_par;             // halo planes this kernel consumes
+  u64 hin_epoch;
+  int xt_par;                      // ghost planes of x_true (channel 3), pushed when the problem is loaded
+  u64 xt_epoch;
+  int meur;                        // Meurant predictor (kernels that are not templated on it)
 };
+
+// An SpMV input vector: the owned slab and (multi-GPU) the ghost planes below and above.
+struct VecIn { const double* v; const double* lo; const double* hi; };
+template <bool SLAB>
+__device__ __forceinline__ double vload(const VecIn& a, i64 j, i64 n, i64 plane) {
+  if constexpr (SLAB) {
+    if (j < 0) return a.lo[j + plane];
+    if (j >= n) return a.hi[j - n];
+  }
+  return a.v[j];
+}
 
 // Stage tags
 enum {
@@ -105,6 +136,157 @@ __device__ __forceinline__ double predict_beta(bool meurant, double nu, double a
   const double a2g = mul_(mul_(a, a), gam);
   const double nup = meurant ? add_(-nu, a2g) : add_(sub_(nu, mul_(mul_(2.0, a), del)), a2g);
   return div_(nup, nu);
+}
+
+// Scalar recurrences that close a fused reduction (run by one thread with the grid -- or,
+// multi-GPU, the all-rank -- totals).  kind: FK_* of cgx_common.cuh.
+__device__ __forceinline__ void apply_finalize(int kind, bool meurant, Scal* sc, const double* acc, int k) {
+  if (kind == FK_HS_NU) {                    // hs_cg.py:120-121
+    const double nu1 = sc->nu;
+    sc->nu1 = nu1; sc->nu = acc[0];
+    sc->b = div_(acc[0], nu1);
+    note_breakdown(sc, k, sc->a, sc->b);
+  } else if (kind == FK_HS_MU) {             // hs_cg.py:124-125
+    sc->mu = acc[0];
+    sc->a1 = sc->a; sc->a = div_(sc->nu, acc[0]);
+    note_breakdown(sc, k, sc->a, sc->b);
+  } else if (kind == FK_CGGV) {              // cg_cg.py:134-136,139-140 ; gv_cg.py:162-164,169-170
+    const double nu1 = sc->nu, a1 = sc->a, nu = acc[0], eta = acc[1];
+    const double bb = div_(nu, nu1);
+    const double mu = sub_(eta, mul_(div_(bb, a1), nu));
+    sc->nu1 = nu1; sc->nu = nu; sc->eta = eta; sc->b = bb; sc->mu = mu;
+    sc->a1 = a1; sc->a = div_(nu, mu);
+    note_breakdown(sc, k, sc->a, bb);
+  } else if (kind == FK_PR_NU) {             // pr_cg.py:157 (consumed by the SpMV pass)
+    sc->nu1 = sc->nu; sc->nu = acc[0];
+  } else if (kind == FK_PR_SP) {             // pr_cg.py:154-158 then :149-150
+    const double mu = acc[0], del = acc[1], gam = acc[2], nu = sc->nu;
+    sc->mu = mu; sc->del = del; sc->gam = gam;
+    const double an = div_(nu, mu);
+    sc->a1 = sc->a; sc->a = an;
+    sc->b = predict_beta(meurant, nu, an, del, gam);
+    note_breakdown(sc, k, an, sc->b);
+  } else if (kind == FK_PIPE) {              // pipe_pr_cg.py:183-187 then :174-175
+    const double mu = acc[0], del = acc[1], gam = acc[2], nu = acc[3];
+    sc->nu1 = sc->nu; sc->nu = nu; sc->mu = mu; sc->del = del; sc->gam = gam;
+    const double an = div_(nu, mu);
+    sc->a1 = sc->a; sc->a = an;
+    sc->b = predict_beta(meurant, nu, an, del, gam);
+    note_breakdown(sc, k, an, sc->b);
+  }
+}
+
+// ---- multi-GPU scalar exchange ------------------------------------------------------
+// Producer side (ONE thread, after the grid total is known): store this rank's record of
+// epoch g.sepoch into every rank's window, fence, then publish the epoch -- and the halo
+// epoch of the planes this kernel wrote into the neighbours' ghosts.
+__device__ __forceinline__ void st_relaxed_sys(u64* p, u64 v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void dist_publish_halo_flags(const Args& g) {
+  for (int c = 0; c < g.hout_n; ++c) {
+    const int ch = g.hout_ch + c;
+    if (g.d.has_lo) st_relaxed_sys(&g.d.win[g.d.rank - 1]->hflag[ch][g.hout_par][1], g.hout_epoch);
+    if (g.d.has_hi) st_relaxed_sys(&g.d.win[g.d.rank + 1]->hflag[ch][g.hout_par][0], g.hout_epoch);
+  }
+}
+template <int NR>
+__device__ __forceinline__ void dist_publish(const Args& g, const double* acc) {
+  const int slot = (int)(g.sepoch % kSlots);
+  if (NR > 0) {
+    if (g.d.mode == 1 || g.d.mode == 3) {
+      for (int r = 0; r < g.d.world; ++r) {
+        if (g.d.mode == 3 && r != g.d.rank) continue;     // stub: the record stays local
+        volatile double* dst = g.d.win[r]->sums[slot][g.d.rank];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) dst[j] = acc[j];
+      }
+    } else {
+      volatile double* dst = g.d.nccl_in + (size_t)slot * kSumW;
+#pragma unroll
+      for (int j = 0; j < NR; ++j) dst[j] = acc[j];
+    }
+  }
+  __threadfence_system();
+  if (NR > 0 && g.d.mode == 1)
+    for (int r = 0; r < g.d.world; ++r) st_relaxed_sys(&g.d.win[r]->sflag[slot][g.d.rank], g.sepoch);
+  dist_publish_halo_flags(g);
+}
+
+// Consumer side (warp 0 of a CTA): all-rank totals of epoch e, added in rank order.
+__device__ __forceinline__ void dist_totals(const Args& g, u64 e, double (&acc)[kNRed]) {
+  const int lane = threadIdx.x & 31;
+  const int slot = (int)(e % kSlots);
+  double v[kNRed] = {0.0, 0.0, 0.0, 0.0};
+  if (g.d.mode == 1) {
+    WinHdr* w = g.d.win[g.d.rank];
+    if (lane < g.d.world) {
+      wait_epoch(&w->sflag[slot][lane], e, &w->error);
+#pragma unroll
+      for (int j = 0; j < kNRed; ++j) v[j] = __ldcv(&w->sums[slot][lane][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kNRed; ++j) {
+      double t = 0.0;
+      for (int r = 0; r < g.d.world; ++r) t += __shfl_sync(0xffffffffu, v[j], r);
+      acc[j] = t;
+    }
+  } else if (g.d.mode == 3) {
+    // timing stub ("stub_allreduce"): no exchange, no wait -- the local record times the
+    // number of ranks stands in for the total (numerically meaningless)
+    WinHdr* w = g.d.win[g.d.rank];
+#pragma unroll
+    for (int j = 0; j < kNRed; ++j) acc[j] = __ldcv(&w->sums[slot][g.d.rank][j]) * (double)g.d.world;
+  } else {
+#pragma unroll
+    for (int j = 0; j < kNRed; ++j) acc[j] = __ldcv(g.d.nccl_out + (size_t)slot * kSumW + j);
+  }
+}
+
+// Every CTA of a kernel that needs alpha/beta: fold the pending reductions into the scalars
+// (redundantly, identical bits everywhere); CTA 0 persists the result in the other parity.
+__device__ __forceinline__ void dist_scalars(const Args& g, bool meurant, double& a, double& b) {
+  __shared__ Scal sh_sc;
+  if (threadIdx.x < 32) {
+    Scal s = g.sc[g.scpar];
+    for (int q = 0; q < g.npend; ++q) {
+      double acc[kNRed];
+      dist_totals(g, g.pend_e[q], acc);
+      apply_finalize(g.pend_kind[q], meurant, &s, acc, g.pend_k[q]);
+    }
+    if (threadIdx.x == 0) {
+      sh_sc = s;
+      if (blockIdx.x == 0 && g.npend) g.sc[g.scpar ^ 1] = s;
+    }
+  }
+  __syncthreads();
+  a = sh_sc.a; b = sh_sc.b;
+}
+
+// The SpMV-input vector a vector pass produces: also store its first / last plane into the
+// ghost planes of the rank below / above (peer memory; 16-byte stores, plane is even).
+template <int W>
+__device__ __forceinline__ void halo_store(const Args& g, int c, i64 i, const Pk<W>& v) {
+  if (g.d.world > 1) {
+    const i64 pl = g.d.plane;
+    if (g.d.has_lo && i < pl) stp<W>(g.d.ghost_lo + ghost_off(g.d, g.hout_ch + c, g.hout_par, 1), i, v);
+    if (g.d.has_hi && i >= g.n - pl)
+      stp<W>(g.d.ghost_hi + ghost_off(g.d, g.hout_ch + c, g.hout_par, 0), i - (g.n - pl), v);
+  }
+}
+// Generic (non-TMA) consumers: one thread waits for the ghost planes of channels
+// hin_ch .. hin_ch+nch-1 before the CTA reads them.
+__device__ __forceinline__ void halo_wait_all(const Args& g, int nch) {
+  if (g.d.world > 1) {
+    if (threadIdx.x == 0) {
+      WinHdr* w = g.d.win[g.d.rank];
+      for (int c = 0; c < nch; ++c) {
+        if (g.d.has_lo) wait_epoch(&w->hflag[g.hin_ch + c][g.hin_par][0], g.hin_epoch, &w->error);
+        if (g.d.has_hi) wait_epoch(&w->hflag[g.hin_ch + c][g.hin_par][1], g.hin_epoch, &w->error);
+      }
+    }
+    __syncthreads();
+  }
 }
 
 // -------------------------------------------------------------------------------------
@@ -137,6 +319,7 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
       p.v[l] = axpy_(M(r.v[l], l), b, p.v[l]);
     }
     stp<W>(g.x, i, x); stp<W>(g.p, i, p);
+    halo_store<W>(g, 0, i, p);
   } else if constexpr (KID == EW_CG) {       // cg_cg.py:137-138 (deferred), :130-132
     Pk<W> x = ldp<W>(g.x, i), r = ldp<W>(g.r, i), rt = ldp<W>(g.rt, i), p = ldp<W>(g.p, i),
           s = ldp<W>(g.s, i), w = ldp<W>(g.w, i);
@@ -150,6 +333,7 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
     }
     stp<W>(g.p, i, p); stp<W>(g.s, i, s); stp<W>(g.x, i, x); stp<W>(g.r, i, r);
     stp<W>(g.rt, i, rt);
+    halo_store<W>(g, 0, i, rt);
   } else if constexpr (KID == EW_GV) {       // gv_cg.py:165-168 (deferred), :151-154,160,162-163
     Pk<W> x = ldp<W>(g.x, i), r = ldp<W>(g.r, i), rt = ldp<W>(g.rt, i), p = ldp<W>(g.p, i),
           s = ldp<W>(g.s, i), st = ldp<W>(g.st, i), w = ldp<W>(g.w, i), wt = ldp<W>(g.wt, i),
@@ -171,6 +355,7 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
     stp<W>(g.p, i, p); stp<W>(g.s, i, s); stp<W>(g.st, i, st); stp<W>(g.u, i, u);
     stp<W>(g.x, i, x); stp<W>(g.r, i, r); stp<W>(g.rt, i, rt); stp<W>(g.w, i, w);
     stp<W>(g.wt, i, wt);
+    halo_store<W>(g, 0, i, wt);
   } else if constexpr (KID == EW_PR) {       // pr_cg.py:146-148,151,157
     Pk<W> x = ldp<W>(g.x, i), r = ldp<W>(g.r, i), rt = ldp<W>(g.rt, i), p = ldp<W>(g.p, i),
           s = ldp<W>(g.s, i);
@@ -183,6 +368,7 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
       red[0] = fma(rt.v[l], r.v[l], red[0]);
     }
     stp<W>(g.x, i, x); stp<W>(g.r, i, r); stp<W>(g.rt, i, rt); stp<W>(g.p, i, p);
+    halo_store<W>(g, 0, i, p);
   } else {                                   // pipe_pr_cg.py:169-178,183-186
     constexpr bool RECOMP = (KID == EW_PIPE_R);
     Pk<W> x = ldp<W>(g.x, i), r = ldp<W>(g.r, i), rt = ldp<W>(g.rt, i), p = ldp<W>(g.p, i),
@@ -212,6 +398,8 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
     }
     stp<W>(g.x, i, x); stp<W>(g.r, i, r); stp<W>(g.rt, i, rt); stp<W>(g.p, i, p);
     stp<W>(g.s, i, s); stp<W>(g.st, i, st);
+    halo_store<W>(g, 0, i, st);
+    if constexpr (RECOMP) halo_store<W>(g, 1, i, rt);
     if constexpr (!RECOMP) {
       stp<W>(g.w, i, w);
       if constexpr (PREC) stp<W>(g.wt, i, wt);
@@ -219,9 +407,19 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
   }
 }
 
+template <int KID> struct EwKind { static constexpr int FK = FK_NONE; };
+template <> struct EwKind<EW_HS1> { static constexpr int FK = FK_HS_NU; };
+template <> struct EwKind<EW_GV> { static constexpr int FK = FK_CGGV; };
+template <> struct EwKind<EW_PR> { static constexpr int FK = FK_PR_NU; };
+template <> struct EwKind<EW_PIPE_R> { static constexpr int FK = FK_PIPE; };
+template <> struct EwKind<EW_PIPE_N> { static constexpr int FK = FK_PIPE; };
+
 template <int KID, int PM, bool MEURANT>
 __global__ void __launch_bounds__(kBlock) ew_kernel(const Args g) {
-  const double a = g.sc->a, b = g.sc->b;
+  const bool dist = g.d.world > 1;
+  double a, b;
+  if (dist) dist_scalars(g, MEURANT, a, b);
+  else { a = g.sc->a; b = g.sc->b; }
   double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
   const i64 nv = g.n >> 1;
   const i64 stride = (i64)gridDim.x * kBlock;
@@ -235,127 +433,162 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(const Args g) {
     double v[NR];
 #pragma unroll
     for (int j = 0; j < NR; ++j) v[j] = red[j];
-    Scal* sc = g.sc;
-    const int k = g.k;
-    grid_sum_finalize<NR>(v, g.partials, g.ticket, [=](const double* acc) {
-      if constexpr (KID == EW_HS1) {            // hs_cg.py:120-121
-        const double nu1 = sc->nu;
-        sc->nu1 = nu1; sc->nu = acc[0];
-        sc->b = div_(acc[0], nu1);
-        note_breakdown(sc, k, sc->a, sc->b);
-      } else if constexpr (KID == EW_GV) {      // gv_cg.py:162-164,169-170
-        const double nu1 = sc->nu, a1 = sc->a, nu = acc[0], eta = acc[1];
-        const double bb = div_(nu, nu1);
-        const double mu = sub_(eta, mul_(div_(bb, a1), nu));
-        sc->nu1 = nu1; sc->nu = nu; sc->eta = eta; sc->b = bb; sc->mu = mu;
-        sc->a1 = a1; sc->a = div_(nu, mu);
-        note_breakdown(sc, k, sc->a, bb);
-      } else if constexpr (KID == EW_PR) {      // pr_cg.py:157 (consumed by the SpMV pass)
-        sc->nu1 = sc->nu; sc->nu = acc[0];
-      } else {                                  // pipe_pr_cg.py:183-187 then :174-175
-        const double mu = acc[0], del = acc[1], gam = acc[2], nu = acc[3];
-        sc->nu1 = sc->nu; sc->nu = nu; sc->mu = mu; sc->del = del; sc->gam = gam;
-        const double an = div_(nu, mu);
-        sc->a1 = sc->a; sc->a = an;
-        sc->b = predict_beta(MEURANT, nu, an, del, gam);
-        note_breakdown(sc, k, an, sc->b);
-      }
-    });
+    grid_sum_finalize<NR>(v, g.partials, g.ticket, [&](const double* acc) {
+      if (dist) dist_publish<NR>(g, acc);
+      else apply_finalize(EwKind<KID>::FK, MEURANT, g.sc, acc, g.k);
+    }, dist);
+  } else {
+    if (dist && g.hout_n > 0) grid_last_finalize(g.ticket, [&]() { dist_publish<0>(g, nullptr); });
   }
 }
 
 // -------------------------------------------------------------------------------------
 // Fused SpMV pass: one sweep over the matrix (or stencil) with the stage's epilogue.
 // -------------------------------------------------------------------------------------
-template <int MODE> struct SpTraits { static constexpr int NR = 0; };
-template <> struct SpTraits<SP_HS> { static constexpr int NR = 1; };
-template <> struct SpTraits<SP_CG> { static constexpr int NR = 2; };
-template <> struct SpTraits<SP_PR> { static constexpr int NR = 3; };
+template <int MODE> struct SpTraits { static constexpr int NR = 0, FK = FK_NONE, NV = 1; };
+template <> struct SpTraits<SP_HS> { static constexpr int NR = 1, FK = FK_HS_MU, NV = 1; };
+template <> struct SpTraits<SP_CG> { static constexpr int NR = 2, FK = FK_CGGV, NV = 1; };
+template <> struct SpTraits<SP_PR> { static constexpr int NR = 3, FK = FK_PR_SP, NV = 1; };
+template <> struct SpTraits<SP_PIPE_R> { static constexpr int NR = 0, FK = FK_NONE, NV = 2; };
 
-// Scalar recurrences that close a fused SpMV pass (run by one thread with the grid totals).
+// Close a fused SpMV pass: single GPU -> scalar recurrences now; multi-GPU -> publish the
+// rank's record (the next vector pass folds all ranks' records).
 template <int MODE, bool MEURANT>
-__device__ __forceinline__ void spmv_finalize(Scal* sc, int k, const double* acc) {
-  if constexpr (MODE == SP_HS) {             // hs_cg.py:124-125
-    sc->mu = acc[0];
-    sc->a1 = sc->a; sc->a = div_(sc->nu, acc[0]);
-    note_breakdown(sc, k, sc->a, sc->b);
-  } else if constexpr (MODE == SP_CG) {      // cg_cg.py:134-136,139-140
-    const double nu1 = sc->nu, a1 = sc->a, nu = acc[0], eta = acc[1];
-    const double bb = div_(nu, nu1);
-    const double mu = sub_(eta, mul_(div_(bb, a1), nu));
-    sc->nu1 = nu1; sc->nu = nu; sc->eta = eta; sc->b = bb; sc->mu = mu;
-    sc->a1 = a1; sc->a = div_(nu, mu);
-    note_breakdown(sc, k, sc->a, bb);
-  } else if constexpr (MODE == SP_PR) {      // pr_cg.py:154-158 then :149-150
-    const double mu = acc[0], del = acc[1], gam = acc[2], nu = sc->nu;
-    sc->mu = mu; sc->del = del; sc->gam = gam;
-    const double an = div_(nu, mu);
-    sc->a1 = sc->a; sc->a = an;
-    sc->b = predict_beta(MEURANT, nu, an, del, gam);
-    note_breakdown(sc, k, an, sc->b);
-  }
-}
-
-template <class Op, int MODE, int PM, bool MEURANT>
-__global__ void __launch_bounds__(kBlock) spmv_kernel(const Op A, const Args g, const double* vin,
-                                                     double* vout) {
-  double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
-  const i64 stride = (i64)gridDim.x * kBlock;
-  for (i64 i = (i64)blockIdx.x * kBlock + threadIdx.x; i < g.n; i += stride) {
-    if constexpr (MODE == SP_PLAIN) {            // y = A v
-      double y[1];
-      A.template row<1>(i, [&](i64 j, double (&v)[1]) { v[0] = vin[j]; }, y);
-      vout[i] = y[0];
-    } else if constexpr (MODE == SP_RESID) {     // r = b - A x0   (e.g. hs_cg.py:84)
-      double y[1];
-      A.template row<1>(i, [&](i64 j, double (&v)[1]) { v[0] = vin[j]; }, y);
-      vout[i] = sub_(g.b[i], y[0]);
-    } else if constexpr (MODE == SP_HS) {        // hs_cg.py:123-124
-      double y[1];
-      A.template row<1>(i, [&](i64 j, double (&v)[1]) { v[0] = g.p[j]; }, y);
-      g.s[i] = y[0];
-      red[0] = fma(g.p[i], y[0], red[0]);
-    } else if constexpr (MODE == SP_CG) {        // cg_cg.py:133-135
-      double y[1];
-      A.template row<1>(i, [&](i64 j, double (&v)[1]) { v[0] = g.rt[j]; }, y);
-      g.w[i] = y[0];
-      const double rti = g.rt[i];
-      red[0] = fma(g.r[i], rti, red[0]);
-      red[1] = fma(y[0], rti, red[1]);
-    } else if constexpr (MODE == SP_GV) {        // gv_cg.py:161
-      double y[1];
-      A.template row<1>(i, [&](i64 j, double (&v)[1]) { v[0] = g.wt[j]; }, y);
-      g.t[i] = y[0];
-    } else if constexpr (MODE == SP_PR) {        // pr_cg.py:152-156
-      double y[1];
-      A.template row<1>(i, [&](i64 j, double (&v)[1]) { v[0] = g.p[j]; }, y);
-      g.s[i] = y[0];
-      const double sti = PM == 1 ? mul_(g.dinv[i], y[0]) : (PM == 2 ? mul_(g.dinv_s, y[0]) : y[0]);
-      red[0] = fma(g.p[i], y[0], red[0]);
-      red[1] = fma(g.r[i], sti, red[1]);
-      red[2] = fma(sti, y[0], red[2]);
-    } else if constexpr (MODE == SP_PIPE_R) {    // pipe_pr_cg.py:179-182: one matrix pass, 2 RHS
-      double y[2];
-      A.template row<2>(i, [&](i64 j, double (&v)[2]) { v[0] = g.st[j]; v[1] = g.rt[j]; }, y);
-      g.u[i] = y[0];
-      g.w[i] = y[1];
-    } else {                                     // SP_PIPE_N: pipe_pr_cg.py:179-180
-      double y[1];
-      A.template row<1>(i, [&](i64 j, double (&v)[1]) { v[0] = g.st[j]; }, y);
-      g.u[i] = y[0];
-    }
-  }
+__device__ __forceinline__ void spmv_close(const Args& g, double (&red)[kNRed]) {
   constexpr int NR = SpTraits<MODE>::NR;
   if constexpr (NR > 0) {
+    const bool dist = g.d.world > 1;
     double v[NR];
 #pragma unroll
     for (int j = 0; j < NR; ++j) v[j] = red[j];
-    Scal* sc = g.sc;
-    const int k = g.k;
-    grid_sum_finalize<NR>(v, g.partials, g.ticket, [=](const double* acc) {
-      spmv_finalize<MODE, MEURANT>(sc, k, acc);
-    });
+    grid_sum_finalize<NR>(v, g.partials, g.ticket, [&](const double* acc) {
+      if (dist) dist_publish<NR>(g, acc);
+      else apply_finalize(SpTraits<MODE>::FK, MEURANT, g.sc, acc, g.k);
+    }, false);
   }
+}
+
+// What a fused SpMV pass does with row i once y = (A in0)_i [, (A in1)_i] is known.
+// in0 / in1: the SpMV input vector(s) of the stage (p | rt | wt | st [, rt]); for SP_PLAIN
+// and SP_RESID any vector.  vout: output of SP_PLAIN / SP_RESID.
+template <int MODE, int PM, int NV>
+__device__ __forceinline__ void sp_epilogue(const Args& g, const VecIn& in0, i64 i, const double (&y)[NV],
+                                            double (&red)[kNRed], double* vout) {
+  if constexpr (MODE == SP_PIPE_R) {           // pipe_pr_cg.py:179-182: one matrix pass, 2 RHS
+    g.u[i] = y[0];
+    g.w[i] = y[NV - 1];
+  } else if constexpr (MODE == SP_PLAIN) {     // y = A v
+    vout[i] = y[0];
+  } else if constexpr (MODE == SP_RESID) {     // r = b - A x0   (e.g. hs_cg.py:84)
+    vout[i] = sub_(g.b[i], y[0]);
+  } else if constexpr (MODE == SP_HS) {        // hs_cg.py:123-124
+    g.s[i] = y[0];
+    red[0] = fma(in0.v[i], y[0], red[0]);
+  } else if constexpr (MODE == SP_CG) {        // cg_cg.py:133-135
+    g.w[i] = y[0];
+    const double rti = in0.v[i];
+    red[0] = fma(g.r[i], rti, red[0]);
+    red[1] = fma(y[0], rti, red[1]);
+  } else if constexpr (MODE == SP_GV) {        // gv_cg.py:161
+    g.t[i] = y[0];
+  } else if constexpr (MODE == SP_PR) {        // pr_cg.py:152-156
+    g.s[i] = y[0];
+    const double sti = PM == 1 ? mul_(g.dinv[i], y[0]) : (PM == 2 ? mul_(g.dinv_s, y[0]) : y[0]);
+    red[0] = fma(in0.v[i], y[0], red[0]);
+    red[1] = fma(g.r[i], sti, red[1]);
+    red[2] = fma(sti, y[0], red[2]);
+  } else {                                     // SP_PIPE_N: pipe_pr_cg.py:179-180
+    g.u[i] = y[0];
+  }
+}
+
+// Generic pass: one thread per row (matrix-free stencil without TMA, slabs included).
+template <class Op, int MODE, int PM, bool MEURANT>
+__global__ void __launch_bounds__(kBlock) spmv_kernel(const Op A, const Args g, const VecIn in0,
+                                                     const VecIn in1, double* vout) {
+  constexpr bool SL = Op::kSlab;
+  constexpr int NV = SpTraits<MODE>::NV;
+  halo_wait_all(g, NV);
+  double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
+  const i64 n = g.n, pl = g.d.plane;
+  const i64 stride = (i64)gridDim.x * kBlock;
+  for (i64 i = (i64)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+    double y[NV];
+    A.template row<NV>(i, [&](i64 j, double (&v)[NV]) {
+      v[0] = vload<SL>(in0, j, n, pl);
+      if constexpr (NV == 2) v[1] = vload<SL>(in1, j, n, pl);
+    }, y);
+    sp_epilogue<MODE, PM, NV>(g, in0, i, y, red, vout);
+  }
+  spmv_close<MODE, MEURANT>(g, red);
+}
+
+// CSR pass ("CSR-stream"): a CTA owns a block of consecutive rows holding at most kCsrCap
+// non-zeros (host-built row_blocks).  The whole CTA streams that contiguous range of
+// (value, column) pairs with coalesced loads, forms the products a_ij * v_j into shared memory,
+// then thread t adds up row t's products IN STORED ORDER -- the matrix is read at full
+// width whatever the row lengths (1 .. 81 in matrices/), and the row sums keep scipy's
+// csr_matvec rounding exactly.  A row longer than kCsrCap is a block of its own, summed in
+// order by one thread chunk after chunk.
+constexpr int kCsrCap = 2048;
+
+template <int MODE, int PM, bool MEURANT>
+__global__ void __launch_bounds__(kBlock) csr_stream_kernel(const CsrOp A, const int* __restrict__ row_blocks,
+                                                           int nblocks, const Args g, const VecIn in0,
+                                                           const VecIn in1, double* vout) {
+  constexpr int NV = SpTraits<MODE>::NV;
+  __shared__ double prod[NV][kCsrCap];
+  double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
+  const int tid = threadIdx.x;
+  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int r0 = __ldg(row_blocks + blk), r1 = __ldg(row_blocks + blk + 1);
+    const int e0 = __ldg(A.ptr + r0), e1 = __ldg(A.ptr + r1);
+    const int cnt = e1 - e0;
+    if (cnt <= kCsrCap) {
+      for (int j = tid; j < cnt; j += kBlock) {
+        const double a = __ldg(A.val + e0 + j);
+        const int col = __ldg(A.idx + e0 + j);
+        prod[0][j] = mul_(a, in0.v[col]);
+        if constexpr (NV == 2) prod[1][j] = mul_(a, in1.v[col]);
+      }
+      __syncthreads();
+      const int row = r0 + tid;
+      if (row < r1) {
+        const int b0 = __ldg(A.ptr + row) - e0, b1 = __ldg(A.ptr + row + 1) - e0;
+        double y[NV];
+#pragma unroll
+        for (int c = 0; c < NV; ++c) y[c] = 0.0;
+        for (int j = b0; j < b1; ++j) {
+#pragma unroll
+          for (int c = 0; c < NV; ++c) y[c] = add_(y[c], prod[c][j]);
+        }
+        sp_epilogue<MODE, PM, NV>(g, in0, (i64)row, y, red, vout);
+      }
+      __syncthreads();
+    } else {                                   // one long row
+      double y[NV];
+#pragma unroll
+      for (int c = 0; c < NV; ++c) y[c] = 0.0;
+      for (int base = 0; base < cnt; base += kCsrCap) {
+        const int m = min(kCsrCap, cnt - base);
+        for (int j = tid; j < m; j += kBlock) {
+          const double a = __ldg(A.val + e0 + base + j);
+          const int col = __ldg(A.idx + e0 + base + j);
+          prod[0][j] = mul_(a, in0.v[col]);
+          if constexpr (NV == 2) prod[1][j] = mul_(a, in1.v[col]);
+        }
+        __syncthreads();
+        if (tid == 0)
+          for (int j = 0; j < m; ++j) {
+#pragma unroll
+            for (int c = 0; c < NV; ++c) y[c] = add_(y[c], prod[c][j]);
+          }
+        __syncthreads();
+      }
+      if (tid == 0) sp_epilogue<MODE, PM, NV>(g, in0, (i64)r0, y, red, vout);
+    }
+  }
+  spmv_close<MODE, MEURANT>(g, red);
 }
 
 // -------------------------------------------------------------------------------------
@@ -363,22 +596,34 @@ __global__ void __launch_bounds__(kBlock) spmv_kernel(const Op A, const Args g, 
 //   e = x - x_true ; error_A_norm = sqrt(e.(A e)) ; residual_2_norm = ||b - A x|| ;
 //   error_2_norm = ||e|| ; updated_residual_2_norm = ||r||.
 // Excluded from the roofline traffic model.
+// Multi-GPU: xin / xtin carry the ghost planes of x (channel hin_ch) and x_true
+// (channel 3, exchanged once when the problem is loaded); the record is published and
+// hist_consume_kernel writes the history entry.
 // -------------------------------------------------------------------------------------
 template <class Op, bool HAS_XTRUE>
-__global__ void __launch_bounds__(kBlock) instrument_kernel(const Op A, const Args g) {
+__global__ void __launch_bounds__(kBlock) instrument_kernel(const Op A, const Args g, const VecIn xin,
+                                                           const VecIn xtin) {
+  constexpr bool SL = Op::kSlab;
+  if (HAS_XTRUE && g.d.world > 1 && threadIdx.x == 0) {
+    WinHdr* w = g.d.win[g.d.rank];
+    if (g.d.has_lo) wait_epoch(&w->hflag[3][g.xt_par][0], g.xt_epoch, &w->error);
+    if (g.d.has_hi) wait_epoch(&w->hflag[3][g.xt_par][1], g.xt_epoch, &w->error);
+  }
+  halo_wait_all(g, 1);
   double red[4] = {0.0, 0.0, 0.0, 0.0};
+  const i64 n = g.n, pl = g.d.plane;
   const i64 stride = (i64)gridDim.x * kBlock;
-  for (i64 i = (i64)blockIdx.x * kBlock + threadIdx.x; i < g.n; i += stride) {
+  for (i64 i = (i64)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
     double y[2] = {0.0, 0.0};
     if constexpr (HAS_XTRUE) {
       A.template row<2>(i, [&](i64 j, double (&v)[2]) {
-        v[0] = g.x[j]; v[1] = sub_(v[0], g.xtrue[j]); }, y);
+        v[0] = vload<SL>(xin, j, n, pl); v[1] = sub_(v[0], vload<SL>(xtin, j, n, pl)); }, y);
       const double e = sub_(g.x[i], g.xtrue[i]);
       red[0] = fma(e, y[1], red[0]);
       red[2] = fma(e, e, red[2]);
     } else {
       double y1[1];
-      A.template row<1>(i, [&](i64 j, double (&v)[1]) { v[0] = g.x[j]; }, y1);
+      A.template row<1>(i, [&](i64 j, double (&v)[1]) { v[0] = vload<SL>(xin, j, n, pl); }, y1);
       y[0] = y1[0];
     }
     const double res = sub_(g.b[i], y[0]);
@@ -386,14 +631,42 @@ __global__ void __launch_bounds__(kBlock) instrument_kernel(const Op A, const Ar
     const double ri = g.r[i];
     red[3] = fma(ri, ri, red[3]);
   }
-  double* hist = g.hist;
-  const int L = g.hist_len, k = g.k;
-  const unsigned mask = g.hist_mask;
-  grid_sum_finalize<4>(red, g.partials, g.ticket, [=](const double* acc) {
+  const bool dist = g.d.world > 1;
+  grid_sum_finalize<4>(red, g.partials, g.ticket, [&](const double* acc) {
+    if (dist) { dist_publish<4>(g, acc); return; }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (mask & (1u << j)) hist[(i64)j * L + k] = sqrt(acc[j]);
+      if (g.hist_mask & (1u << j)) g.hist[(i64)j * g.hist_len + g.k] = sqrt(acc[j]);
   });
+}
+
+// multi-GPU: fold all ranks' instrumentation records of epoch pend_e[0] into history entry k
+__global__ void hist_consume_kernel(const Args g) {
+  double acc[kNRed];
+  dist_totals(g, g.pend_e[0], acc);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (g.hist_mask & (1u << j)) g.hist[(i64)j * g.hist_len + g.k] = sqrt(acc[j]);
+  }
+}
+
+// multi-GPU: fold the pending reductions into the persisted scalars (end of cgx_advance)
+__global__ void flush_scalars_kernel(const Args g) {
+  double a, b;
+  dist_scalars(g, g.meur != 0, a, b);
+}
+
+// multi-GPU: copy the first / last plane of v into the neighbours' ghost planes of channel
+// hout_ch (initialisation SpMVs, instrumentation x, x_true) and publish the halo epoch.
+__global__ void __launch_bounds__(kBlock) halo_push_kernel(const Args g, const double* __restrict__ v) {
+  const i64 pl = g.d.plane;
+  const i64 stride = (i64)gridDim.x * kBlock;
+  for (i64 i = (i64)blockIdx.x * kBlock + threadIdx.x; i < pl; i += stride) {
+    if (g.d.has_lo) g.d.ghost_lo[ghost_off(g.d, g.hout_ch, g.hout_par, 1) + i] = v[i];
+    if (g.d.has_hi) g.d.ghost_hi[ghost_off(g.d, g.hout_ch, g.hout_par, 0) + i] = v[g.n - pl + i];
+  }
+  grid_last_finalize(g.ticket, [&]() { dist_publish<0>(g, nullptr); });
 }
 
 // -------------------------------------------------------------------------------------
@@ -407,7 +680,7 @@ __global__ void __launch_bounds__(kBlock) scale_kernel(const double* __restrict_
     out[i] = dinv ? mul_(dinv[i], v[i]) : v[i];
 }
 
-// sc->tmp[slot] = u . (dinv ? dinv*v : v)
+// sc->tmp[slot] = u . (dinv ? dinv*v : v)   (multi-GPU: the rank's partial)
 __global__ void __launch_bounds__(kBlock) dot_kernel(const double* __restrict__ u,
                                                     const double* __restrict__ v,
                                                     const double* __restrict__ dinv, i64 n,
@@ -422,9 +695,50 @@ __global__ void __launch_bounds__(kBlock) dot_kernel(const double* __restrict__ 
   grid_sum_finalize<1>(red, partials, ticket, [=](const double* acc) { sc->tmp[slot] = acc[0]; });
 }
 
+// multi-GPU: publish the rank's eight initialisation partials (tmp[0..7]) as epoch sepoch
+__global__ void push_tmp_kernel(const Args g) {
+  if (threadIdx.x != 0) return;
+  const Scal* sc = g.sc + g.scpar;
+  const int slot = (int)(g.sepoch % kSlots);
+  if (g.d.mode == 1 || g.d.mode == 3) {
+    for (int r = 0; r < g.d.world; ++r) {
+      if (g.d.mode == 3 && r != g.d.rank) continue;
+      volatile double* dst = g.d.win[r]->sums[slot][g.d.rank];
+      for (int j = 0; j < kSumW; ++j) dst[j] = sc->tmp[j];
+    }
+    __threadfence_system();
+    if (g.d.mode == 1)
+      for (int r = 0; r < g.d.world; ++r) st_relaxed_sys(&g.d.win[r]->sflag[slot][g.d.rank], g.sepoch);
+  } else {
+    volatile double* dst = g.d.nccl_in + (size_t)slot * kSumW;
+    for (int j = 0; j < kSumW; ++j) dst[j] = sc->tmp[j];
+  }
+}
+
 // Initial scalars from the initialisation dots.  tmp: 0 nu, 1 mu, 2 eta, 3 delta, 4 gamma.
-__global__ void init_scalars_kernel(Scal* sc, int variant_class, int meurant) {
-  // variant_class: 0 HS, 1 CG/GV (mu := p.s), 2 PR/M/pipe (predict first beta)
+// variant_class: 0 HS, 1 CG/GV (mu := p.s), 2 PR/M/pipe (predict first beta).
+// Multi-GPU (g.d.world > 1): tmp[] first becomes the all-rank total of epoch pend_e[0].
+__global__ void init_scalars_kernel(const Args g, int variant_class, int meurant) {
+  if (threadIdx.x != 0) return;
+  Scal* sc = g.sc + g.scpar;
+  if (g.d.world > 1) {
+    const int slot = (int)(g.pend_e[0] % kSlots);
+    double acc[kSumW];
+    for (int j = 0; j < kSumW; ++j) acc[j] = 0.0;
+    if (g.d.mode == 1) {
+      WinHdr* w = g.d.win[g.d.rank];
+      for (int r = 0; r < g.d.world; ++r) {
+        wait_epoch(&w->sflag[slot][r], g.pend_e[0], &w->error);
+        for (int j = 0; j < kSumW; ++j) acc[j] += __ldcv(&w->sums[slot][r][j]);
+      }
+    } else if (g.d.mode == 3) {
+      WinHdr* w = g.d.win[g.d.rank];
+      for (int j = 0; j < kSumW; ++j) acc[j] = __ldcv(&w->sums[slot][g.d.rank][j]) * (double)g.d.world;
+    } else {
+      for (int j = 0; j < kSumW; ++j) acc[j] = __ldcv(g.d.nccl_out + (size_t)slot * kSumW + j);
+    }
+    for (int j = 0; j < kSumW; ++j) sc->tmp[j] = acc[j];
+  }
   const double nu = sc->tmp[0], mu = sc->tmp[1];
   sc->nu = nu; sc->nu1 = nu; sc->mu = mu; sc->eta = sc->tmp[2];
   sc->del = sc->tmp[3]; sc->gam = sc->tmp[4];

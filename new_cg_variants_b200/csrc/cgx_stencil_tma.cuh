@@ -80,12 +80,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 }
 
 // Geometry of one launch.  zlo/zhi: does a plane exist below z=0 / above z=nz-1 of THIS
-// slab (ghost planes of a multi-GPU partition; the tensor map then covers them and
-// zoff = 1 shifts local plane z to tensor coordinate z + 1).
+// slab (multi-GPU partition).  Those ghost planes live in the rank's window, written by the
+// neighbours, and are fetched through a second tensor map (nx, ny, 4) whose z coordinate is
+// parity*2 + side, after the halo epoch of that side has been published.
 struct TmaGeom {
   int nx, ny, nz;
   int ntx, nty, nchunks, lz;     // tiles in x, y; z-chunks; planes per chunk
-  int zoff;                      // tensor z coordinate of local plane 0
   int has_zlo, has_zhi;
   double diag, off;
 };
@@ -94,6 +94,7 @@ struct TmaGeom {
 template <int MODE, int PM, bool MEUR>
 __global__ void __launch_bounds__(kTmaThreads)
 stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                   const __grid_constant__ CUtensorMap tg0, const __grid_constant__ CUtensorMap tg1,
                    const TmaGeom G, const Args g) {
   constexpr int NV = (MODE == SP_PIPE_R) ? 2 : 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -143,9 +144,19 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         return;
       }
       double* dst = smem + (size_t)slot * NV * kPlaneStride;
+      if (z < 0 || z >= G.nz) {                     // ghost plane: written by a neighbour rank
+        const int side = z < 0 ? 0 : 1;
+        WinHdr* w = g.d.win[g.d.rank];
+        for (int c = 0; c < NV; ++c) wait_epoch(&w->hflag[g.hin_ch + c][g.hin_par][side], g.hin_epoch, &w->error);
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_arrive_expect_tx(&bar[slot], kBytes);
+        tma_load_3d(dst, &tg0, x0 - 2, y0 - 1, g.hin_par * 2 + side, &bar[slot]);
+        if constexpr (NV == 2) tma_load_3d(dst + kPlaneStride, &tg1, x0 - 2, y0 - 1, g.hin_par * 2 + side, &bar[slot]);
+        return;
+      }
       mbar_arrive_expect_tx(&bar[slot], kBytes);
-      tma_load_3d(dst, &tm0, x0 - 2, y0 - 1, z + G.zoff, &bar[slot]);
-      if constexpr (NV == 2) tma_load_3d(dst + kPlaneStride, &tm1, x0 - 2, y0 - 1, z + G.zoff, &bar[slot]);
+      tma_load_3d(dst, &tm0, x0 - 2, y0 - 1, z, &bar[slot]);
+      if constexpr (NV == 2) tma_load_3d(dst + kPlaneStride, &tm1, x0 - 2, y0 - 1, z, &bar[slot]);
     };
     auto wait_load = [&](uint32_t li) { mbar_wait(&bar[li % kRing], (li / kRing) & 1u); };
 
@@ -243,17 +254,7 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     L = Lbase + (uint32_t)(z1 - z0) + 2;   // planes z0-1 .. z1 were issued
   }
 
-  constexpr int NR = SpTraits<MODE>::NR;
-  if constexpr (NR > 0) {
-    double v[NR];
-#pragma unroll
-    for (int j = 0; j < NR; ++j) v[j] = red[j];
-    Scal* sc = g.sc;
-    const int k = g.k;
-    grid_sum_finalize<NR>(v, g.partials, g.ticket, [=](const double* acc) {
-      spmv_finalize<MODE, MEUR>(sc, k, acc);
-    });
-  }
+  spmv_close<MODE, MEUR>(g, red);
 }
 
 }  // namespace cgx

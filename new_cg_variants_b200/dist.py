@@ -1,0 +1,334 @@
+"""Row-partitioned multi-GPU runs: z-slabs of the Poisson grid, one
+rank per GPU, halo planes by peer-to-peer stores over NVLink, the fused scalars summed in
+rank order on every GPU.
+
+``DistSession``  one rank of a torchrun job (one process per GPU); ``torch.distributed`` is
+                 used only to hand the 64-byte window handles (and the NCCL id) around and
+                 for barriers -- never on the data path.
+``GroupSession`` the same partition driven from one process (all ranks on one GPU sharing a
+                 stream, or one context per visible GPU): how the protocol is tested on a
+                 single GPU, bit-identical to the multi-process run.
+
+The reference's distributed solvers are ``scaling_experiments_mpi4py/cg_variants/*.py``
+(column blocks + an Allreduce of the whole vector, hs_cg.py:49-51); the row/slab layout
+follows its PETSc driver (ex2b.c:71).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from .operators import PoissonStencil
+from .session import _f64
+
+MODES = {"p2p": 1, "nccl": 2}
+
+
+# ---------------------------------------------------------------------------------------
+# host-side partition logic (pure Python; covered by the CPU tests)
+# ---------------------------------------------------------------------------------------
+def slab_grid(S: PoissonStencil):
+    """(nx, ny, nz) of the 3-D slab view of a stencil operator: a 2-D nx x ny grid is the
+    3-D grid nx x 1 x ny (same canonical term order: y-1, x-1, c, x+1, y+1)."""
+    if S.dim == 3:
+        return S.nx, S.ny, S.nz
+    return S.nx, 1, S.ny
+
+
+def partition_planes(nz: int, world: int):
+    """Contiguous plane ranges [z0, z1) per rank, sizes differing by at most one."""
+    if world < 1 or nz < world:
+        raise ValueError(f"cannot cut {nz} planes into {world} non-empty slabs")
+    base, extra = divmod(nz, world)
+    out, z = [], 0
+    for r in range(world):
+        m = base + (1 if r < extra else 0)
+        out.append((z, z + m))
+        z += m
+    return out
+
+
+def row_range(S: PoissonStencil, world: int, rank: int):
+    nx, ny, nz = slab_grid(S)
+    z0, z1 = partition_planes(nz, world)[rank]
+    return z0 * nx * ny, z1 * nx * ny
+
+
+def nccl_library_path():
+    """libnccl.so.2 bundled with torch (the library this process already has loaded)."""
+    try:
+        import nvidia.nccl
+        base = os.path.dirname(nvidia.nccl.__file__) if getattr(nvidia.nccl, "__file__", None) \
+            else list(nvidia.nccl.__path__)[0]
+        p = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(p):
+            return p
+    except Exception:
+        pass
+    return "libnccl.so.2"
+
+
+def exchange_bytes(payload: bytes, group=None):
+    """all-gather one bytes object per rank through torch.distributed (any backend)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = [None] * world
+    dist.all_gather_object(out, payload, group=group)
+    return out
+
+
+def _mask(histories):
+    m = 0
+    for h in histories:
+        m |= _lib.HIST_BITS[h]
+    return m
+
+
+class _RankBase:
+    """Shared by DistSession / the members of a GroupSession."""
+
+    def _create(self, S, world, rank, device):
+        if not isinstance(S, PoissonStencil):
+            raise NotImplementedError("row-partitioned runs take a PoissonStencil operator "
+                                      "(CSR matrices of the reference are single-GPU cases)")
+        self._lib = _lib.load()
+        self.S, self.world, self.rank, self.device = S, int(world), int(rank), int(device)
+        self.n_global = S.shape[0]
+        nx, ny, nz = slab_grid(S)
+        z0, z1 = partition_planes(nz, self.world)[self.rank]
+        self.row0, self.row1 = z0 * nx * ny, z1 * nx * ny
+        self.n = self.row1 - self.row0
+        self._ctx = C.c_void_p()
+        _lib.check(self._lib.cgx_ctx_create(self.device, C.byref(self._ctx)))
+        _lib.check(self._lib.cgx_set_stencil_slab(self._ctx, nx, ny, z1 - z0, self.world, self.rank,
+                                                  S.diag, S.off))
+        self.info = None
+        self._max_iter = 0
+
+    def _set_jacobi(self, dinv):
+        if dinv is None:
+            _lib.check(self._lib.cgx_set_jacobi_host(self._ctx, None, self.n))
+        else:
+            d = _f64(dinv, self.n_global, "dinv")[self.row0:self.row1].copy()
+            _lib.check(self._lib.cgx_set_jacobi_host(self._ctx, _lib.dptr(d), self.n))
+
+    def local(self, v):
+        return None if v is None else np.ascontiguousarray(_f64(v, self.n_global)[self.row0:self.row1])
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.cgx_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def get_info(self):
+        info = _lib.CgxInfo()
+        _lib.check(self._lib.cgx_get_info(self._ctx, C.byref(info)))
+        self.info = info.as_dict()
+        return self.info
+
+    def fetch_local(self, want_x=True, want_hist=True):
+        x = np.empty(self.n) if want_x else None
+        hist = np.empty((len(_lib.HIST_NAMES), self._max_iter)) if want_hist else None
+        _lib.check(self._lib.cgx_fetch_host(self._ctx, _lib.dptr(x), _lib.dptr(hist)))
+        return x, hist
+
+    def scalars(self):
+        out = np.zeros(9)
+        _lib.check(self._lib.cgx_get_scalars(self._ctx, _lib.dptr(out)))
+        return dict(zip(("a", "a1", "b", "nu", "nu1", "mu", "eta", "delta", "gamma"), out.tolist()))
+
+    def set_option(self, name, value):
+        _lib.check(self._lib.cgx_set_option(self._ctx, name.encode(), int(value)))
+
+
+class DistSession(_RankBase):
+    """This process's rank of a partitioned operator (``torch.distributed`` must be
+    initialised; any backend).  Every method is collective."""
+
+    def __init__(self, S, dinv=None, device=None, rank=None, world=None, mode="p2p", group=None):
+        import torch.distributed as dist
+        self.group = group
+        rank = dist.get_rank(group) if rank is None else rank
+        world = dist.get_world_size(group) if world is None else world
+        device = int(os.environ.get("LOCAL_RANK", rank)) if device is None else device
+        self._create(S, world, rank, device)
+        self.mode = mode
+        if self.world > 1:
+            handle = (C.c_ubyte * 64)()
+            _lib.check(self._lib.cgx_dist_ipc_handle(self._ctx, handle))
+            handles = exchange_bytes(bytes(handle), group)
+            for r, h in enumerate(handles):
+                if r != self.rank:
+                    buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                    _lib.check(self._lib.cgx_dist_attach_ipc(self._ctx, r, buf))
+            nid, libpath = None, None
+            if mode == "nccl":
+                libpath = nccl_library_path().encode()
+                raw = (C.c_ubyte * 128)()
+                if self.rank == 0:
+                    _lib.check(self._lib.cgx_dist_nccl_unique_id(libpath, raw))
+                ids = exchange_bytes(bytes(raw), group)
+                nid = (C.c_ubyte * 128).from_buffer_copy(ids[0])
+            _lib.check(self._lib.cgx_dist_commit(self._ctx, MODES[mode], libpath, nid))
+            dist.barrier(group)       # every window is mapped and zeroed before anyone stores into it
+        self._set_jacobi(dinv)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(self.group)
+
+    def load_problem(self, b, x0, x_true=None):
+        """GLOBAL host vectors; each rank copies its own rows."""
+        self.load_problem_local(self.local(b), self.local(x0), self.local(x_true))
+
+    def load_problem_local(self, b, x0, x_true=None):
+        _lib.check(self._lib.cgx_load_problem_host(self._ctx, _lib.dptr(b), _lib.dptr(x0),
+                                                   _lib.dptr(x_true), self.n))
+
+    def run(self, variant, max_iter, histories=(), path="auto"):
+        info = _lib.CgxInfo()
+        p = _lib.PATHS["stream" if self.world > 1 else path]
+        rc = self._lib.cgx_run(self._ctx, _lib.VARIANT_IDS[variant], int(max_iter), _mask(histories), p,
+                               C.byref(info))
+        _lib.check(rc, allow_breakdown=True)
+        self.info = info.as_dict()
+        self._max_iter = int(max_iter)
+        return self.info
+
+    def solve_local(self, variant, b_loc, x0_loc, max_iter, x_true_loc=None, histories=(), return_x=True):
+        """The C-ABI round trip with this rank's HOST slices (cgx_solve_host)."""
+        mask = _mask(histories)
+        x = np.empty(self.n) if return_x else None
+        hist = np.zeros((len(_lib.HIST_NAMES), int(max_iter))) if mask else None
+        info = _lib.CgxInfo()
+        rc = self._lib.cgx_solve_host(self._ctx, _lib.VARIANT_IDS[variant], _lib.dptr(b_loc), _lib.dptr(x0_loc),
+                                      _lib.dptr(x_true_loc), self.n, int(max_iter), mask, _lib.PATHS["stream"],
+                                      _lib.dptr(x), _lib.dptr(hist), C.byref(info))
+        _lib.check(rc, allow_breakdown=True)
+        self.info = info.as_dict()
+        self._max_iter = int(max_iter)
+        out = {}
+        for i, name in enumerate(_lib.HIST_NAMES):
+            if name in histories and (x_true_loc is not None or "error" not in name):
+                out[name] = hist[i].copy()
+        return x, out, self.info
+
+    def solve(self, variant, b, x0, max_iter, x_true=None, histories=_lib.HIST_NAMES, return_x=True):
+        return self.solve_local(variant, self.local(b), self.local(x0), max_iter, self.local(x_true),
+                                histories, return_x)
+
+    def gather_x(self, x_local):
+        """Global x on every rank (host side, through torch.distributed objects)."""
+        if self.world == 1:
+            return x_local
+        parts = exchange_bytes(x_local.tobytes(), self.group)
+        return np.concatenate([np.frombuffer(p, dtype=np.float64) for p in parts])
+
+    def e2e_bench(self, variant, b_loc, x0_loc, max_iter, steps, barrier):
+        """End-to-end timing through cgx_solve_host with (pinned) host slices: wall clock
+        between two barriers, max over ranks taken by the caller's barrier."""
+        import time
+        for _ in range(2):
+            self.solve_local(variant, b_loc, x0_loc, max_iter, return_x=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            _, _, info = self.solve_local(variant, b_loc, x0_loc, max_iter, return_x=True)
+        barrier()
+        dt = time.perf_counter() - t0
+        return {"value": (max_iter - 1) * steps / dt, "unit": "iterations/s",
+                "h2d_bytes_per_step": info["h2d_bytes"] * self.world,
+                "d2h_bytes_per_step": info["d2h_bytes"] * self.world, "ms_per_step": 1e3 * dt / steps,
+                "api": "cgx_solve_host on every rank: pinned host slices of b,x0 in, slice of x out"}
+
+
+class GroupSession:
+    """All ranks of a partition inside this process.  ``devices``: one device index per rank
+    (default: every rank on device 0 -- the single-GPU emulation of the protocol)."""
+
+    class _Member(_RankBase):
+        pass
+
+    def __init__(self, S, world, dinv=None, devices=None, mode="p2p"):
+        if mode != "p2p":
+            raise NotImplementedError("GroupSession drives the peer-to-peer scalar exchange only")
+        self._lib = _lib.load()
+        self.S, self.world = S, int(world)
+        self.n = S.shape[0]
+        devices = [0] * self.world if devices is None else list(devices)
+        self.members = []
+        for r in range(self.world):
+            m = GroupSession._Member()
+            m._create(S, self.world, r, devices[r])
+            self.members.append(m)
+        if self.world > 1:
+            for a in self.members:
+                for b in self.members:
+                    if a is not b:
+                        _lib.check(self._lib.cgx_dist_attach_ctx(a._ctx, b.rank, b._ctx))
+            for m in self.members:
+                _lib.check(self._lib.cgx_dist_commit(m._ctx, 1, None, None))
+        for m in self.members:
+            m._set_jacobi(dinv)
+        self._arr = (C.c_void_p * self.world)(*[m._ctx for m in self.members])
+        self._max_iter = 0
+
+    def close(self):
+        for m in self.members:
+            m.close()
+
+    def load_problem(self, b, x0, x_true=None):
+        b, x0 = _f64(b, self.n, "b"), _f64(x0, self.n, "x0")
+        xt = None if x_true is None else _f64(x_true, self.n, "x_true")
+        if self.world == 1:
+            m = self.members[0]
+            _lib.check(self._lib.cgx_load_problem_host(m._ctx, _lib.dptr(b), _lib.dptr(x0), _lib.dptr(xt), self.n))
+        else:
+            _lib.check(self._lib.cgx_group_load_problem_host(self._arr, self.world, _lib.dptr(b), _lib.dptr(x0),
+                                                             _lib.dptr(xt), self.n))
+
+    def begin(self, variant, max_iter, histories=()):
+        if self.world == 1:
+            _lib.check(self._lib.cgx_begin(self.members[0]._ctx, _lib.VARIANT_IDS[variant], int(max_iter),
+                                           _mask(histories), _lib.PATHS["stream"]))
+        else:
+            _lib.check(self._lib.cgx_group_begin(self._arr, self.world, _lib.VARIANT_IDS[variant], int(max_iter),
+                                                 _mask(histories)))
+        self._max_iter = int(max_iter)
+        for m in self.members:
+            m._max_iter = int(max_iter)
+
+    def advance(self, niter):
+        if self.world == 1:
+            _lib.check(self._lib.cgx_advance(self.members[0]._ctx, int(niter)))
+        else:
+            _lib.check(self._lib.cgx_group_advance(self._arr, self.world, int(niter)))
+
+    def solve(self, variant, b, x0, max_iter, x_true=None, histories=_lib.HIST_NAMES):
+        """-> (global x, {history: array}, [per-rank info])."""
+        self.load_problem(b, x0, x_true)
+        self.begin(variant, max_iter, histories)
+        self.advance(max_iter - 1)
+        xs, hists = [], []
+        for m in self.members:
+            x, h = m.fetch_local()
+            xs.append(x)
+            hists.append(h)
+        for h in hists[1:]:          # every rank holds the same global histories, bit for bit
+            if not np.array_equal(h, hists[0]):
+                raise AssertionError("ranks disagree on the histories")
+        out = {}
+        for i, name in enumerate(_lib.HIST_NAMES):
+            if name in histories and (x_true is not None or "error" not in name):
+                out[name] = hists[0][i].copy()
+        return np.concatenate(xs), out, [m.get_info() for m in self.members]

@@ -1,0 +1,67 @@
+"""torchrun worker: one rank per GPU runs the partitioned solve (DistSession, CUDA IPC
+windows) and rank 0 compares with the single-GPU emulation of the same partition
+(GroupSession) -- they must agree bit for bit -- for both scalar-exchange modes."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from new_cg_variants_b200 import PoissonStencil
+    from new_cg_variants_b200.dist import DistSession, GroupSession
+    from new_cg_variants_b200 import _lib
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--shape", default="64,20,24")
+    args = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")          # plumbing only: window handles and barriers
+    nx, ny, nz = map(int, args.shape.split(","))
+    S = PoissonStencil(nx, ny, nz, dim=3)
+    n = S.shape[0]
+    x_true = np.ones(n) / np.sqrt(n)
+    b, x0 = S @ x_true, np.zeros(n)
+    dinv = 1 / S.diagonal()
+    hist = _lib.HIST_NAMES
+    ok = True
+    for mode in ("p2p", "nccl"):
+        sess = DistSession(S, dinv=dinv, device=local, mode=mode)
+        results = {}
+        for tag in ("hs", "cg", "gv", "pr", "m", "pipe_pr", "pipe_p"):
+            x_loc, h, info = sess.solve(tag, b, x0, 25, x_true=x_true, histories=hist)
+            x = sess.gather_x(x_loc)
+            results[tag] = (x, h)
+        sess.close()
+        if rank == 0:
+            grp = GroupSession(S, world, dinv=dinv, devices=[local] * world)
+            for tag, (x, h) in results.items():
+                xg, hg, _ = grp.solve(tag, b, x0, 25, x_true=x_true)
+                if mode == "p2p":         # same rank-ordered sums: same bits
+                    same = np.array_equal(x, xg) and all(np.array_equal(h[k], hg[k], equal_nan=True) for k in hist)
+                else:                     # NCCL picks its own summation tree: rounding-level agreement
+                    same = np.allclose(x, xg, rtol=1e-9, atol=1e-13) and \
+                        all(np.allclose(h[k][:10], hg[k][:10], rtol=1e-10) for k in hist)
+                print(f"[{mode}] {tag}: {'match' if same else 'MISMATCH'}", flush=True)
+                ok = ok and same
+            grp.close()
+        dist.barrier()
+    flag = torch.tensor([1 if ok else 0])
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    if rank == 0 and flag.item():
+        print("dist_worker ok", flush=True)
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,105 @@
+"""GPU (-m gpu): the row-partitioned multi-GPU protocol (z-slabs, peer-to-peer halo planes,
+rank-ordered scalar exchange) exercised on ONE GPU with `GroupSession`: the ranks are
+contexts sharing a stream and run the very kernels of a multi-process run, stage by stage.
+A real 2-GPU run of the same partition (tests/dist_worker.py under torchrun) must return
+the same bits; it runs when two devices are visible."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import orc
+from new_cg_variants_b200 import PoissonStencil, Session
+from new_cg_variants_b200.dist import GroupSession
+
+pytestmark = pytest.mark.gpu
+ALL_TAGS = list(orc.VARIANTS)
+
+
+def _problem(S):
+    n = S.shape[0]
+    x_true = np.ones(n) / np.sqrt(n)
+    return x_true, S @ x_true, np.zeros(n)
+
+
+@pytest.mark.parametrize("shape,world", [((16, 12, 8), 2), ((130, 10, 9), 3), ((258, 9, 12), 4),
+                                         ((20, 18, 16), 8), ((64, 1, 40), 4), ((7, 6, 10), 2)])
+def test_partitioned_run_matches_single_gpu(shape, world):
+    """Every variant, Jacobi and identity: histories of the G-slab run agree with the
+    single-context run to rounding over the first iterations (only the summation order of
+    the dots differs: per-rank partials added in rank order), x likewise; all ranks hold
+    identical histories (checked inside GroupSession.solve); runs are bitwise repeatable."""
+    nx, ny, nz = shape
+    S = PoissonStencil(nx, ny, nz, dim=3)
+    x_true, b, x0 = _problem(S)
+    n = S.shape[0]
+    for dinv in (1 / S.diagonal(), None, 1 / (S.diagonal() + np.arange(n) % 3)):
+        grp = GroupSession(S, world, dinv=dinv)
+        one = Session(S, dinv=dinv)
+        try:
+            for tag in ALL_TAGS:
+                xg, hg, infos = grp.solve(tag, b, x0, 14, x_true=x_true)
+                xg2, hg2, _ = grp.solve(tag, b, x0, 14, x_true=x_true)
+                x1, h1, _ = one.solve(tag, b, x0, 14, x_true=x_true, path="stream")
+                assert all(i["kernel_launches"] > 0 for i in infos)
+                np.testing.assert_allclose(xg, x1, rtol=1e-9, atol=1e-13, err_msg=f"{shape}x{world}/{tag}")
+                assert np.array_equal(xg, xg2)
+                for h in orc.HISTORIES:
+                    np.testing.assert_allclose(hg[h][:10], h1[h][:10], rtol=1e-10, err_msg=f"{shape}x{world}/{tag}/{h}")
+                    assert np.array_equal(hg[h], hg2[h], equal_nan=True)
+        finally:
+            grp.close()
+            one.close()
+
+
+def test_partitioned_run_parity_with_oracle():
+    """The parity rule of tests/helpers.py on a partitioned run (poisson3d_12 fixture, 3 slabs)."""
+    case = "poisson3d_12_jacobi"
+    A, b, x0, x_true, dinv, max_iter = helpers.case_problem(case)
+    S = PoissonStencil(12, 12, 12, dim=3)
+    assert (S.tocsr() != A).nnz == 0
+    bands = helpers.cases()[case]["kstar"]
+    grp = GroupSession(S, 3, dinv=dinv)
+    try:
+        for tag in ALL_TAGS:
+            _, dev, _ = grp.solve(tag, b, x0, max_iter, x_true=x_true)
+            live = orc.solve(tag, A, b, x0, max_iter, dinv=dinv, x_true=x_true)
+            helpers.check_parity(dev, live, bands[tag], f"{case}/{tag} x3 slabs")
+    finally:
+        grp.close()
+
+
+def test_resume_and_scalars_in_partitioned_run():
+    S = PoissonStencil(16, 16, 16, dim=3)
+    x_true, b, x0 = _problem(S)
+    grp = GroupSession(S, 4, dinv=1 / S.diagonal())
+    try:
+        _, h_one, _ = grp.solve("pipe_pr", b, x0, 30, x_true=x_true)
+        grp.load_problem(b, x0, x_true)
+        grp.begin("pipe_pr", 30, orc.HISTORIES)
+        for chunk in (1, 2, 9, 100):
+            grp.advance(chunk)
+        sc = [m.scalars() for m in grp.members]
+        assert all(s == sc[0] for s in sc)           # identical bits on every rank
+        _, hh = grp.members[0].fetch_local()
+        for i, h in enumerate(orc.HISTORIES):
+            assert np.array_equal(hh[i], h_one[h], equal_nan=True)
+    finally:
+        grp.close()
+
+
+def test_two_processes_two_gpus_match_emulation():
+    """torchrun, one rank per GPU (CUDA IPC windows, NVLink stores): same bits as the
+    single-GPU emulation.  Needs two visible devices; otherwise only the emulation ran."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU visible: the multi-process run is covered by `gpurun --gpus 2`")
+    worker = os.path.join(os.path.dirname(__file__), "dist_worker.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29571", worker, "--check"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "dist_worker ok" in out.stdout

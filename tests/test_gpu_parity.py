@@ -60,13 +60,18 @@ def _device_solve(tag, A, b, x0, max_iter, dinv, x_true, **kw):
     return f(A, b, x0, max_iter, preconditioner=prec, callbacks=STD_CALLBACKS, x_true=x_true, **kw)
 
 
+@pytest.mark.parametrize("path", ["stream", "persistent"])
 @pytest.mark.parametrize("case", list(helpers.cases()))
-def test_variants_match_oracle_and_goldens(case):
+def test_variants_match_oracle_and_goldens(case, path):
+    """Every variant on every fixture, through both execution paths: `stream` (2-3 fused
+    kernels per iteration) and `persistent` (one cooperative launch for the whole solve)."""
     A, b, x0, x_true, dinv, max_iter = helpers.case_problem(case)
     bands = helpers.cases()[case]["kstar"]
     report = []
     for tag in ALL_TAGS:
-        dev = _device_solve(tag, A, b, x0, max_iter, dinv, x_true)
+        dev = _device_solve(tag, A, b, x0, max_iter, dinv, x_true, path=path, return_info=True)
+        assert dev["_info"]["path"] == {"stream": 1, "persistent": 2}[path]
+        assert dev["_info"]["kernel_launches"] > 0
         assert dev["name"] == orc.VARIANTS[tag] and dev["max_iter"] == max_iter
         live = orc.solve(tag, A, b, x0, max_iter, dinv=dinv, x_true=x_true)
         gold = {h: helpers.golden_history(case, tag, h) for h in orc.HISTORIES}
@@ -78,7 +83,7 @@ def test_variants_match_oracle_and_goldens(case):
         helpers.check_parity(dev, gold, bands[tag], f"{case}/{tag} vs golden")
         kd = min(helpers.first_deviation(dev[h], live[h]) for h in helpers.RESIDUAL_HISTS)
         report.append(f"{tag}: agree<1e-10 to k={kd} (window {bands[tag]['window']}, k*10 {bands[tag]['kstar10']}) it={it} acc={acc:.2f}")
-    print(f"\n[{case}] " + " | ".join(report))
+    print(f"\n[{case}/{path}] " + " | ".join(report))
 
 
 def test_unpreconditioned_twins_and_names():
@@ -245,7 +250,7 @@ def test_tma_stencil_path_equals_generic_path(shape):
             with Session(S, dinv=dinv) as s:
                 s.set_option("tma", tma)
                 for tag in ALL_TAGS:
-                    x, hist, info = s.solve(tag, b, x0, 12, x_true=x_true)
+                    x, hist, info = s.solve(tag, b, x0, 12, x_true=x_true, path="stream")
                     res[(tma, tag)] = (x, hist)
         for tag in ALL_TAGS:
             x1, h1 = res[(1, tag)]
@@ -253,3 +258,65 @@ def test_tma_stencil_path_equals_generic_path(shape):
             np.testing.assert_allclose(x1, x0_, rtol=1e-10, atol=1e-13, err_msg=f"{shape}/{tag}")
             for h in orc.HISTORIES:
                 np.testing.assert_allclose(h1[h], h0[h], rtol=1e-10, err_msg=f"{shape}/{tag}/{h}")
+
+
+# ------------------------------------------------------------------ persistent vs stream
+def test_persistent_path_equals_stream_path():
+    """Same per-row arithmetic, another fixed summation order of the fused dots: agreement
+    to rounding over the first iterations; each path bitwise repeatable; AUTO picks the
+    persistent kernel for latency-bound sizes and the stream kernels for large ones."""
+    S = PoissonStencil(24, 20, 12, dim=3)
+    A = S.tocsr()
+    x_true, b, x0 = orc.setup_problem(A)
+    for op, dinv in ((S, 1 / A.diagonal()), (A, 1 / (A.diagonal() + np.arange(A.shape[0]) % 3)), (A, None)):
+        for tag in ALL_TAGS:
+            o_s = _device_solve(tag, op, b, x0, 30, dinv, x_true, path="stream")
+            o_p = _device_solve(tag, op, b, x0, 30, dinv, x_true, path="persistent")
+            o_p2 = _device_solve(tag, op, b, x0, 30, dinv, x_true, path="persistent")
+            for h in orc.HISTORIES:
+                np.testing.assert_allclose(o_p[h][:12], o_s[h][:12], rtol=1e-10, err_msg=f"{tag}/{h}")
+                assert np.array_equal(o_p[h], o_p2[h], equal_nan=True)
+    auto = _device_solve("pr", S, b, x0, 10, None, x_true, return_info=True)
+    assert auto["_info"]["path"] == 2
+    with Session(S) as s:
+        s.set_option("persistent_threshold", 100)
+        _, _, info = s.solve("pr", b, x0, 10, x_true=x_true)
+        assert info["path"] == 1
+
+
+def test_persistent_path_long_run_and_resume():
+    """1250 iterations of un-preconditioned bcsstk03 in ONE launch, and the same run cut
+    into pieces with cgx_advance (the scalars survive the kernel boundary bit for bit)."""
+    A, b, x0, x_true, dinv, max_iter = helpers.case_problem("bcsstk03_None")
+    with Session(A) as s:
+        s.load_problem(b, x0, x_true)
+        info = s.run("pipe_pr", max_iter, histories=orc.HISTORIES, path="persistent")
+        assert info["path"] == 2 and info["kernel_launches"] < 40
+        _, h_one = s.fetch()
+        s.begin("pipe_pr", max_iter, histories=orc.HISTORIES, path="persistent")
+        for chunk in (1, 7, 300, 5000):
+            s.advance(chunk)
+        _, h_cut = s.fetch()
+        assert np.array_equal(h_one, h_cut, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["bcsstk16", "bcsstk18", "nos7", "bcsstm24", "model_48_8_3"])
+def test_csr_stream_kernel_equals_row_kernel(name):
+    """CSR-stream SpMV (CTA-wide coalesced sweep, products staged in shared memory, row sums in
+    stored order) against the one-thread-per-row kernel: bit-identical products, solves equal to rounding."""
+    A = helpers.load_matrix(name)
+    x_true, b, x0 = orc.setup_problem(A)
+    dinv = orc.jacobi_dinv(A)
+    res = {}
+    for flag in (1, 0):
+        with Session(A, dinv=dinv) as s:
+            s.set_option("csr_stream", flag)
+            for tag in ("hs", "cg", "pr", "pipe_pr", "gv"):
+                x, hist, _ = s.solve(tag, b, x0, 10, x_true=x_true, path="stream")
+                res[(flag, tag)] = (x, hist)
+            v = np.random.default_rng(3).standard_normal(A.shape[0])
+            res[(flag, "spmv")] = s.spmv(v)
+            assert np.array_equal(res[(flag, "spmv")], A @ v)            # scipy's csr_matvec, bit for bit
+    for tag in ("hs", "cg", "pr", "pipe_pr", "gv"):
+        for h in orc.HISTORIES:      # same row sums; the fused dots are summed in another fixed order
+            np.testing.assert_allclose(res[(1, tag)][1][h][:6], res[(0, tag)][1][h][:6], rtol=1e-9, err_msg=f"{tag}/{h}")
