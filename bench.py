@@ -228,10 +228,10 @@ def run_ours(args, rank, world, local_rank):
     value = its * args.steps / (dev_ms / 1e3)
 
     # ---- e2e through the C-ABI call with host buffers (pinned), copies inside the timing
-    tb, hb = pinned(b)
-    tx0, hx0 = pinned(x0)
     e2e = None
     if world == 1:
+        tb, hb = pinned(b)
+        tx0, hx0 = pinned(x0)
         for _ in range(2):
             sess.solve(variant, hb, hx0, its + 1, histories=(), path=args.path)
         barrier()
@@ -245,45 +245,58 @@ def run_ours(args, rank, world, local_rank):
                "ms_per_step": 1e3 * e_dt / args.steps,
                "api": "cgx_solve_host (Session.solve): pinned host b,x0 in, x out"}
     else:
+        tb, hb = pinned(sess.local(b))
+        tx0, hx0 = pinned(sess.local(x0))
         e2e = sess.e2e_bench(variant, hb, hx0, its + 1, args.steps, barrier)
+        t = torch.tensor([e2e["ms_per_step"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e["ms_per_step"] = t.item()
+        e2e["value"] = its / (t.item() / 1e3)
 
-    # ---- per-kernel timing for the roofline (separate, untimed pass with event pairs)
-    roofline = None
+    # ---- per-kernel timing for the roofline (separate, untimed pass with event pairs; on
+    #      N > 1 the rows are this rank's slab and the times include waiting for the peers)
+    n_loc = n if world == 1 else sess.n
+    peak, peak_src = measured_peak()
+    sess.set_profile(True)
+    sess.run(variant, its + 1, histories=(), path="stream")
+    prof = sess.get_profile()
+    sess.set_profile(False)
+    top = max(prof, key=lambda c: prof[c][0])
+    ms, cnt = prof[top]
+    # a constant Jacobi diagonal (every Poisson stencil) travels as a scalar: no dinv stream
+    dinv_stream = 0 if np.all(dinv == dinv[0]) else 1
+    cw = lambda c: CLASS_WORDS[c][0] + CLASS_WORDS[c][1] * dinv_stream
+    words = cw(top)
+    bytes_per_launch = 8.0 * n_loc * words
+    achieved = bytes_per_launch / (ms / cnt * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic if world == 1 else None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": ms / cnt,
+                "rows_per_launch": n_loc,
+                "share_of_loop": ms / sum(v[0] for v in prof.values()),
+                "kernels": {c: {"avg_ms": v[0] / v[1], "launches": v[1],
+                                "words_per_row": cw(c),
+                                "GBps": 8.0 * n_loc * cw(c) / (v[0] / v[1] * 1e-3) / 1e9}
+                            for c, v in prof.items() if c in CLASS_WORDS}}
+    # ---- the other variants on the same problem (2 solves each, resident inputs)
     variants = {}
-    if world == 1:
-        peak, peak_src = measured_peak()
-        sess.set_profile(True)
-        sess.run(variant, its + 1, histories=(), path="stream")
-        prof = sess.get_profile()
-        sess.set_profile(False)
-        top = max(prof, key=lambda c: prof[c][0])
-        ms, cnt = prof[top]
-        # a constant Jacobi diagonal (every Poisson stencil) travels as a scalar: no dinv stream
-        dinv_stream = 0 if np.all(dinv == dinv[0]) else 1
-        cw = lambda c: CLASS_WORDS[c][0] + CLASS_WORDS[c][1] * dinv_stream
-        words = cw(top)
-        bytes_per_launch = 8.0 * n * words
-        achieved = bytes_per_launch / (ms / cnt * 1e-3) / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": ms / cnt,
-                    "share_of_loop": ms / sum(v[0] for v in prof.values()),
-                    "kernels": {c: {"avg_ms": v[0] / v[1], "launches": v[1],
-                                    "words_per_row": cw(c),
-                                    "GBps": 8.0 * n * cw(c) / (v[0] / v[1] * 1e-3) / 1e9}
-                                for c, v in prof.items() if c in CLASS_WORDS}}
-        # ---- the other variants on the same problem (2 solves each, resident inputs)
-        for v in ("hs", "cg", "m", "gv", "pr", "pipe_pr"):
-            sess.run(v, its + 1, histories=(), path=args.path)
-            info = sess.run(v, its + 1, histories=(), path=args.path)
-            ips = its / (info["loop_ms"] / 1e3)
-            variants[v] = {"iterations_per_s_loop": ips, "ms_per_iteration": info["loop_ms"] / its,
-                           "hbm_gbs_model": ips * 8 * n * W_V[v] / 1e9}
+    for v in ("hs", "cg", "m", "gv", "pr", "pipe_pr"):
+        sess.run(v, its + 1, histories=(), path=args.path)
+        info = sess.run(v, its + 1, histories=(), path=args.path)
+        lm = info["loop_ms"]
+        if world > 1:
+            t = torch.tensor([lm], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            lm = t.item()
+        ips = its / (lm / 1e3)
+        variants[v] = {"iterations_per_s_loop": ips, "ms_per_iteration": lm / its,
+                       "hbm_gbs_model": ips * 8 * n * W_V[v] / 1e9,
+                       "pct_of_8TBs_per_gpu": 100 * ips * 8 * n * W_V[v] / 8e12 / world}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -301,8 +314,8 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "no flush needed: one iteration streams %.2f GB >> 126 MB L2" % (b_iter / 1e9)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "wall_ms_per_step": wall_ms / args.steps, "loop_ms_per_iteration": loop_ms / (its * args.steps),
-            "hbm_gbs_model": value * b_iter / 1e9, "pct_of_8TBs": 100 * value * b_iter / 8e12,
-            "pct_of_measured_peak": 100 * value * b_iter / 1e9 / measured_peak()[0],
+            "hbm_gbs_model": value * b_iter / 1e9, "pct_of_8TBs": 100 * value * b_iter / 8e12 / world,
+            "pct_of_measured_peak": 100 * value * b_iter / 1e9 / measured_peak()[0] / world,
             "roofline": roofline, "cpu_baseline": cpu, "variants": variants,
         }
         print(json.dumps(line))

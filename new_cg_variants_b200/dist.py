@@ -149,6 +149,18 @@ class _RankBase:
     def set_option(self, name, value):
         _lib.check(self._lib.cgx_set_option(self._ctx, name.encode(), int(value)))
 
+    def set_profile(self, on=True):
+        _lib.check(self._lib.cgx_set_profile(self._ctx, 1 if on else 0))
+
+    def get_profile(self):
+        out = {}
+        for cls in range(self._lib.cgx_profile_class_count()):
+            ms, cnt = C.c_double(), C.c_int64()
+            _lib.check(self._lib.cgx_get_profile(self._ctx, cls, C.byref(ms), C.byref(cnt)))
+            if cnt.value:
+                out[self._lib.cgx_profile_class_name(cls).decode()] = (ms.value, cnt.value)
+        return out
+
 
 class DistSession(_RankBase):
     """This process's rank of a partitioned operator (``torch.distributed`` must be
