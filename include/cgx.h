@@ -144,7 +144,8 @@ int cgx_get_scalars(cgx_ctx* ctx, double* out9);
 /* ---- tuning/testing switches.  "tma" = 0 forces the generic (non-TMA) stencil kernel and
  *      "csr_stream" = 0 the thread-per-row CSR kernel, so that two SpMV implementations can
  *      be compared bit for bit; "persistent_threshold" = rows below which CGX_PATH_AUTO
- *      takes the persistent kernel; "stub_allreduce" = 1 replaces the multi-GPU scalar
+ *      takes the persistent kernel ("pers_threads" / "pers_ctas" override its CTA shape);
+ *      "stub_allreduce" = 1 replaces the multi-GPU scalar
  *      exchange by a local stand-in (timing experiment: exposed allreduce time). */
 int cgx_set_option(cgx_ctx* ctx, const char* name, int value);
 
@@ -202,7 +203,8 @@ int cgx_dist_commit(cgx_ctx* ctx, int mode, const char* nccl_libpath, const void
 int cgx_group_load_problem_host(cgx_ctx** ctxs, int count, const double* b_host,
                                 const double* x0_host, const double* x_true_host,
                                 int64_t n_total);
-int cgx_group_begin(cgx_ctx** ctxs, int count, int variant, int max_iter, unsigned hist_mask);
+int cgx_group_begin(cgx_ctx** ctxs, int count, int variant, int max_iter, unsigned hist_mask,
+                    int path);
 int cgx_group_advance(cgx_ctx** ctxs, int count, int niter);
 
 /* ---- single primitives, exposed for the unit tests of SURVEY.md section 7:

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <functional>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/cgx.h"
@@ -166,9 +167,13 @@ struct cgx_ctx {
   cudaEvent_t ev_prod[kSlots] = {}, ev_red[kSlots] = {};
   double* d_nccl = nullptr;                // [2][kSlots][kSumW]: in, out
   // persistent path
-  double* d_ppart = nullptr;               // [2][grid][kPersRed]
-  u64* d_pbar = nullptr;                   // [0] grid barrier counter, [1] error flag
+  double* d_ppart = nullptr;               // [2][kPersMaxGrid][kPersRed]
+  u64* d_pbar = nullptr;                   // sync-point counter
+  PersOut* d_pout = nullptr;
+  void* d_prank = nullptr;                 // PersRank<Op>[kMaxWorld] (rank 0 of a group holds all)
+  double* d_exp[2][2] = {};                // exported SpMV inputs [parity][rhs]
   int pers_threshold = 1 << 19;            // AUTO: rows below which the persistent kernel runs
+  int pers_threads = 0, pers_ctas = 0;     // 0 = choose (options "pers_threads", "pers_ctas")
   // current run
   int variant = 0, max_iter = 0, cur_k = 0, path = CGX_PATH_STREAM;
   i64 launches_run = 0;
@@ -197,6 +202,7 @@ static void free_problem(cgx_ctx* c) {
 }
 static void free_state(cgx_ctx* c) {
   for (int i = 0; i < V_COUNT; ++i) { cudaFree(c->vec[i]); c->vec[i] = nullptr; }
+  for (auto& pp : c->d_exp) for (auto& q : pp) { cudaFree(q); q = nullptr; }
   cudaFree(c->d_hist); c->d_hist = nullptr; c->hist_len = 0;
   c->ran = false;
 }
@@ -241,6 +247,9 @@ extern "C" int cgx_ctx_create(int device, cgx_ctx** out) {
   CU(cudaMalloc(&c->d_ppart, sizeof(double) * 2 * kPersMaxGrid * kPersRed));
   CU(cudaMalloc(&c->d_pbar, sizeof(u64) * 2));
   CU(cudaMemset(c->d_pbar, 0, sizeof(u64) * 2));
+  CU(cudaMalloc(&c->d_pout, sizeof(PersOut)));
+  CU(cudaMemset(c->d_pout, 0, sizeof(PersOut)));
+  CU(cudaMalloc(&c->d_prank, std::max(sizeof(PersRank<CsrOp>), sizeof(PersRank<StencilOp>)) * kMaxWorld));
   c->dist.world = 1;
   *out = c;
   return CGX_OK;
@@ -270,7 +279,7 @@ extern "C" int cgx_ctx_destroy(cgx_ctx* c) {
   dist_release(c);
   free_state(c); free_problem(c); free_op(c);
   cudaFree(c->d_dinv); cudaFree(c->d_sc); cudaFree(c->d_partials); cudaFree(c->d_ticket);
-  cudaFree(c->d_ppart); cudaFree(c->d_pbar);
+  cudaFree(c->d_ppart); cudaFree(c->d_pbar); cudaFree(c->d_pout); cudaFree(c->d_prank);
   for (auto& e : c->ev) cudaEventDestroy(e);
   for (auto& e : c->prof_events) cudaEventDestroy(e);
   cudaStreamDestroy(c->own_stream);
@@ -898,47 +907,97 @@ extern "C" int cgx_load_problem_dev(cgx_ctx* c, const double* b, const double* x
 // ---------------------------------------------------------------------------------------
 // persistent path (cgx_persistent.cuh): one cooperative launch runs every iteration
 // ---------------------------------------------------------------------------------------
-static int pers_grid(const cgx_ctx* c) {
-  i64 g = (c->n + kBlock - 1) / kBlock;
-  g = std::min<i64>(g, (i64)c->sm_count * 2);
-  g = std::min<i64>(g, kPersMaxGrid);
-  return (int)std::max<i64>(g, 1);
+struct PersGeom { int T, nb, R, nslot; unsigned vmask; size_t smem; bool ok; };
+
+// CTA shape for n rows per rank with `ranks_in_launch` ranks sharing one GPU's SMs
+static PersGeom pers_geometry(const cgx_ctx* c, int variant, int ranks_in_launch) {
+  PersGeom G{};
+  const VariantInfo vi = variant_info(variant, c->d_dinv != nullptr);
+  G.vmask = vi.need;
+  G.nslot = __builtin_popcount(vi.need) + (c->pm == 1 ? 1 : 0);
+  const int sm_cap = std::max(1, c->sm_count / std::max(1, ranks_in_launch));
+  int T = c->pers_threads ? c->pers_threads : (c->n <= (i64)sm_cap * 256 ? 256 : 512);
+  T = std::min(512, std::max(32, (T + 31) / 32 * 32));
+  const i64 chunks = (c->n + T - 1) / T;
+  int cap = c->pers_ctas ? std::min(c->pers_ctas, sm_cap) : sm_cap;
+  cap = std::max(1, std::min(cap, kPersMaxGrid / std::max(1, ranks_in_launch)));
+  const i64 R = (chunks + cap - 1) / cap;
+  G.T = T; G.R = (int)R; G.nb = (int)((chunks + R - 1) / R);
+  G.smem = (size_t)G.nslot * R * T * sizeof(double);
+  G.ok = G.smem <= 216 * 1024;
+  return G;
 }
 
 template <class Op, int PM>
-static int pers_launch_pm(cgx_ctx* c, const Op& A, PersArgs pa) {
-  void* params[] = {(void*)&A, (void*)&pa};
+static int pers_launch_pm(cgx_ctx** cs, int count, const PersGeom& G, int k0, int k1) {
+  cgx_ctx* c0 = cs[0];
+  std::vector<PersRank<Op>> h(count);
+  for (int i = 0; i < count; ++i) {
+    cgx_ctx* c = cs[i];
+    PersRank<Op>& r = h[i];
+    if constexpr (std::is_same<Op, CsrOp>::value) r.A = c->csr; else r.A = c->sten;
+    Args g = make_args(c);
+    Plan p;                                         // fills scpar / x_true epochs
+    plan_apply(c, g, p);
+    r.g = g;
+    for (int v = 0; v < V_COUNT; ++v) r.vecs[v] = c->vec[v];
+    r.vecs[10] = c->d_dinv; r.vecs[11] = nullptr;
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) r.exp_[a][b] = c->d_exp[a][b];
+    r.bar = c->d_pbar; r.part = c->d_ppart; r.out = c->d_pout;
+    r.epoch0 = c->epoch;
+    for (int ch = 0; ch < kChan; ++ch) r.hepoch0[ch] = c->hepoch[ch];
+    CU(cudaMemsetAsync(c->d_pbar, 0, sizeof(u64) * 2, c0->stream));
+    CU(cudaMemsetAsync(c->d_pout, 0, sizeof(PersOut), c0->stream));
+  }
+  CU(cudaMemcpyAsync(c0->d_prank, h.data(), sizeof(PersRank<Op>) * count, cudaMemcpyHostToDevice, c0->stream));
+  CU(cudaStreamSynchronize(c0->stream));           // h is a host temporary
+  PersLaunch L{};
+  L.k0 = k0; L.k1 = k1; L.nb = G.nb; L.R = G.R; L.vmask = G.vmask; L.nslot = G.nslot;
+  const PersRank<Op>* dr = static_cast<const PersRank<Op>*>(c0->d_prank);
+  void* params[] = {(void*)&dr, (void*)&L};
   const void* fn = nullptr;
 #define CGX_PV(V) case V: fn = (const void*)persistent_kernel<Op, V, PM>; break;
-  switch (c->variant) {
+  switch (c0->variant) {
     CGX_PV(CGX_HS) CGX_PV(CGX_CG) CGX_PV(CGX_GV) CGX_PV(CGX_PR) CGX_PV(CGX_M) CGX_PV(CGX_PIPE_PR)
     CGX_PV(CGX_PIPE_P) CGX_PV(CGX_PIPE_PR_M) CGX_PV(CGX_PIPE_P_M)
   }
 #undef CGX_PV
   if (!fn) return fail(CGX_ERR_ARG, "persistent path: unknown variant");
+  CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0));
-  int grid = std::min(pers_grid(c), std::max(1, per_sm) * c->sm_count);
-  pa.nblocks = grid;
-  CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), params, 0, c->stream));
-  c->launches++;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, G.T, G.smem));
+  if ((i64)per_sm * c0->sm_count < (i64)G.nb * count)
+    return fail(CGX_ERR_UNSUPPORTED, "persistent path: %d CTAs of %d threads / %zu B shared memory are not co-resident",
+                G.nb * count, G.T, G.smem);
+  CU(cudaLaunchCooperativeKernel(fn, dim3(G.nb * count), dim3(G.T), params, G.smem, c0->stream));
+  c0->launches++;
   return CGX_OK;
 }
-static int pers_launch(cgx_ctx* c, const PersArgs& pa) {
+static int pers_launch(cgx_ctx** cs, int count, const PersGeom& G, int k0, int k1) {
+  cgx_ctx* c = cs[0];
   if (c->op_kind == 1) {
-    if (c->pm == 2) return pers_launch_pm<CsrOp, 2>(c, c->csr, pa);
-    if (c->pm == 1) return pers_launch_pm<CsrOp, 1>(c, c->csr, pa);
-    return pers_launch_pm<CsrOp, 0>(c, c->csr, pa);
+    if (c->pm == 2) return pers_launch_pm<CsrOp, 2>(cs, count, G, k0, k1);
+    if (c->pm == 1) return pers_launch_pm<CsrOp, 1>(cs, count, G, k0, k1);
+    return pers_launch_pm<CsrOp, 0>(cs, count, G, k0, k1);
   }
-  if (c->pm == 2) return pers_launch_pm<StencilOp, 2>(c, c->sten, pa);
-  if (c->pm == 1) return pers_launch_pm<StencilOp, 1>(c, c->sten, pa);
-  return pers_launch_pm<StencilOp, 0>(c, c->sten, pa);
+  if (c->pm == 2) return pers_launch_pm<StencilOp, 2>(cs, count, G, k0, k1);
+  if (c->pm == 1) return pers_launch_pm<StencilOp, 1>(cs, count, G, k0, k1);
+  return pers_launch_pm<StencilOp, 0>(cs, count, G, k0, k1);
+}
+// after the launch has drained: adopt the epoch counters the kernel advanced
+static int pers_collect(cgx_ctx* c) {
+  PersOut o;
+  CU(cudaMemcpy(&o, c->d_pout, sizeof o, cudaMemcpyDeviceToHost));
+  if (o.err) return fail(CGX_ERR_CUDA, "persistent kernel: a sync point or a peer wait timed out (rank %d)", c->dist.rank);
+  c->epoch = o.epoch;
+  for (int ch = 0; ch < kChan; ++ch) c->hepoch[ch] = o.hepoch[ch];
+  return CGX_OK;
 }
 
 // ---------------------------------------------------------------------------------------
 // begin / advance, for one context or a lockstep group of ranks
 // ---------------------------------------------------------------------------------------
-static int begin_prepare(cgx_ctx* c, int variant, int max_iter, unsigned hist_mask, int path) {
+static int begin_prepare(cgx_ctx* c, int variant, int max_iter, unsigned hist_mask, int path, int ranks_in_launch) {
   if (!c) return fail(CGX_ERR_ARG, "cgx_begin: ctx is NULL");
   if (variant < 0 || variant >= CGX_NUM_VARIANTS) return fail(CGX_ERR_ARG, "cgx_begin: unknown variant %d", variant);
   if (max_iter < 1) return fail(CGX_ERR_ARG, "cgx_begin: max_iter must be >= 1");
@@ -947,8 +1006,6 @@ static int begin_prepare(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
     return fail(CGX_ERR_ARG, "cgx_begin: unknown path %d", path);
   if (c->dist.world > 1 && !c->dist_ready)
     return fail(CGX_ERR_ARG, "cgx_begin: cgx_dist_commit has not been called on this rank");
-  if (c->dist.world > 1 && path == CGX_PATH_PERSISTENT)
-    return fail(CGX_ERR_UNSUPPORTED, "cgx_begin: the persistent path is single-GPU in this version");
   CU(cudaSetDevice(c->device));
   const bool prec = c->d_dinv != nullptr;
   const VariantInfo vi = variant_info(variant, prec);
@@ -967,8 +1024,21 @@ static int begin_prepare(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
   c->hist_mask = hist_mask;
   { int trc = setup_tma(c, vi.need); if (trc) return trc; }
   c->variant = variant; c->max_iter = max_iter; c->cur_k = 0;
-  if (path == CGX_PATH_AUTO)
-    path = (c->dist.world <= 1 && c->n < c->pers_threshold) ? CGX_PATH_PERSISTENT : CGX_PATH_STREAM;
+  {
+    const PersGeom G = pers_geometry(c, variant, ranks_in_launch);
+    const bool mode_ok = c->dist.world <= 1 || c->dist.mode == 1 || c->dist.mode == 3;   // in-kernel exchange only
+    if (path == CGX_PATH_AUTO)
+      path = (c->n < c->pers_threshold && G.ok && mode_ok) ? CGX_PATH_PERSISTENT : CGX_PATH_STREAM;
+    if (path == CGX_PATH_PERSISTENT && !G.ok)
+      return fail(CGX_ERR_UNSUPPORTED, "cgx_begin: %lld rows x %d resident vectors do not fit the SMs' shared memory "
+                  "(%zu B per CTA); use the stream path", (long long)c->n, G.nslot, G.smem);
+    if (path == CGX_PATH_PERSISTENT && !mode_ok)
+      return fail(CGX_ERR_UNSUPPORTED, "cgx_begin: the persistent path exchanges scalars peer to peer (mode 1), not through NCCL");
+  }
+  if (path == CGX_PATH_PERSISTENT)
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < (vi.pipe && vi.recompute ? 2 : 1); ++b)
+        if (!c->d_exp[a][b]) CU(cudaMalloc(&c->d_exp[a][b], sizeof(double) * c->n));
   c->path = path;
   c->launches_run = 0; c->loop_ms = 0.0;
   c->pend.clear();
@@ -994,11 +1064,6 @@ static int check_device_flags(cgx_ctx* c, const char* who) {
     CU(cudaMemcpyFromSymbol(&flag, g_tma_timeout, sizeof(int)));
     if (flag) return fail(CGX_ERR_CUDA, "%s: a TMA plane copy did not complete within 1 s", who);
   }
-  if (c->path == CGX_PATH_PERSISTENT) {
-    int err = 0;
-    CU(cudaMemcpy(&err, c->d_pbar + 1, sizeof(int), cudaMemcpyDeviceToHost));
-    if (err) return fail(CGX_ERR_CUDA, "%s: the persistent kernel's grid barrier timed out", who);
-  }
   if (c->dist.world > 1 && c->d_win) {
     int err = 0;
     CU(cudaMemcpy(&err, c->d_win + offsetof(WinHdr, error), sizeof(int), cudaMemcpyDeviceToHost));
@@ -1010,8 +1075,10 @@ static int check_device_flags(cgx_ctx* c, const char* who) {
 
 // Lockstep driver: `count` contexts (ranks of one partitioned problem, or a single context).
 static int group_begin(cgx_ctx** cs, int count, int variant, int max_iter, unsigned hist_mask, int path) {
+  bool same_device = count > 1;
+  for (int i = 1; i < count; ++i) same_device = same_device && cs[i]->device == cs[0]->device;
   for (int i = 0; i < count; ++i) {
-    int rc = begin_prepare(cs[i], variant, max_iter, hist_mask, path);
+    int rc = begin_prepare(cs[i], variant, max_iter, hist_mask, path, same_device ? count : 1);
     if (rc) return rc;
   }
   std::vector<Steps> steps(count);
@@ -1068,14 +1135,15 @@ static int group_advance(cgx_ctx** cs, int count, int niter) {
     gs[i] = make_args(cs[i]);
     CU(cudaEventRecord(cs[i]->ev[1], cs[i]->stream));
   }
+  const bool ran_pers = c0->path == CGX_PATH_PERSISTENT && last > c0->cur_k;
   if (c0->path == CGX_PATH_PERSISTENT) {
     if (last > c0->cur_k) {
-      PersArgs pa{};
-      pa.g = gs[0];
-      pa.k0 = c0->cur_k + 1; pa.k1 = last;
-      pa.part = c0->d_ppart; pa.bar = c0->d_pbar; pa.err = reinterpret_cast<int*>(c0->d_pbar + 1);
-      CU(cudaMemsetAsync(c0->d_pbar, 0, sizeof(u64) * 2, c0->stream));
-      int rc = pers_launch(c0, pa);
+      bool same_device = count > 1;
+      for (int i = 1; i < count; ++i) same_device = same_device && cs[i]->device == cs[0]->device;
+      if (count > 1 && !same_device)
+        return fail(CGX_ERR_UNSUPPORTED, "cgx_group_advance: persistent path: one process per GPU, or all ranks on one GPU");
+      const PersGeom G = pers_geometry(c0, c0->variant, count);
+      int rc = pers_launch(cs, count, G, c0->cur_k + 1, last);
       if (rc) return rc;
     }
   } else {
@@ -1109,6 +1177,7 @@ static int group_advance(cgx_ctx** cs, int count, int niter) {
     if (c->profile) prof_resolve(c);
     int rc = check_device_flags(c, "cgx_advance");
     if (rc) return rc;
+    if (ran_pers) { rc = pers_collect(c); if (rc) return rc; }
     c->launches_run += c->launches - l0[i];
     c->cur_k = std::max(c->cur_k, last);
   }
@@ -1136,11 +1205,11 @@ static void group_share_stream(cgx_ctx** cs, int count, bool on) {
   for (int i = 1; i < count; ++i)
     if (cs[i]->device == cs[0]->device) cs[i]->stream = on ? cs[0]->own_stream : cs[i]->own_stream;
 }
-extern "C" int cgx_group_begin(cgx_ctx** cs, int count, int variant, int max_iter, unsigned hist_mask) {
+extern "C" int cgx_group_begin(cgx_ctx** cs, int count, int variant, int max_iter, unsigned hist_mask, int path) {
   int rc = group_check(cs, count);
   if (rc) return rc;
   group_share_stream(cs, count, true);
-  rc = group_begin(cs, count, variant, max_iter, hist_mask, CGX_PATH_STREAM);
+  rc = group_begin(cs, count, variant, max_iter, hist_mask, path);
   group_share_stream(cs, count, false);
   return rc;
 }
@@ -1190,6 +1259,8 @@ extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
   if (!strcmp(name, "tma")) { c->no_tma = (value == 0); return CGX_OK; }
   if (!strcmp(name, "csr_stream")) { c->no_csr_stream = (value == 0); return CGX_OK; }
   if (!strcmp(name, "persistent_threshold")) { c->pers_threshold = value; return CGX_OK; }
+  if (!strcmp(name, "pers_threads")) { c->pers_threads = value; return CGX_OK; }
+  if (!strcmp(name, "pers_ctas")) { c->pers_ctas = value; return CGX_OK; }
   if (!strcmp(name, "stub_allreduce")) {
     // timing experiment (SURVEY.md section 8d "allreduce-hiding metric"): value != 0 replaces the
     // scalar exchange by a local stand-in; value == 0 restores the mode chosen at commit

@@ -1,81 +1,98 @@
-// cgx_persistent.cuh -- latency-bound path: ONE cooperative launch runs every iteration.
+// cgx_persistent.cuh -- latency-bound path: ONE cooperative launch runs every iteration,
+// on one GPU or on every GPU of a row partition.
 //
 // Every matrix in predict_and_recompute/matrices (n <= 15 439) and the 64^3 Poisson tail are
 // far below one GPU's worth of bandwidth work: with 2-4 launches per iteration the stream
-// path is bounded by launch latency.  Here the grid (co-resident by cooperative launch)
-// stays on the SMs; the stages of an iteration are separated by a grid barrier (one atomic
-// arrive per CTA + acquire spin), the fused dot products travel through a double-buffered
-// per-CTA partials array that EVERY warp sums in the same fixed order after the barrier
-// (deterministic, no "last block" hand-off, no scalar round trip through global memory),
-// and alpha/beta live in registers.  The state vectors stay L2-resident.
+// path is bounded by launch latency.  Here
+//   * the grid (co-resident by cooperative launch) stays on the SMs for the whole solve;
+//   * the STATE VECTORS LIVE IN SHARED MEMORY: CTA c owns the row chunks c, c+nb, c+2nb, ...
+//     (T rows each) in both stages of an iteration, so x, r, r~, p, s, ... never leave the
+//     SM; only the SpMV input (p | r~ | w~ | s~ [, r~]) is exported to global memory -- L2 --
+//     for the neighbouring rows to read (double-buffered by iteration parity), and on a
+//     partition its boundary planes go straight into the neighbours' ghost planes over NVLink;
+//   * a sync point = one atomic arrive per CTA + a relaxed spin; the CTA that arrives last
+//     adds the per-CTA partial dots in CTA order.  One GPU: every warp reads the partials
+//     itself.  Partition: the last CTA stores the rank's record into every rank's window and
+//     publishes the epoch; consumers add the records in rank order (bit-identical everywhere);
+//   * alpha/beta and the other recurrences live in registers;
+//   * the number of sync points per iteration is the variant's number of global
+//     synchronisations: 3 for HS-CG, 2 for CG-CG / PR-CG / M-CG, ONE for GV-CG and the
+//     pipe-PR family -- whose scalar exchange then travels while the SpMV stage runs
+//     (the paper's communication-hiding claim, pipeprcg.c:154-173).
 //
-// The stage bodies are the same ew_body / Op::row / sp_epilogue code as the stream path,
-// so the arithmetic per row is identical; only the summation order of the dots differs
-// (grid shape), which stays run-to-run deterministic.
+// The stage arithmetic is the stream path's ew_body / Op::row / sp_epilogue (called with
+// an Args whose vector pointers address shared memory), so every per-row operation is
+// identical; only the summation order of the dots differs, and stays deterministic.
 //
-// Instrumentation (the four standard callbacks) is fused into the SpMV stage as two more
-// right-hand sides (x and e = x - x_true) of the same matrix sweep.
+// Ranks of a partition can also be emulated inside ONE cooperative launch (CTA range r*nb ..
+// (r+1)*nb-1 acts as rank r): that is how the multi-GPU protocol of this kernel is tested on
+// a single GPU without ever having two launches wait for each other.
 #pragma once
 #include "cgx_kernels.cuh"
 
 namespace cgx {
 
-constexpr int kPersMaxGrid = 512;
+constexpr int kPersMaxGrid = 1024;
 constexpr int kPersRed = 8;            // <= 4 recurrence sums + 4 instrumentation sums
+constexpr int kPersMaxVec = 12;        // 10 state vectors + dinv + spare
 
-struct PersArgs {
-  Args g;
-  int k0, k1;                          // iterations k0 .. k1 (inclusive)
-  double* part;                        // [2][kPersMaxGrid][kPersRed]
-  u64* bar;                            // grid barrier counter (zeroed by the host)
-  int* err;
-  int nblocks;
+struct PersOut { u64 epoch; u64 hepoch[kChan]; int err; int pad; };
+
+template <class Op>
+struct PersRank {
+  Op A;
+  Args g;                              // global pointers; g.d = this rank's Dist (world 1: unused)
+  double* vecs[kPersMaxVec];           // global address of state vector v (cgx.cu V_* order), dinv at [10]
+  double* exp_[2][2];                  // exported SpMV inputs [parity][rhs]
+  u64* bar;                            // sync-point counter of this rank (zeroed by the host)
+  double* part;                        // [2][nb][kPersRed]
+  PersOut* out;
+  u64 epoch0;
+  u64 hepoch0[kChan];
 };
 
-__device__ __forceinline__ u64 ld_acquire_gpu(const u64* p) {
+struct PersLaunch {
+  int k0, k1;                          // iterations k0 .. k1 (inclusive)
+  int nb;                              // CTAs per rank
+  int R;                               // row chunks per CTA
+  unsigned vmask;                      // state vectors of the variant (bit v)
+  int nslot;                           // shared-memory vector slots (popcount(vmask) [+1 for dinv])
+};
+
+__device__ __forceinline__ u64 ld_relaxed_gpu(const u64* p) {
   u64 v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ u64 ld_relaxed_sys(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
-// Arrive + wait.  `target` = nblocks * (number of barriers so far, this one included).
-__device__ __forceinline__ void grid_barrier(u64* bar, u64 target, int* err) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(reinterpret_cast<unsigned long long*>(bar), 1ull);
-    if (ld_acquire_gpu(bar) < target) {
-      const u64 t0 = timer_ns();
-      while (ld_acquire_gpu(bar) < target) {
-        if (timer_ns() - t0 > 5000000000ull) { atomicExch(err, 1); break; }
-      }
+// Bounded waits.  After the first time-out every later wait returns at once, so a lost
+// peer costs one time-out, not one per iteration.
+__device__ __forceinline__ void pers_wait_gpu(const u64* p, u64 target, int* err) {
+  if (ld_relaxed_gpu(p) < target) {
+    const u64 t0 = timer_ns();
+    while (ld_relaxed_gpu(p) < target) {
+      if (*(volatile int*)err) break;
+      if (timer_ns() - t0 > 10000000000ull) { atomicExch(err, 1); break; }
     }
   }
-  __syncthreads();
+  fence_acq_rel_gpu();
 }
-
-// CTA partial sums -> partials buffer (thread 0), to be summed by everyone after the barrier
-template <int NR>
-__device__ __forceinline__ void pers_put(double (&red)[kPersRed], double* __restrict__ part, double* sh) {
-  double v[NR];
-#pragma unroll
-  for (int j = 0; j < NR; ++j) v[j] = red[j];
-  block_sum<NR>(v, sh);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int j = 0; j < NR; ++j) __stcg(&part[(size_t)blockIdx.x * kPersRed + j], v[j]);
+__device__ __forceinline__ void pers_wait_sys(const u64* p, u64 target, int* err) {
+  if (ld_relaxed_sys(p) < target) {
+    const u64 t0 = timer_ns();
+    while (ld_relaxed_sys(p) < target) {
+      if (*(volatile int*)err) break;
+      if (timer_ns() - t0 > 10000000000ull) { atomicExch(err, 1); break; }
+    }
   }
-}
-// Every warp: totals in a fixed order (lane-strided over CTAs, then the butterfly)
-template <int NR>
-__device__ __forceinline__ void pers_get(const double* __restrict__ part, int nblocks, double (&acc)[kPersRed]) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int j = 0; j < NR; ++j) {
-    double t = 0.0;
-    for (int b = lane; b < nblocks; b += 32) t += __ldcg(&part[(size_t)b * kPersRed + j]);
-    acc[j] = warp_sum(t);
-  }
+  fence_acq_rel_sys();
 }
 
 template <int VAR> struct PersPlan;      // stage kernels of each variant
@@ -89,115 +106,393 @@ template <> struct PersPlan<CGX_PIPE_PR_M> { static constexpr int EW = EW_PIPE_R
 template <> struct PersPlan<CGX_PIPE_P> { static constexpr int EW = EW_PIPE_N, SP = SP_PIPE_N; static constexpr bool MEUR = false; };
 template <> struct PersPlan<CGX_PIPE_P_M> { static constexpr int EW = EW_PIPE_N, SP = SP_PIPE_N; static constexpr bool MEUR = true; };
 
-template <int MODE> struct SpIn;          // which state vector(s) the SpMV stage multiplies
-template <> struct SpIn<SP_HS> { static __device__ const double* v0(const Args& g) { return g.p; } static __device__ const double* v1(const Args&) { return nullptr; } };
-template <> struct SpIn<SP_PR> { static __device__ const double* v0(const Args& g) { return g.p; } static __device__ const double* v1(const Args&) { return nullptr; } };
-template <> struct SpIn<SP_CG> { static __device__ const double* v0(const Args& g) { return g.rt; } static __device__ const double* v1(const Args&) { return nullptr; } };
-template <> struct SpIn<SP_GV> { static __device__ const double* v0(const Args& g) { return g.wt; } static __device__ const double* v1(const Args&) { return nullptr; } };
-template <> struct SpIn<SP_PIPE_R> { static __device__ const double* v0(const Args& g) { return g.st; } static __device__ const double* v1(const Args& g) { return g.rt; } };
-template <> struct SpIn<SP_PIPE_N> { static __device__ const double* v0(const Args& g) { return g.st; } static __device__ const double* v1(const Args&) { return nullptr; } };
+// index (cgx.cu V_* order) of the state vector(s) the SpMV stage multiplies
+template <int MODE> struct SpInV { static constexpr int v0 = 3, v1 = -1; };            // p
+template <> struct SpInV<SP_CG> { static constexpr int v0 = 2, v1 = -1; };            // rt
+template <> struct SpInV<SP_GV> { static constexpr int v0 = 7, v1 = -1; };            // wt
+template <> struct SpInV<SP_PIPE_R> { static constexpr int v0 = 5, v1 = 2; };         // st, rt
+template <> struct SpInV<SP_PIPE_N> { static constexpr int v0 = 5, v1 = -1; };        // st
+
+__device__ __forceinline__ double*& args_vec(Args& g, int v) {
+  switch (v) {
+    case 0: return g.x; case 1: return g.r; case 2: return g.rt; case 3: return g.p; case 4: return g.s;
+    case 5: return g.st; case 6: return g.w; case 7: return g.wt; case 8: return g.u; default: return g.t;
+  }
+}
+
+struct PersRec { u64 e; int kind; int k; int hist; };      // a published record still to be folded
 
 template <class Op, int VAR, int PM>
-__global__ void __launch_bounds__(kBlock) persistent_kernel(const Op A, const PersArgs pa) {
+__global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __restrict__ ranks,
+                                                          const PersLaunch L) {
   using P = PersPlan<VAR>;
   constexpr int EW = P::EW, SP = P::SP;
   constexpr bool MEUR = P::MEUR;
   constexpr int NRE = EwTraits<EW>::NR, NRS = SpTraits<SP>::NR, NV = SpTraits<SP>::NV;
-  __shared__ double sh[kPersRed * (kBlock / 32)];
+  constexpr bool SL = Op::kSlab;
+  extern __shared__ __align__(16) double smem[];               // [nslot][R*T]
+  __shared__ double sh[kPersRed * 32];
+  __shared__ double sh_acc[kPersRed];
+  __shared__ Args gg;                                          // this rank's global-memory Args
+  __shared__ Args gl;                                          // same, vectors in shared memory
+  __shared__ int sh_last;
 
-  const Args& g = pa.g;
-  const int nb = pa.nblocks;
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int nb = L.nb;
+  const int rk = blockIdx.x / nb, cta = blockIdx.x - rk * nb;
+  const PersRank<Op>& pr = ranks[rk];
+  const Op A = pr.A;
+  if (tid == 0) {
+    gg = pr.g;
+    gl = pr.g;
+    int slot = 0;
+    for (int v = 0; v < 10; ++v)
+      if (L.vmask & (1u << v)) { args_vec(gl, v) = smem + (size_t)slot * L.R * T; ++slot; }
+    if (PM == 1) gl.dinv = smem + (size_t)slot * L.R * T;
+    gl.d.world = 1;                                            // halo stores are done here, not in ew_body
+  }
+  __syncthreads();
+  const Args& g = gg;
   const i64 n = g.n;
-  const i64 stride = (i64)nb * kBlock;
-  const i64 first = (i64)blockIdx.x * kBlock + threadIdx.x;
+  const int world = g.d.world, rank = g.d.rank;
+  const bool dist = world > 1;
+  int* err = &pr.out->err;
+  u64* bar = pr.bar;
   const bool hist = g.hist_mask != 0;
-  const bool has_xt = g.xtrue != nullptr && (g.hist_mask & 5u);
-  Scal s = *g.sc;                                  // the recurrences live in registers
-  u64 nbar = 0;
-  int buf = 0;
-  const VecIn in0{SpIn<SP>::v0(g), nullptr, nullptr};
-  const double* v1p = SpIn<SP>::v1(g);
+  const bool has_xt = (g.hist_mask & 5u) != 0;
+  const i64 pl = g.d.plane;
+  WinHdr* mywin = dist ? g.d.win[rank] : nullptr;
 
-  for (int k = pa.k0; k <= pa.k1; ++k) {
-    // ---- vector stage(s) ----------------------------------------------------------
-    {
-      double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
-      for (i64 i = first; i < n; i += stride) ew_body<EW, PM, 1>(g, i, s.a, s.b, red);
-      if constexpr (NRE > 0) {
-        double r8[kPersRed] = {red[0], red[1], red[2], red[3], 0.0, 0.0, 0.0, 0.0};
-        pers_put<NRE>(r8, pa.part + (size_t)buf * kPersMaxGrid * kPersRed, sh);
+  // ---- state -> shared memory ---------------------------------------------------------
+  {
+    int slot = 0;
+    for (int v = 0; v < 10; ++v) {
+      if (!(L.vmask & (1u << v))) continue;
+      const double* src = pr.vecs[v];
+      double* dst = smem + (size_t)slot * L.R * T;
+      for (int j = 0; j < L.R; ++j) {
+        const i64 row = ((i64)j * nb + cta) * T + tid;
+        if (row < n) dst[j * T + tid] = src[row];
       }
-      grid_barrier(pa.bar, (u64)nb * (++nbar), pa.err);
-      if constexpr (NRE > 0) {
-        double acc[kPersRed];
-        pers_get<NRE>(pa.part + (size_t)buf * kPersMaxGrid * kPersRed, nb, acc);
-        apply_finalize(EwKind<EW>::FK, MEUR, &s, acc, k);
-        buf ^= 1;
+      ++slot;
+    }
+    if (PM == 1) {
+      double* dst = smem + (size_t)slot * L.R * T;
+      for (int j = 0; j < L.R; ++j) {
+        const i64 row = ((i64)j * nb + cta) * T + tid;
+        if (row < n) dst[j * T + tid] = g.dinv[row];
       }
     }
-    if constexpr (VAR == CGX_HS) {                 // hs_cg.py:117,119,122: needs beta from nu
-      double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
-      for (i64 i = first; i < n; i += stride) ew_body<EW_HS2, PM, 1>(g, i, s.a, s.b, red);
-      grid_barrier(pa.bar, (u64)nb * (++nbar), pa.err);
-    }
-    // ---- SpMV stage with the fused epilogue (+ instrumentation) --------------------
-    {
-      double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
-      double hs[4] = {0.0, 0.0, 0.0, 0.0};
-      for (i64 i = first; i < n; i += stride) {
-        if (hist) {
-          double y[NV + 2];
-          A.template row<NV + 2>(i, [&](i64 j, double (&v)[NV + 2]) {
-            v[0] = in0.v[j];
-            if constexpr (NV == 2) v[1] = v1p[j];
-            const double xj = g.x[j];
-            v[NV] = xj;
-            v[NV + 1] = has_xt ? sub_(xj, g.xtrue[j]) : 0.0;
-          }, y);
-          double ysp[NV];
+  }
+  __syncthreads();
+
+  Scal s;                                                      // the recurrences live in registers
+  {
+    const Scal* i0 = &g.sc[dist ? g.scpar : 0];
+    s.a = i0->a; s.a1 = i0->a1; s.b = i0->b; s.nu = i0->nu; s.nu1 = i0->nu1; s.mu = i0->mu; s.eta = i0->eta;
+    s.del = i0->del; s.gam = i0->gam; s.breakdown = i0->breakdown;
+  }
+  u64 nbar = 0, epoch = pr.epoch0;
+  u64 hep[kChan];
 #pragma unroll
-          for (int c = 0; c < NV; ++c) ysp[c] = y[c];
-          sp_epilogue<SP, PM, NV>(g, in0, i, ysp, red, nullptr);
-          if (has_xt) {                            // callbacks/error_A_norm.py, error_2_norm.py
-            const double e = sub_(g.x[i], g.xtrue[i]);
-            hs[0] = fma(e, y[NV + 1], hs[0]);
-            hs[2] = fma(e, e, hs[2]);
-          }
-          const double res = sub_(g.b[i], y[NV]);  // callbacks/residual_2_norm.py
-          hs[1] = fma(res, res, hs[1]);
-          const double ri = g.r[i];                // callbacks/updated_residual_2_norm.py
-          hs[3] = fma(ri, ri, hs[3]);
-        } else {
-          double y[NV];
-          A.template row<NV>(i, [&](i64 j, double (&v)[NV]) {
-            v[0] = in0.v[j];
-            if constexpr (NV == 2) v[1] = v1p[j];
-          }, y);
-          sp_epilogue<SP, PM, NV>(g, in0, i, y, red, nullptr);
+  for (int c = 0; c < kChan; ++c) hep[c] = pr.hepoch0[c];
+  int buf = 0;
+  PersRec pend[3];
+  int npend = 0;
+
+  // ---- sync point: every CTA of the rank has finished the stage; optionally the rank's
+  //      record (NR sums) is formed and, on a partition, published with the halo epochs
+  auto sync_point = [&](double (&red)[kPersRed], int NR, int kind, int k, bool rec_hist, int halo_n, int halo_ch) {
+    double* part = pr.part + (size_t)buf * kPersMaxGrid * kPersRed;
+    if (NR > 0) {
+      double v[kPersRed];
+#pragma unroll
+      for (int j = 0; j < kPersRed; ++j) v[j] = red[j];
+      block_sum<kPersRed>(v, sh);
+      if (tid == 0) {
+#pragma unroll
+        for (int j = 0; j < kPersRed; ++j) __stcg(&part[(size_t)cta * kPersRed + j], v[j]);
+      }
+    }
+    ++nbar;
+    const u64 target = (u64)nb * nbar;
+    u64 e = 0;
+    if (NR > 0) e = ++epoch;
+    __syncthreads();
+    if (tid == 0) {
+      if (dist) fence_acq_rel_sys(); else fence_acq_rel_gpu();
+      const u64 t = atomicAdd(reinterpret_cast<unsigned long long*>(bar), 1ull);
+      sh_last = (t == target - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (dist && sh_last && tid < 32) {                         // warp 0 of the last CTA: publish
+      fence_acq_rel_gpu();
+      if (NR > 0) {
+        const int slot = (int)(e % kSlots);
+        double tot[kPersRed];
+#pragma unroll
+        for (int j = 0; j < kPersRed; ++j) {
+          double t = 0.0;
+          for (int b = tid; b < nb; b += 32) t += __ldcg(&part[(size_t)b * kPersRed + j]);
+          tot[j] = warp_sum(t);
+        }
+        if (tid < world) {
+          volatile double* dst = g.d.win[tid]->sums[slot][rank];
+#pragma unroll
+          for (int j = 0; j < kPersRed; ++j) dst[j] = tot[j];
+          fence_acq_rel_sys();
+          st_release_sys(&g.d.win[tid]->sflag[slot][rank], e);
         }
       }
-      double* part = pa.part + (size_t)buf * kPersMaxGrid * kPersRed;
-      if (NRS > 0 || hist) {
-        double r8[kPersRed] = {red[0], red[1], red[2], red[3], hs[0], hs[1], hs[2], hs[3]};
-        if (hist) pers_put<kPersRed>(r8, part, sh);
-        else if constexpr (NRS > 0) pers_put<NRS>(r8, part, sh);
+      if (halo_n > 0 && tid == 0) {
+        for (int c = 0; c < halo_n; ++c) {
+          const int ch = halo_ch + c;
+          const int par = (int)(hep[ch] & 1);
+          if (g.d.has_lo) st_release_sys(&g.d.win[rank - 1]->hflag[ch][par][1], hep[ch]);
+          if (g.d.has_hi) st_release_sys(&g.d.win[rank + 1]->hflag[ch][par][0], hep[ch]);
+        }
       }
-      grid_barrier(pa.bar, (u64)nb * (++nbar), pa.err);
-      if (NRS > 0 || hist) {
+    }
+    if (tid == 0) pers_wait_gpu(bar, target, err);
+    __syncthreads();
+    if (NR > 0) {
+      if (dist) {
+        pend[npend].e = e; pend[npend].kind = kind; pend[npend].k = k; pend[npend].hist = rec_hist ? 1 : 0;
+        ++npend;
+      } else {                                                 // one GPU: every warp adds the partials itself
         double acc[kPersRed];
-        if (hist) pers_get<kPersRed>(part, nb, acc);
-        else if constexpr (NRS > 0) pers_get<NRS>(part, nb, acc);
-        if constexpr (NRS > 0) apply_finalize(SpTraits<SP>::FK, MEUR, &s, acc, k);
-        if (hist && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int lane = tid & 31;
+#pragma unroll
+        for (int j = 0; j < kPersRed; ++j) {
+          double t = 0.0;
+          for (int b = lane; b < nb; b += 32) t += __ldcg(&part[(size_t)b * kPersRed + j]);
+          acc[j] = warp_sum(t);
+        }
+        if (kind != FK_NONE) apply_finalize(kind, MEUR, &s, acc, k);
+        if (rec_hist && cta == 0 && tid == 0) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (g.hist_mask & (1u << j)) g.hist[(i64)j * g.hist_len + k] = sqrt(acc[4 + j]);
         }
-        buf ^= 1;
+      }
+      buf ^= 1;
+    }
+  };
+
+  // ---- partition: fold the published records of all ranks into the scalars ---------------
+  auto fold_pending = [&]() {
+    if (!dist) return;
+    for (int q = 0; q < npend; ++q) {
+      const u64 e = pend[q].e;
+      const int slot = (int)(e % kSlots);
+      __syncthreads();
+      if (tid < 32) {
+        double v[kPersRed];
+#pragma unroll
+        for (int j = 0; j < kPersRed; ++j) v[j] = 0.0;
+        if (tid < world) {
+          if (g.d.mode != 3) pers_wait_sys(&mywin->sflag[slot][tid], e, err);
+          const int src = (g.d.mode == 3) ? rank : tid;        // stub: the local record stands in
+#pragma unroll
+          for (int j = 0; j < kPersRed; ++j) v[j] = __ldcv(&mywin->sums[slot][src][j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kPersRed; ++j) {
+          double t = 0.0;
+          for (int r = 0; r < world; ++r) t += __shfl_sync(0xffffffffu, v[j], r);
+          if (tid == 0) sh_acc[j] = t;
+        }
+      }
+      __syncthreads();
+      double acc[kPersRed];
+#pragma unroll
+      for (int j = 0; j < kPersRed; ++j) acc[j] = sh_acc[j];
+      if (pend[q].kind != FK_NONE) apply_finalize(pend[q].kind, MEUR, &s, acc, pend[q].k);
+      if (pend[q].hist && cta == 0 && tid == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (g.hist_mask & (1u << j)) g.hist[(i64)j * g.hist_len + pend[q].k] = sqrt(acc[4 + j]);
       }
     }
+    npend = 0;
+  };
+
+  // ---- export the SpMV input(s) (and x when instrumenting) of the rows this CTA owns ------
+  auto export_inputs = [&](int par) {
+    const double* l0 = args_vec(gl, SpInV<SP>::v0);
+    const double* l1 = NV == 2 ? args_vec(gl, SpInV<SP>::v1 < 0 ? 0 : SpInV<SP>::v1) : nullptr;
+    double* e0 = pr.exp_[par][0];
+    double* e1 = pr.exp_[par][1];
+    if (dist) { ++hep[0]; if (NV == 2) ++hep[1]; if (hist) ++hep[2]; }
+    const int hp0 = (int)(hep[0] & 1), hp1 = (int)(hep[1] & 1), hp2 = (int)(hep[2] & 1);
+    for (int j = 0; j < L.R; ++j) {
+      const i64 row = ((i64)j * nb + cta) * T + tid;
+      if (row >= n) continue;
+      const double a0 = l0[j * T + tid];
+      e0[row] = a0;
+      double a1 = 0.0, xv = 0.0;
+      if (NV == 2) { a1 = l1[j * T + tid]; e1[row] = a1; }
+      if (hist) { xv = gl.x[j * T + tid]; pr.vecs[0][row] = xv; }
+      if (dist) {
+        if (g.d.has_lo && row < pl) {
+          g.d.ghost_lo[ghost_off(g.d, 0, hp0, 1) + row] = a0;
+          if (NV == 2) g.d.ghost_lo[ghost_off(g.d, 1, hp1, 1) + row] = a1;
+          if (hist) g.d.ghost_lo[ghost_off(g.d, 2, hp2, 1) + row] = xv;
+        }
+        if (g.d.has_hi && row >= n - pl) {
+          const i64 o = row - (n - pl);
+          g.d.ghost_hi[ghost_off(g.d, 0, hp0, 0) + o] = a0;
+          if (NV == 2) g.d.ghost_hi[ghost_off(g.d, 1, hp1, 0) + o] = a1;
+          if (hist) g.d.ghost_hi[ghost_off(g.d, 2, hp2, 0) + o] = xv;
+        }
+      }
+    }
+  };
+
+  // does this CTA own rows of the first / last plane (it then reads ghost planes)?
+  bool touch_lo = false, touch_hi = false;
+  if (dist) {
+    for (int j = 0; j < L.R; ++j) {
+      const i64 r0 = ((i64)j * nb + cta) * T, r1 = min(n, r0 + T);
+      if (r0 < n && r0 < pl) touch_lo = true;
+      if (r0 < n && r1 > n - pl) touch_hi = true;
+    }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *g.sc = s;
+  auto wait_halo = [&](int ch) {
+    if (tid == 0) {
+      const int par = (int)(hep[ch] & 1);
+      if (touch_lo && g.d.has_lo) pers_wait_sys(&mywin->hflag[ch][par][0], hep[ch], err);
+      if (touch_hi && g.d.has_hi) pers_wait_sys(&mywin->hflag[ch][par][1], hep[ch], err);
+    }
+  };
+
+  for (int k = L.k0; k <= L.k1; ++k) {
+    const int par = k & 1;
+    double red[kPersRed];
+    // ---- vector stage(s) ----------------------------------------------------------
+    fold_pending();
+#pragma unroll
+    for (int j = 0; j < kPersRed; ++j) red[j] = 0.0;
+    {
+      double r4[kNRed] = {0.0, 0.0, 0.0, 0.0};
+      for (int j = 0; j < L.R; ++j) {
+        const i64 row = ((i64)j * nb + cta) * T + tid;
+        if (row < n) ew_body<EW, PM, 1>(gl, (i64)j * T + tid, s.a, s.b, r4);
+      }
+#pragma unroll
+      for (int j = 0; j < kNRed; ++j) red[j] = r4[j];
+    }
+    if constexpr (VAR == CGX_HS) {                 // hs_cg.py:120-122: beta needs nu first
+      sync_point(red, NRE, EwKind<EW>::FK, k, false, 0, 0);
+      fold_pending();
+      double r4[kNRed] = {0.0, 0.0, 0.0, 0.0};
+      for (int j = 0; j < L.R; ++j) {
+        const i64 row = ((i64)j * nb + cta) * T + tid;
+        if (row < n) ew_body<EW_HS2, PM, 1>(gl, (i64)j * T + tid, s.a, s.b, r4);
+      }
+      export_inputs(par);
+      sync_point(red, 0, FK_NONE, k, false, hist ? 3 : 1, 0);
+    } else {
+      export_inputs(par);
+      sync_point(red, NRE, EwKind<EW>::FK, k, false, hist ? 3 : NV, 0);
+    }
+    // ---- SpMV stage with the fused epilogue (+ instrumentation) --------------------
+#pragma unroll
+    for (int j = 0; j < kPersRed; ++j) red[j] = 0.0;
+    {
+      if (dist) {
+        wait_halo(0);
+        if (NV == 2) wait_halo(1);
+        if (hist) wait_halo(2);
+        if (hist && has_xt && tid == 0) {          // x_true ghosts, pushed when the problem was loaded
+          if (touch_lo && g.d.has_lo) pers_wait_sys(&mywin->hflag[3][g.xt_par][0], g.xt_epoch, err);
+          if (touch_hi && g.d.has_hi) pers_wait_sys(&mywin->hflag[3][g.xt_par][1], g.xt_epoch, err);
+        }
+        __syncthreads();
+      }
+      const int hp0 = (int)(hep[0] & 1), hp1 = (int)(hep[1] & 1), hp2 = (int)(hep[2] & 1);
+      VecIn in0{pr.exp_[par][0], nullptr, nullptr}, in1{pr.exp_[par][1], nullptr, nullptr};
+      VecIn xin{pr.vecs[0], nullptr, nullptr}, xtin{g.xtrue, nullptr, nullptr};
+      if (dist) {
+        in0.lo = g.d.ghost + ghost_off(g.d, 0, hp0, 0); in0.hi = g.d.ghost + ghost_off(g.d, 0, hp0, 1);
+        in1.lo = g.d.ghost + ghost_off(g.d, 1, hp1, 0); in1.hi = g.d.ghost + ghost_off(g.d, 1, hp1, 1);
+        xin.lo = g.d.ghost + ghost_off(g.d, 2, hp2, 0); xin.hi = g.d.ghost + ghost_off(g.d, 2, hp2, 1);
+        xtin.lo = g.d.ghost + ghost_off(g.d, 3, g.xt_par, 0); xtin.hi = g.d.ghost + ghost_off(g.d, 3, g.xt_par, 1);
+      }
+      auto ldv = [&](const VecIn& a, i64 j) -> double {
+        if constexpr (SL) {
+          if (j < 0) return __ldcg(a.lo + (j + pl));
+          if (j >= n) return __ldcg(a.hi + (j - n));
+        }
+        return __ldcg(a.v + j);
+      };
+      const VecIn loc0{args_vec(gl, SpInV<SP>::v0), nullptr, nullptr};
+      double r4[kNRed] = {0.0, 0.0, 0.0, 0.0};
+      double hs[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int j = 0; j < L.R; ++j) {
+        const i64 row = ((i64)j * nb + cta) * T + tid;
+        if (row >= n) continue;
+        const i64 li = (i64)j * T + tid;
+        if (hist) {
+          double y[NV + 2];
+          A.template row<NV + 2>(row, [&](i64 c, double (&v)[NV + 2]) {
+            v[0] = ldv(in0, c);
+            if constexpr (NV == 2) v[1] = ldv(in1, c);
+            const double xj = ldv(xin, c);
+            v[NV] = xj;
+            v[NV + 1] = has_xt ? sub_(xj, ldv(xtin, c)) : 0.0;
+          }, y);
+          double ysp[NV];
+#pragma unroll
+          for (int c = 0; c < NV; ++c) ysp[c] = y[c];
+          sp_epilogue<SP, PM, NV>(gl, loc0, li, ysp, r4, nullptr);
+          if (has_xt) {                            // callbacks/error_A_norm.py, error_2_norm.py
+            const double e = sub_(gl.x[li], g.xtrue[row]);
+            hs[0] = fma(e, y[NV + 1], hs[0]);
+            hs[2] = fma(e, e, hs[2]);
+          }
+          const double res = sub_(g.b[row], y[NV]);  // callbacks/residual_2_norm.py
+          hs[1] = fma(res, res, hs[1]);
+          const double ri = gl.r[li];                // callbacks/updated_residual_2_norm.py
+          hs[3] = fma(ri, ri, hs[3]);
+        } else {
+          double y[NV];
+          A.template row<NV>(row, [&](i64 c, double (&v)[NV]) {
+            v[0] = ldv(in0, c);
+            if constexpr (NV == 2) v[1] = ldv(in1, c);
+          }, y);
+          sp_epilogue<SP, PM, NV>(gl, loc0, li, y, r4, nullptr);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { red[j] = r4[j]; red[4 + j] = hs[j]; }
+    }
+    if (NRS > 0 || hist) sync_point(red, kPersRed, SpTraits<SP>::FK, k, hist, 0, 0);
+  }
+  fold_pending();
+
+  // ---- shared memory -> state; scalars and epoch counters back to the host's view ---------
+  __syncthreads();
+  {
+    int slot = 0;
+    for (int v = 0; v < 10; ++v) {
+      if (!(L.vmask & (1u << v))) continue;
+      double* dstv = pr.vecs[v];
+      const double* src = smem + (size_t)slot * L.R * T;
+      for (int j = 0; j < L.R; ++j) {
+        const i64 row = ((i64)j * nb + cta) * T + tid;
+        if (row < n) dstv[row] = src[j * T + tid];
+      }
+      ++slot;
+    }
+  }
+  if (cta == 0 && tid == 0) {
+    Scal* o = &g.sc[dist ? g.scpar : 0];           // (tmp[] is initialisation scratch: not kept live)
+    o->a = s.a; o->a1 = s.a1; o->b = s.b; o->nu = s.nu; o->nu1 = s.nu1; o->mu = s.mu; o->eta = s.eta;
+    o->del = s.del; o->gam = s.gam; o->breakdown = s.breakdown;
+    pr.out->epoch = epoch;
+    for (int c = 0; c < kChan; ++c) pr.out->hepoch[c] = hep[c];
+  }
 }
 
 }  // namespace cgx

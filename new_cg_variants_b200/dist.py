@@ -209,7 +209,7 @@ class DistSession(_RankBase):
 
     def run(self, variant, max_iter, histories=(), path="auto"):
         info = _lib.CgxInfo()
-        p = _lib.PATHS["stream" if self.world > 1 else path]
+        p = _lib.PATHS[path]
         rc = self._lib.cgx_run(self._ctx, _lib.VARIANT_IDS[variant], int(max_iter), _mask(histories), p,
                                C.byref(info))
         _lib.check(rc, allow_breakdown=True)
@@ -217,14 +217,15 @@ class DistSession(_RankBase):
         self._max_iter = int(max_iter)
         return self.info
 
-    def solve_local(self, variant, b_loc, x0_loc, max_iter, x_true_loc=None, histories=(), return_x=True):
+    def solve_local(self, variant, b_loc, x0_loc, max_iter, x_true_loc=None, histories=(), return_x=True,
+                    path="auto"):
         """The C-ABI round trip with this rank's HOST slices (cgx_solve_host)."""
         mask = _mask(histories)
         x = np.empty(self.n) if return_x else None
         hist = np.zeros((len(_lib.HIST_NAMES), int(max_iter))) if mask else None
         info = _lib.CgxInfo()
         rc = self._lib.cgx_solve_host(self._ctx, _lib.VARIANT_IDS[variant], _lib.dptr(b_loc), _lib.dptr(x0_loc),
-                                      _lib.dptr(x_true_loc), self.n, int(max_iter), mask, _lib.PATHS["stream"],
+                                      _lib.dptr(x_true_loc), self.n, int(max_iter), mask, _lib.PATHS[path],
                                       _lib.dptr(x), _lib.dptr(hist), C.byref(info))
         _lib.check(rc, allow_breakdown=True)
         self.info = info.as_dict()
@@ -235,9 +236,9 @@ class DistSession(_RankBase):
                 out[name] = hist[i].copy()
         return x, out, self.info
 
-    def solve(self, variant, b, x0, max_iter, x_true=None, histories=_lib.HIST_NAMES, return_x=True):
+    def solve(self, variant, b, x0, max_iter, x_true=None, histories=_lib.HIST_NAMES, return_x=True, path="auto"):
         return self.solve_local(variant, self.local(b), self.local(x0), max_iter, self.local(x_true),
-                                histories, return_x)
+                                histories, return_x, path)
 
     def gather_x(self, x_local):
         """Global x on every rank (host side, through torch.distributed objects)."""
@@ -309,13 +310,13 @@ class GroupSession:
             _lib.check(self._lib.cgx_group_load_problem_host(self._arr, self.world, _lib.dptr(b), _lib.dptr(x0),
                                                              _lib.dptr(xt), self.n))
 
-    def begin(self, variant, max_iter, histories=()):
+    def begin(self, variant, max_iter, histories=(), path="stream"):
         if self.world == 1:
             _lib.check(self._lib.cgx_begin(self.members[0]._ctx, _lib.VARIANT_IDS[variant], int(max_iter),
-                                           _mask(histories), _lib.PATHS["stream"]))
+                                           _mask(histories), _lib.PATHS[path]))
         else:
             _lib.check(self._lib.cgx_group_begin(self._arr, self.world, _lib.VARIANT_IDS[variant], int(max_iter),
-                                                 _mask(histories)))
+                                                 _mask(histories), _lib.PATHS[path]))
         self._max_iter = int(max_iter)
         for m in self.members:
             m._max_iter = int(max_iter)
@@ -326,10 +327,10 @@ class GroupSession:
         else:
             _lib.check(self._lib.cgx_group_advance(self._arr, self.world, int(niter)))
 
-    def solve(self, variant, b, x0, max_iter, x_true=None, histories=_lib.HIST_NAMES):
+    def solve(self, variant, b, x0, max_iter, x_true=None, histories=_lib.HIST_NAMES, path="stream"):
         """-> (global x, {history: array}, [per-rank info])."""
         self.load_problem(b, x0, x_true)
-        self.begin(variant, max_iter, histories)
+        self.begin(variant, max_iter, histories, path)
         self.advance(max_iter - 1)
         xs, hists = [], []
         for m in self.members:

@@ -38,7 +38,7 @@ def main():
         sess = DistSession(S, dinv=dinv, device=local, mode=mode)
         results = {}
         for tag in ("hs", "cg", "gv", "pr", "m", "pipe_pr", "pipe_p"):
-            x_loc, h, info = sess.solve(tag, b, x0, 25, x_true=x_true, histories=hist)
+            x_loc, h, info = sess.solve(tag, b, x0, 25, x_true=x_true, histories=hist, path="stream")
             x = sess.gather_x(x_loc)
             results[tag] = (x, h)
         sess.close()

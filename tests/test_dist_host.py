@@ -1,0 +1,98 @@
+"""CPU (-m "not gpu"): host-side logic of the row-partitioned multi-GPU path -- slab
+partition, slicing of global vectors, the handle exchange through torch.distributed
+(gloo, world_size 2) -- and that a rank fails loudly without a GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from new_cg_variants_b200 import PoissonStencil
+from new_cg_variants_b200 import dist as cdist
+
+
+def test_partition_planes_tiles_the_grid():
+    for nz in (1, 2, 7, 8, 64, 256):
+        for world in (1, 2, 3, 4, 8):
+            if nz < world:
+                with pytest.raises(ValueError):
+                    cdist.partition_planes(nz, world)
+                continue
+            parts = cdist.partition_planes(nz, world)
+            assert parts[0][0] == 0 and parts[-1][1] == nz
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 1
+
+
+def test_row_ranges_and_2d_slab_view():
+    S3 = PoissonStencil(6, 5, 9, dim=3)
+    assert cdist.slab_grid(S3) == (6, 5, 9)
+    ranges = [cdist.row_range(S3, 4, r) for r in range(4)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == S3.shape[0]
+    assert all(r[0] % 30 == 0 and r[1] % 30 == 0 for r in ranges)
+    S2 = PoissonStencil(8, 10, 1, dim=2)            # 2-D: planes are grid rows
+    assert cdist.slab_grid(S2) == (8, 1, 10)
+    assert cdist.row_range(S2, 2, 1) == (40, 80)
+    # the slab view is the same operator: nx x 1 x ny 3-D stencil with the 2-D diagonal
+    A2 = S2.tocsr()
+    A3 = PoissonStencil(8, 1, 10, dim=3, diag=S2.diag).tocsr()
+    assert (A2 != A3).nnz == 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        S = PoissonStencil(4, 3, 5, dim=3)
+        n = S.shape[0]
+        v = np.arange(n, dtype=np.float64)
+        r0, r1 = cdist.row_range(S, world, rank)
+        # what DistSession does with the window handles: one fixed-size payload per rank, rank order
+        payload = bytes([rank]) * 64
+        got = cdist.exchange_bytes(payload)
+        ok_handles = got == [bytes([r]) * 64 for r in range(world)]
+        # gather_x: local slices concatenated in rank order reproduce the global vector
+        parts = cdist.exchange_bytes(v[r0:r1].tobytes())
+        glob = np.concatenate([np.frombuffer(p, dtype=np.float64) for p in parts])
+        ok_gather = np.array_equal(glob, v)
+        # a rank without a GPU must fail loudly (no CPU fallback)
+        try:
+            cdist.DistSession(S, dinv=None, device=0)
+            loud = False
+        except Exception as e:          # CgxError (no CUDA device) -- never a silent CPU path
+            loud = "CUDA" in str(e) or "cuda" in str(e) or "device" in str(e)
+        q.put((rank, ok_handles, ok_gather, loud))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_exchange_and_loud_failure():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only test (on a GPU box the real path is exercised by test_gpu_dist.py)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True, True, True), (1, True, True, True)]
+
+
+def test_nccl_library_path_resolves():
+    p = cdist.nccl_library_path()
+    assert p.endswith("libnccl.so.2")

@@ -103,3 +103,42 @@ def test_two_processes_two_gpus_match_emulation():
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "dist_worker ok" in out.stdout
+
+
+@pytest.mark.parametrize("shape,world", [((16, 12, 8), 2), ((64, 10, 9), 3), ((20, 18, 16), 8), ((64, 64, 16), 4)])
+def test_partitioned_persistent_kernel(shape, world):
+    """The persistent kernel on a partition: all ranks inside ONE cooperative launch (CTA range
+    r*nb..(r+1)*nb-1 acts as rank r; windows, ghost planes and flags as between GPUs).  Against
+    the stream path of the same partition: rounding-level agreement; bitwise repeatable;
+    resumable; histories identical on every rank."""
+    nx, ny, nz = shape
+    S = PoissonStencil(nx, ny, nz, dim=3)
+    x_true, b, x0 = _problem(S)
+    n = S.shape[0]
+    for dinv in (1 / S.diagonal(), 1 / (S.diagonal() + np.arange(n) % 3), None):
+        grp = GroupSession(S, world, dinv=dinv)
+        try:
+            for tag in ALL_TAGS:
+                xs, hs, _ = grp.solve(tag, b, x0, 14, x_true=x_true, path="stream")
+                xp, hp, infos = grp.solve(tag, b, x0, 14, x_true=x_true, path="persistent")
+                xp2, hp2, _ = grp.solve(tag, b, x0, 14, x_true=x_true, path="persistent")
+                assert infos[0]["path"] == 2
+                np.testing.assert_allclose(xp, xs, rtol=1e-9, atol=1e-13, err_msg=f"{shape}x{world}/{tag}")
+                assert np.array_equal(xp, xp2)
+                for h in orc.HISTORIES:
+                    np.testing.assert_allclose(hp[h][:10], hs[h][:10], rtol=1e-10, err_msg=f"{shape}x{world}/{tag}/{h}")
+                    assert np.array_equal(hp[h], hp2[h], equal_nan=True)
+            # no instrumentation (the timed configuration) and a run cut into pieces
+            grp.load_problem(b, x0, x_true)
+            grp.begin("pipe_pr", 40, (), path="persistent")
+            grp.advance(39)
+            x_one = np.concatenate([m.fetch_local(want_hist=False)[0] for m in grp.members])
+            grp.begin("pipe_pr", 40, (), path="persistent")
+            for chunk in (1, 5, 33):
+                grp.advance(chunk)
+            x_cut = np.concatenate([m.fetch_local(want_hist=False)[0] for m in grp.members])
+            assert np.array_equal(x_one, x_cut)
+            sc = [m.scalars() for m in grp.members]
+            assert all(s == sc[0] for s in sc)
+        finally:
+            grp.close()
