@@ -919,11 +919,11 @@ static PersGeom pers_geometry(const cgx_ctx* c, int variant, int ranks_in_launch
   int T = c->pers_threads ? c->pers_threads : (c->n <= (i64)sm_cap * 256 ? 256 : 512);
   T = std::min(512, std::max(32, (T + 31) / 32 * 32));
   const i64 chunks = (c->n + T - 1) / T;
-  int cap = c->pers_ctas ? std::min(c->pers_ctas, sm_cap) : sm_cap;
+  int cap = c->pers_ctas ? std::min(c->pers_ctas, 4 * sm_cap) : sm_cap;     // co-residency is checked at launch
   cap = std::max(1, std::min(cap, kPersMaxGrid / std::max(1, ranks_in_launch)));
   const i64 R = (chunks + cap - 1) / cap;
   G.T = T; G.R = (int)R; G.nb = (int)((chunks + R - 1) / R);
-  G.smem = (size_t)G.nslot * R * T * sizeof(double);
+  G.smem = (size_t)G.nslot * R * T * sizeof(double) + (((size_t)R * T + 15) / 16) * 16;   // + row masks
   G.ok = G.smem <= 216 * 1024;
   return G;
 }

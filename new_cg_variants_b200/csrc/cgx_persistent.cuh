@@ -28,6 +28,8 @@
 // (r+1)*nb-1 acts as rank r): that is how the multi-GPU protocol of this kernel is tested on
 // a single GPU without ever having two launches wait for each other.
 #pragma once
+#include <type_traits>
+
 #include "cgx_kernels.cuh"
 
 namespace cgx {
@@ -120,6 +122,42 @@ __device__ __forceinline__ double*& args_vec(Args& g, int v) {
   }
 }
 
+// Row product inside the persistent kernel.  The stencil's neighbour pattern of a row does not
+// change between iterations: it is decoded once (two integer divisions) into a 6-bit mask kept
+// in shared memory; the sum keeps the canonical term order of StencilOp::row.
+__device__ __forceinline__ unsigned stencil_mask(const StencilOp& A, int row) {
+  const int plane = A.nx * A.ny;
+  const int z = row / plane, rem = row - z * plane, yy = rem / A.nx, xx = rem - yy * A.nx;
+  return (unsigned)((z > 0 || A.has_zlo) ? 1 : 0) | ((yy > 0) ? 2u : 0u) | ((xx > 0) ? 4u : 0u) |
+         ((xx < A.nx - 1) ? 8u : 0u) | ((yy < A.ny - 1) ? 16u : 0u) | ((z < A.nz - 1 || A.has_zhi) ? 32u : 0u);
+}
+__device__ __forceinline__ unsigned stencil_mask(const CsrOp&, int) { return 0u; }
+
+template <int NVX, class Ld>
+__device__ __forceinline__ void pers_row(const StencilOp& A, int row, unsigned m, Ld ld, double (&y)[NVX]) {
+  const int plane = A.nx * A.ny;
+  double v[NVX];
+#pragma unroll
+  for (int c = 0; c < NVX; ++c) y[c] = 0.0;
+#define CGX_PT(bit, j, coef)                                                               \
+  if (m & (bit)) {                                                                         \
+    ld((i64)(j), v);                                                                       \
+    _Pragma("unroll") for (int c = 0; c < NVX; ++c) y[c] = add_(y[c], mul_((coef), v[c])); \
+  }
+  CGX_PT(1u, row - plane, A.off)
+  CGX_PT(2u, row - A.nx, A.off)
+  CGX_PT(4u, row - 1, A.off)
+  CGX_PT(~0u, row, A.diag)
+  CGX_PT(8u, row + 1, A.off)
+  CGX_PT(16u, row + A.nx, A.off)
+  CGX_PT(32u, row + plane, A.off)
+#undef CGX_PT
+}
+template <int NVX, class Ld>
+__device__ __forceinline__ void pers_row(const CsrOp& A, int row, unsigned, Ld ld, double (&y)[NVX]) {
+  A.template row<NVX>((i64)row, ld, y);
+}
+
 struct PersRec { u64 e; int kind; int k; int hist; };      // a published record still to be folded
 
 template <class Op, int VAR, int PM>
@@ -184,6 +222,11 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
       }
     }
   }
+  unsigned char* smask = reinterpret_cast<unsigned char*>(smem + (size_t)L.nslot * L.R * T);
+  for (int j = 0; j < L.R; ++j) {
+    const i64 row = ((i64)j * nb + cta) * T + tid;
+    if (row < n) smask[j * T + tid] = (unsigned char)stencil_mask(A, (int)row);
+  }
   __syncthreads();
 
   Scal s;                                                      // the recurrences live in registers
@@ -202,82 +245,114 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
 
   // ---- sync point: every CTA of the rank has finished the stage; optionally the rank's
   //      record (NR sums) is formed and, on a partition, published with the halo epochs
-  auto sync_point = [&](double (&red)[kPersRed], int NR, int kind, int k, bool rec_hist, int halo_n, int halo_ch) {
+  auto sync_point = [&](double (&red)[kPersRed], auto NRc, int kind, int k, bool rec_hist, int halo_n, int halo_ch) {
+    constexpr int NR = decltype(NRc)::value;                   // sums in the record: 0 (barrier only) .. 8
     double* part = pr.part + (size_t)buf * kPersMaxGrid * kPersRed;
-    if (NR > 0) {
-      double v[kPersRed];
+    double v[NR > 0 ? NR : 1];
+    if constexpr (NR > 0) {
 #pragma unroll
-      for (int j = 0; j < kPersRed; ++j) v[j] = red[j];
-      block_sum<kPersRed>(v, sh);
-      if (tid == 0) {
-#pragma unroll
-        for (int j = 0; j < kPersRed; ++j) __stcg(&part[(size_t)cta * kPersRed + j], v[j]);
-      }
+      for (int j = 0; j < NR; ++j) v[j] = red[j];
+      block_sum<NR>(v, sh);                                    // totals of the CTA in warp 0
     }
-    ++nbar;
-    const u64 target = (u64)nb * nbar;
-    u64 e = 0;
-    if (NR > 0) e = ++epoch;
-    __syncthreads();
-    if (tid == 0) {
-      if (dist) fence_acq_rel_sys(); else fence_acq_rel_gpu();
-      const u64 t = atomicAdd(reinterpret_cast<unsigned long long*>(bar), 1ull);
-      sh_last = (t == target - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (dist && sh_last && tid < 32) {                         // warp 0 of the last CTA: publish
-      fence_acq_rel_gpu();
-      if (NR > 0) {
-        const int slot = (int)(e % kSlots);
-        double tot[kPersRed];
-#pragma unroll
-        for (int j = 0; j < kPersRed; ++j) {
-          double t = 0.0;
-          for (int b = tid; b < nb; b += 32) t += __ldcg(&part[(size_t)b * kPersRed + j]);
-          tot[j] = warp_sum(t);
-        }
-        if (tid < world) {
-          volatile double* dst = g.d.win[tid]->sums[slot][rank];
-#pragma unroll
-          for (int j = 0; j < kPersRed; ++j) dst[j] = tot[j];
-          fence_acq_rel_sys();
-          st_release_sys(&g.d.win[tid]->sflag[slot][rank], e);
-        }
-      }
-      if (halo_n > 0 && tid == 0) {
-        for (int c = 0; c < halo_n; ++c) {
-          const int ch = halo_ch + c;
-          const int par = (int)(hep[ch] & 1);
-          if (g.d.has_lo) st_release_sys(&g.d.win[rank - 1]->hflag[ch][par][1], hep[ch]);
-          if (g.d.has_hi) st_release_sys(&g.d.win[rank + 1]->hflag[ch][par][0], hep[ch]);
-        }
-      }
-    }
-    if (tid == 0) pers_wait_gpu(bar, target, err);
-    __syncthreads();
-    if (NR > 0) {
-      if (dist) {
-        pend[npend].e = e; pend[npend].kind = kind; pend[npend].k = k; pend[npend].hist = rec_hist ? 1 : 0;
-        ++npend;
-      } else {                                                 // one GPU: every warp adds the partials itself
-        double acc[kPersRed];
-        const int lane = tid & 31;
-#pragma unroll
-        for (int j = 0; j < kPersRed; ++j) {
-          double t = 0.0;
-          for (int b = lane; b < nb; b += 32) t += __ldcg(&part[(size_t)b * kPersRed + j]);
-          acc[j] = warp_sum(t);
-        }
-        if (kind != FK_NONE) apply_finalize(kind, MEUR, &s, acc, k);
+    auto finish_local = [&](const double* acc) {               // one GPU: recurrences now
+      if (kind != FK_NONE) apply_finalize(kind, MEUR, &s, acc, k);
+      if constexpr (NR == kPersRed) {
         if (rec_hist && cta == 0 && tid == 0) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (g.hist_mask & (1u << j)) g.hist[(i64)j * g.hist_len + k] = sqrt(acc[4 + j]);
         }
       }
+    };
+    if (!dist && nb == 1) {                                    // a single CTA: shared memory only
+      if constexpr (NR > 0) {
+        if (tid == 0) {
+#pragma unroll
+          for (int j = 0; j < NR; ++j) sh_acc[j] = v[j];
+        }
+      }
+      __syncthreads();
+      if constexpr (NR > 0) {
+        double acc[kPersRed] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < NR; ++j) acc[j] = sh_acc[j];
+        finish_local(acc);
+      }
+      return;
+    }
+    ++nbar;
+    const u64 target = (u64)nb * nbar;
+    u64 e = 0;
+    if (NR > 0) e = ++epoch;
+    if constexpr (NR == 0) __syncthreads();                    // (block_sum already synchronised the CTA)
+    if (tid == 0) {
+      if constexpr (NR > 0) {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) __stcg(&part[(size_t)cta * kPersRed + j], v[j]);
+      }
+      if (dist) {
+        fence_acq_rel_sys();
+        const u64 t = atomicAdd(reinterpret_cast<unsigned long long*>(bar), 1ull);
+        sh_last = (t == target - 1) ? 1 : 0;
+      } else {                                                 // release-add, no round trip
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar), "l"(1ull) : "memory");
+        pers_wait_gpu(bar, target, err);
+      }
+    }
+    __syncthreads();
+    if (dist) {
+      if (sh_last && tid < 32) {                               // warp 0 of the last CTA: publish
+        fence_acq_rel_gpu();
+        if constexpr (NR > 0) {
+          const int slot = (int)(e % kSlots);
+          double tot[NR];
+#pragma unroll
+          for (int j = 0; j < NR; ++j) {
+            double t = 0.0;
+            for (int b = tid; b < nb; b += 32) t += __ldcg(&part[(size_t)b * kPersRed + j]);
+            tot[j] = warp_sum(t);
+          }
+          if (tid < world) {
+            volatile double* dst = g.d.win[tid]->sums[slot][rank];
+#pragma unroll
+            for (int j = 0; j < NR; ++j) dst[j] = tot[j];
+            fence_acq_rel_sys();
+            st_release_sys(&g.d.win[tid]->sflag[slot][rank], e);
+          }
+        }
+        if (halo_n > 0 && tid == 0) {
+          for (int c = 0; c < halo_n; ++c) {
+            const int ch = halo_ch + c;
+            const int par = (int)(hep[ch] & 1);
+            if (g.d.has_lo) st_release_sys(&g.d.win[rank - 1]->hflag[ch][par][1], hep[ch]);
+            if (g.d.has_hi) st_release_sys(&g.d.win[rank + 1]->hflag[ch][par][0], hep[ch]);
+          }
+        }
+      }
+      if (tid == 0) pers_wait_gpu(bar, target, err);
+      __syncthreads();
+    }
+    if constexpr (NR > 0) {
+      if (dist) {
+        pend[npend].e = e; pend[npend].kind = kind; pend[npend].k = k;
+        pend[npend].hist = (rec_hist ? 1 : 0) | (NR << 8);
+        ++npend;
+      } else {                                                 // one GPU: every warp adds the partials itself
+        double acc[kPersRed] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        const int lane = tid & 31;
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          double t = 0.0;
+          for (int b = lane; b < nb; b += 32) t += __ldcg(&part[(size_t)b * kPersRed + j]);
+          acc[j] = warp_sum(t);
+        }
+        finish_local(acc);
+      }
       buf ^= 1;
     }
   };
+  using NR0 = std::integral_constant<int, 0>;
+  using NR8 = std::integral_constant<int, kPersRed>;
 
   // ---- partition: fold the published records of all ranks into the scalars ---------------
   auto fold_pending = [&]() {
@@ -290,11 +365,13 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
         double v[kPersRed];
 #pragma unroll
         for (int j = 0; j < kPersRed; ++j) v[j] = 0.0;
+        const int nr = pend[q].hist >> 8;
         if (tid < world) {
           if (g.d.mode != 3) pers_wait_sys(&mywin->sflag[slot][tid], e, err);
           const int src = (g.d.mode == 3) ? rank : tid;        // stub: the local record stands in
 #pragma unroll
-          for (int j = 0; j < kPersRed; ++j) v[j] = __ldcv(&mywin->sums[slot][src][j]);
+          for (int j = 0; j < kPersRed; ++j)
+            if (j < nr) v[j] = __ldcv(&mywin->sums[slot][src][j]);
         }
 #pragma unroll
         for (int j = 0; j < kPersRed; ++j) {
@@ -308,7 +385,7 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
 #pragma unroll
       for (int j = 0; j < kPersRed; ++j) acc[j] = sh_acc[j];
       if (pend[q].kind != FK_NONE) apply_finalize(pend[q].kind, MEUR, &s, acc, pend[q].k);
-      if (pend[q].hist && cta == 0 && tid == 0) {
+      if ((pend[q].hist & 1) && cta == 0 && tid == 0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (g.hist_mask & (1u << j)) g.hist[(i64)j * g.hist_len + pend[q].k] = sqrt(acc[4 + j]);
@@ -383,7 +460,7 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
       for (int j = 0; j < kNRed; ++j) red[j] = r4[j];
     }
     if constexpr (VAR == CGX_HS) {                 // hs_cg.py:120-122: beta needs nu first
-      sync_point(red, NRE, EwKind<EW>::FK, k, false, 0, 0);
+      sync_point(red, std::integral_constant<int, NRE>{}, EwKind<EW>::FK, k, false, 0, 0);
       fold_pending();
       double r4[kNRed] = {0.0, 0.0, 0.0, 0.0};
       for (int j = 0; j < L.R; ++j) {
@@ -391,10 +468,10 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
         if (row < n) ew_body<EW_HS2, PM, 1>(gl, (i64)j * T + tid, s.a, s.b, r4);
       }
       export_inputs(par);
-      sync_point(red, 0, FK_NONE, k, false, hist ? 3 : 1, 0);
+      sync_point(red, NR0{}, FK_NONE, k, false, hist ? 3 : 1, 0);
     } else {
       export_inputs(par);
-      sync_point(red, NRE, EwKind<EW>::FK, k, false, hist ? 3 : NV, 0);
+      sync_point(red, std::integral_constant<int, NRE>{}, EwKind<EW>::FK, k, false, hist ? 3 : NV, 0);
     }
     // ---- SpMV stage with the fused epilogue (+ instrumentation) --------------------
 #pragma unroll
@@ -419,28 +496,35 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
         xin.lo = g.d.ghost + ghost_off(g.d, 2, hp2, 0); xin.hi = g.d.ghost + ghost_off(g.d, 2, hp2, 1);
         xtin.lo = g.d.ghost + ghost_off(g.d, 3, g.xt_par, 0); xtin.hi = g.d.ghost + ghost_off(g.d, 3, g.xt_par, 1);
       }
-      auto ldv = [&](const VecIn& a, i64 j) -> double {
+      // element c of an exported vector: rows of the CTA's own chunk come from shared memory
+      // (same bits as the exported copy), the rest from L2, ghost planes from the window
+      auto ldv = [&](const VecIn& a, const double* loc, i64 r0, i64 c) -> double {
+        const i64 d = c - r0;
+        if (loc && d >= 0 && d < T && c < n) return loc[d];
         if constexpr (SL) {
-          if (j < 0) return __ldcg(a.lo + (j + pl));
-          if (j >= n) return __ldcg(a.hi + (j - n));
+          if (c < 0) return __ldcg(a.lo + (c + pl));
+          if (c >= n) return __ldcg(a.hi + (c - n));
         }
-        return __ldcg(a.v + j);
+        return __ldcg(a.v + c);
       };
       const VecIn loc0{args_vec(gl, SpInV<SP>::v0), nullptr, nullptr};
+      const double* sl0 = loc0.v;
+      const double* sl1 = NV == 2 ? args_vec(gl, SpInV<SP>::v1 < 0 ? 0 : SpInV<SP>::v1) : nullptr;
       double r4[kNRed] = {0.0, 0.0, 0.0, 0.0};
       double hs[4] = {0.0, 0.0, 0.0, 0.0};
       for (int j = 0; j < L.R; ++j) {
         const i64 row = ((i64)j * nb + cta) * T + tid;
         if (row >= n) continue;
         const i64 li = (i64)j * T + tid;
+        const i64 r0 = ((i64)j * nb + cta) * T;
         if (hist) {
           double y[NV + 2];
-          A.template row<NV + 2>(row, [&](i64 c, double (&v)[NV + 2]) {
-            v[0] = ldv(in0, c);
-            if constexpr (NV == 2) v[1] = ldv(in1, c);
-            const double xj = ldv(xin, c);
+          pers_row<NV + 2>(A, (int)row, smask[li], [&](i64 c, double (&v)[NV + 2]) {
+            v[0] = ldv(in0, sl0 + (i64)j * T, r0, c);
+            if constexpr (NV == 2) v[1] = ldv(in1, sl1 + (i64)j * T, r0, c);
+            const double xj = ldv(xin, gl.x + (i64)j * T, r0, c);
             v[NV] = xj;
-            v[NV + 1] = has_xt ? sub_(xj, ldv(xtin, c)) : 0.0;
+            v[NV + 1] = has_xt ? sub_(xj, ldv(xtin, nullptr, r0, c)) : 0.0;
           }, y);
           double ysp[NV];
 #pragma unroll
@@ -457,9 +541,9 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
           hs[3] = fma(ri, ri, hs[3]);
         } else {
           double y[NV];
-          A.template row<NV>(row, [&](i64 c, double (&v)[NV]) {
-            v[0] = ldv(in0, c);
-            if constexpr (NV == 2) v[1] = ldv(in1, c);
+          pers_row<NV>(A, (int)row, smask[li], [&](i64 c, double (&v)[NV]) {
+            v[0] = ldv(in0, sl0 + (i64)j * T, r0, c);
+            if constexpr (NV == 2) v[1] = ldv(in1, sl1 + (i64)j * T, r0, c);
           }, y);
           sp_epilogue<SP, PM, NV>(gl, loc0, li, y, r4, nullptr);
         }
@@ -467,7 +551,8 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
 #pragma unroll
       for (int j = 0; j < 4; ++j) { red[j] = r4[j]; red[4 + j] = hs[j]; }
     }
-    if (NRS > 0 || hist) sync_point(red, kPersRed, SpTraits<SP>::FK, k, hist, 0, 0);
+    if (hist) sync_point(red, NR8{}, SpTraits<SP>::FK, k, true, 0, 0);
+    else if constexpr (NRS > 0) sync_point(red, std::integral_constant<int, NRS>{}, SpTraits<SP>::FK, k, false, 0, 0);
   }
   fold_pending();
 

@@ -37,21 +37,23 @@ def main():
     for mode in ("p2p", "nccl"):
         sess = DistSession(S, dinv=dinv, device=local, mode=mode)
         results = {}
-        for tag in ("hs", "cg", "gv", "pr", "m", "pipe_pr", "pipe_p"):
-            x_loc, h, info = sess.solve(tag, b, x0, 25, x_true=x_true, histories=hist, path="stream")
-            x = sess.gather_x(x_loc)
-            results[tag] = (x, h)
+        paths = ("stream", "persistent") if mode == "p2p" else ("stream",)
+        for path in paths:
+            for tag in ("hs", "cg", "gv", "pr", "m", "pipe_pr", "pipe_p"):
+                x_loc, h, info = sess.solve(tag, b, x0, 25, x_true=x_true, histories=hist, path=path)
+                x = sess.gather_x(x_loc)
+                results[(tag, path)] = (x, h)
         sess.close()
         if rank == 0:
             grp = GroupSession(S, world, dinv=dinv, devices=[local] * world)
-            for tag, (x, h) in results.items():
-                xg, hg, _ = grp.solve(tag, b, x0, 25, x_true=x_true)
+            for (tag, path), (x, h) in results.items():
+                xg, hg, _ = grp.solve(tag, b, x0, 25, x_true=x_true, path=path)
                 if mode == "p2p":         # same rank-ordered sums: same bits
                     same = np.array_equal(x, xg) and all(np.array_equal(h[k], hg[k], equal_nan=True) for k in hist)
                 else:                     # NCCL picks its own summation tree: rounding-level agreement
                     same = np.allclose(x, xg, rtol=1e-9, atol=1e-13) and \
                         all(np.allclose(h[k][:10], hg[k][:10], rtol=1e-10) for k in hist)
-                print(f"[{mode}] {tag}: {'match' if same else 'MISMATCH'}", flush=True)
+                print(f"[{mode}/{path}] {tag}: {'match' if same else 'MISMATCH'}", flush=True)
                 ok = ok and same
             grp.close()
         dist.barrier()

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--modes", default="p2p,nccl")
     ap.add_argument("--variants", default="hs,cg,pr,gv,pipe_pr")
+    ap.add_argument("--path", default="stream", choices=["stream", "persistent"])
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -47,6 +48,8 @@ def main():
     b, x0 = S @ x_true, np.zeros(n)
     dinv = 1 / S.diagonal()
     res = {}
+    if args.path == "persistent":
+        args.modes = "p2p"          # the persistent kernel exchanges scalars in-kernel only
     for mode in args.modes.split(","):
         sess = DistSession(S, dinv=dinv, device=local, mode=mode)
         sess.load_problem(b, x0, None)
@@ -56,7 +59,7 @@ def main():
                 best = None
                 for rep in range(args.reps + 1):
                     dist.barrier()
-                    info = sess.run(v, args.iters + 1)
+                    info = sess.run(v, args.iters + 1, path=args.path)
                     t = torch.tensor([info["loop_ms"]], dtype=torch.float64, device="cuda")
                     dist.all_reduce(t, op=dist.ReduceOp.MAX)
                     if rep > 0:
@@ -66,7 +69,7 @@ def main():
         sess.close()
         dist.barrier()
     if rank == 0:
-        out = {"workload": f"poisson3d_{args.grid} jacobi, {args.iters} iterations, {world} GPUs, stream path",
+        out = {"workload": f"poisson3d_{args.grid} jacobi, {args.iters} iterations, {world} GPUs, {args.path} path",
                "unit": "us/iteration", "modes": {}}
         for mode in args.modes.split(","):
             m = {}
