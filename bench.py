@@ -152,7 +152,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "hbm_gbs_model": value * (8 * n * W_V[args.variant] + 12 * A.nnz + 4 * (n + 1)) / 1e9,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ our arm
@@ -318,12 +318,30 @@ def run_ours(args, rank, world, local_rank):
             "pct_of_measured_peak": 100 * value * b_iter / 1e9 / measured_peak()[0] / world,
             "roofline": roofline, "cpu_baseline": cpu, "variants": variants,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else any library
+    prints (e.g. NCCL's version banner) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # fd 1 -> stderr for the duration of the run
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

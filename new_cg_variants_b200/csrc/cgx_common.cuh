@@ -130,11 +130,11 @@ __device__ __forceinline__ void grid_sum_finalize(double (&v)[NR], double* __res
 // For kernels without a reduction that still have something to publish when the whole grid
 // is done (halo epochs): `fin()` runs in one thread of the CTA that arrives last.
 template <class Fin>
-__device__ __forceinline__ void grid_last_finalize(unsigned* __restrict__ ticket, Fin fin) {
+__device__ __forceinline__ void grid_last_finalize(unsigned* __restrict__ ticket, Fin fin, bool sys = true) {
   __shared__ bool is_last0;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    if (sys) __threadfence_system(); else __threadfence();
     unsigned t = atomicAdd(ticket, 1u);
     is_last0 = (t == gridDim.x - 1);
     if (is_last0) { *ticket = 0u; fin(); }
@@ -172,8 +172,11 @@ constexpr int kChan = 4;     // halo channels: 0,1 SpMV inputs, 2 x (instrumenta
 typedef unsigned long long u64;
 
 struct WinHdr {
-  double sums[kSlots][kMaxWorld][kSumW];
-  u64 sflag[kSlots][kMaxWorld];
+  // scalar records, "LL" style: every 8-byte word carries half a double and the epoch tag
+  // ((epoch32 << 32) | 32 data bits), so a record needs no separate flag and no fence: the
+  // consumer polls the words themselves (aligned 8-byte stores are single-copy atomic, also
+  // across NVLink).  [slot][producer rank][2 words per value]
+  u64 ll[kSlots][kMaxWorld][2 * kSumW];
   u64 hflag[kChan][2][2];          // [channel][parity][side]; side 0 = plane below, 1 = above
   int error;                       // set when a bounded wait expired
   int pad;
@@ -214,8 +217,32 @@ __device__ __forceinline__ void wait_epoch(const u64* flag, u64 epoch, int* err)
   if (ld_acquire_sys(flag) >= epoch) return;
   const u64 t0 = timer_ns();
   while (ld_acquire_sys(flag) < epoch) {
+    if (*(volatile int*)err) return;
     if (timer_ns() - t0 > 10000000000ull) { atomicExch(err, 1); return; }
   }
+}
+__device__ __forceinline__ void ll_store(u64* dst, double v, u64 epoch) {
+  const u64 b = (u64)__double_as_longlong(v), tag = (epoch & 0xffffffffull) << 32;
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"((b & 0xffffffffull) | tag) : "memory");
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 1), "l"((b >> 32) | tag) : "memory");
+}
+__device__ __forceinline__ u64 ll_poll(const u64* src, u64 tag32, int* err) {
+  u64 w;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+  if ((w >> 32) == tag32) return w;
+  const u64 t0 = timer_ns();
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+    if ((w >> 32) == tag32) return w;
+    if (*(volatile int*)err) return w;
+    if (timer_ns() - t0 > 10000000000ull) { atomicExch(err, 1); return w; }
+  }
+}
+// value j of the record of `epoch` (bounded wait; see wait_epoch)
+__device__ __forceinline__ double ll_load(const u64* rec, int j, u64 epoch, int* err) {
+  const u64 tag = epoch & 0xffffffffull;
+  const u64 lo = ll_poll(rec + 2 * j, tag, err), hi = ll_poll(rec + 2 * j + 1, tag, err);
+  return __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
 }
 __host__ __device__ __forceinline__ size_t ghost_off(const Dist& d, int ch, int par, int side) {
   return ((size_t)(ch * 2 + par) * 2 + side) * (size_t)d.plane;

@@ -197,9 +197,9 @@ __device__ __forceinline__ void dist_publish(const Args& g, const double* acc) {
     if (g.d.mode == 1 || g.d.mode == 3) {
       for (int r = 0; r < g.d.world; ++r) {
         if (g.d.mode == 3 && r != g.d.rank) continue;     // stub: the record stays local
-        volatile double* dst = g.d.win[r]->sums[slot][g.d.rank];
+        u64* dst = g.d.win[r]->ll[slot][g.d.rank];
 #pragma unroll
-        for (int j = 0; j < NR; ++j) dst[j] = acc[j];
+        for (int j = 0; j < NR; ++j) ll_store(dst + 2 * j, acc[j], g.sepoch);
       }
     } else {
       volatile double* dst = g.d.nccl_in + (size_t)slot * kSumW;
@@ -207,23 +207,33 @@ __device__ __forceinline__ void dist_publish(const Args& g, const double* acc) {
       for (int j = 0; j < NR; ++j) dst[j] = acc[j];
     }
   }
-  __threadfence_system();
-  if (NR > 0 && g.d.mode == 1)
-    for (int r = 0; r < g.d.world; ++r) st_relaxed_sys(&g.d.win[r]->sflag[slot][g.d.rank], g.sepoch);
-  dist_publish_halo_flags(g);
+  if (g.hout_n > 0) {                 // the halo planes are bulk data: fence, then their epochs
+    __threadfence_system();
+    dist_publish_halo_flags(g);
+  }
 }
 
 // Consumer side (warp 0 of a CTA): all-rank totals of epoch e, added in rank order.
-__device__ __forceinline__ void dist_totals(const Args& g, u64 e, double (&acc)[kNRed]) {
+// number of sums in a record of kind FK_* (a consumer must not poll words nobody stores)
+__device__ __forceinline__ int fk_width(int kind) {
+  switch (kind) {
+    case FK_NONE: return 0;
+    case FK_CGGV: return 2;
+    case FK_PR_SP: return 3;
+    case FK_PIPE: return 4;
+    default: return 1;               // FK_HS_NU, FK_HS_MU, FK_PR_NU
+  }
+}
+__device__ __forceinline__ void dist_totals(const Args& g, u64 e, int nr, double (&acc)[kNRed]) {
   const int lane = threadIdx.x & 31;
   const int slot = (int)(e % kSlots);
   double v[kNRed] = {0.0, 0.0, 0.0, 0.0};
+  WinHdr* w = g.d.win[g.d.rank];
   if (g.d.mode == 1) {
-    WinHdr* w = g.d.win[g.d.rank];
     if (lane < g.d.world) {
-      wait_epoch(&w->sflag[slot][lane], e, &w->error);
 #pragma unroll
-      for (int j = 0; j < kNRed; ++j) v[j] = __ldcv(&w->sums[slot][lane][j]);
+      for (int j = 0; j < kNRed; ++j)
+        if (j < nr) v[j] = ll_load(w->ll[slot][lane], j, e, &w->error);
     }
 #pragma unroll
     for (int j = 0; j < kNRed; ++j) {
@@ -234,9 +244,9 @@ __device__ __forceinline__ void dist_totals(const Args& g, u64 e, double (&acc)[
   } else if (g.d.mode == 3) {
     // timing stub ("stub_allreduce"): no exchange, no wait -- the local record times the
     // number of ranks stands in for the total (numerically meaningless)
-    WinHdr* w = g.d.win[g.d.rank];
 #pragma unroll
-    for (int j = 0; j < kNRed; ++j) acc[j] = __ldcv(&w->sums[slot][g.d.rank][j]) * (double)g.d.world;
+    for (int j = 0; j < kNRed; ++j)
+      acc[j] = (j < nr) ? ll_load(w->ll[slot][g.d.rank], j, e, &w->error) * (double)g.d.world : 0.0;
   } else {
 #pragma unroll
     for (int j = 0; j < kNRed; ++j) acc[j] = __ldcv(g.d.nccl_out + (size_t)slot * kSumW + j);
@@ -251,7 +261,7 @@ __device__ __forceinline__ void dist_scalars(const Args& g, bool meurant, double
     Scal s = g.sc[g.scpar];
     for (int q = 0; q < g.npend; ++q) {
       double acc[kNRed];
-      dist_totals(g, g.pend_e[q], acc);
+      dist_totals(g, g.pend_e[q], fk_width(g.pend_kind[q]), acc);
       apply_finalize(g.pend_kind[q], meurant, &s, acc, g.pend_k[q]);
     }
     if (threadIdx.x == 0) {
@@ -423,10 +433,19 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(const Args g) {
   double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
   const i64 nv = g.n >> 1;
   const i64 stride = (i64)gridDim.x * kBlock;
-  for (i64 i = (i64)blockIdx.x * kBlock + threadIdx.x; i < nv; i += stride)
+  // Only the CTAs that stored boundary planes into a peer need a system-scope fence before
+  // they take their ticket (a fence.sys in each of ~1200 CTAs costs tens of microseconds).
+  bool peer = false;
+  const i64 lo_end = g.d.has_lo ? g.d.plane : 0, hi_begin = g.d.has_hi ? g.n - g.d.plane : g.n;
+  for (i64 i = (i64)blockIdx.x * kBlock + threadIdx.x; i < nv; i += stride) {
     ew_body<KID, PM, 2>(g, 2 * i, a, b, red);
-  if ((g.n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+    peer |= (2 * i < lo_end) | (2 * i + 2 > hi_begin);
+  }
+  if ((g.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     ew_body<KID, PM, 1>(g, g.n - 1, a, b, red);
+    peer = true;
+  }
+  const bool cta_peer = dist && g.hout_n > 0 && __syncthreads_or(peer ? 1 : 0);
 
   constexpr int NR = EwTraits<KID>::NR;
   if constexpr (NR > 0) {
@@ -436,9 +455,10 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(const Args g) {
     grid_sum_finalize<NR>(v, g.partials, g.ticket, [&](const double* acc) {
       if (dist) dist_publish<NR>(g, acc);
       else apply_finalize(EwKind<KID>::FK, MEURANT, g.sc, acc, g.k);
-    }, dist);
+    }, cta_peer);
   } else {
-    if (dist && g.hout_n > 0) grid_last_finalize(g.ticket, [&]() { dist_publish<0>(g, nullptr); });
+    if (dist && g.hout_n > 0)
+      grid_last_finalize(g.ticket, [&]() { dist_publish<0>(g, nullptr); }, cta_peer);
   }
 }
 
@@ -643,7 +663,7 @@ __global__ void __launch_bounds__(kBlock) instrument_kernel(const Op A, const Ar
 // multi-GPU: fold all ranks' instrumentation records of epoch pend_e[0] into history entry k
 __global__ void hist_consume_kernel(const Args g) {
   double acc[kNRed];
-  dist_totals(g, g.pend_e[0], acc);
+  dist_totals(g, g.pend_e[0], 4, acc);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -703,12 +723,9 @@ __global__ void push_tmp_kernel(const Args g) {
   if (g.d.mode == 1 || g.d.mode == 3) {
     for (int r = 0; r < g.d.world; ++r) {
       if (g.d.mode == 3 && r != g.d.rank) continue;
-      volatile double* dst = g.d.win[r]->sums[slot][g.d.rank];
-      for (int j = 0; j < kSumW; ++j) dst[j] = sc->tmp[j];
+      u64* dst = g.d.win[r]->ll[slot][g.d.rank];
+      for (int j = 0; j < kSumW; ++j) ll_store(dst + 2 * j, sc->tmp[j], g.sepoch);
     }
-    __threadfence_system();
-    if (g.d.mode == 1)
-      for (int r = 0; r < g.d.world; ++r) st_relaxed_sys(&g.d.win[r]->sflag[slot][g.d.rank], g.sepoch);
   } else {
     volatile double* dst = g.d.nccl_in + (size_t)slot * kSumW;
     for (int j = 0; j < kSumW; ++j) dst[j] = sc->tmp[j];
@@ -727,13 +744,12 @@ __global__ void init_scalars_kernel(const Args g, int variant_class, int meurant
     for (int j = 0; j < kSumW; ++j) acc[j] = 0.0;
     if (g.d.mode == 1) {
       WinHdr* w = g.d.win[g.d.rank];
-      for (int r = 0; r < g.d.world; ++r) {
-        wait_epoch(&w->sflag[slot][r], g.pend_e[0], &w->error);
-        for (int j = 0; j < kSumW; ++j) acc[j] += __ldcv(&w->sums[slot][r][j]);
-      }
+      for (int r = 0; r < g.d.world; ++r)
+        for (int j = 0; j < kSumW; ++j) acc[j] += ll_load(w->ll[slot][r], j, g.pend_e[0], &w->error);
     } else if (g.d.mode == 3) {
       WinHdr* w = g.d.win[g.d.rank];
-      for (int j = 0; j < kSumW; ++j) acc[j] = __ldcv(&w->sums[slot][g.d.rank][j]) * (double)g.d.world;
+      for (int j = 0; j < kSumW; ++j)
+        acc[j] = ll_load(w->ll[slot][g.d.rank], j, g.pend_e[0], &w->error) * (double)g.d.world;
     } else {
       for (int j = 0; j < kSumW; ++j) acc[j] = __ldcv(g.d.nccl_out + (size_t)slot * kSumW + j);
     }

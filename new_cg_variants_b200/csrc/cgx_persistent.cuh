@@ -140,9 +140,13 @@ __device__ __forceinline__ void pers_row(const StencilOp& A, int row, unsigned m
 #pragma unroll
   for (int c = 0; c < NVX; ++c) y[c] = 0.0;
 #define CGX_PT(bit, j, coef)                                                               \
-  if (m & (bit)) {                                                                         \
-    ld((i64)(j), v);                                                                       \
-    _Pragma("unroll") for (int c = 0; c < NVX; ++c) y[c] = add_(y[c], mul_((coef), v[c])); \
+  {                                                                                        \
+    const bool ex = (m & (bit)) != 0u;               /* absent neighbour: read the row itself, drop the term */ \
+    ld(ex ? (j) : row, v);                                                                 \
+    _Pragma("unroll") for (int c = 0; c < NVX; ++c) {                                      \
+      const double t = add_(y[c], mul_((coef), v[c]));                                     \
+      y[c] = ex ? t : y[c];                                                                \
+    }                                                                                      \
   }
   CGX_PT(1u, row - plane, A.off)
   CGX_PT(2u, row - A.nx, A.off)
@@ -155,7 +159,7 @@ __device__ __forceinline__ void pers_row(const StencilOp& A, int row, unsigned m
 }
 template <int NVX, class Ld>
 __device__ __forceinline__ void pers_row(const CsrOp& A, int row, unsigned, Ld ld, double (&y)[NVX]) {
-  A.template row<NVX>((i64)row, ld, y);
+  A.template row<NVX>((i64)row, [&](i64 c, double (&v)[NVX]) { ld((int)c, v); }, y);
 }
 
 struct PersRec { u64 e; int kind; int k; int hist; };      // a published record still to be folded
@@ -172,7 +176,6 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
   __shared__ double sh[kPersRed * 32];
   __shared__ double sh_acc[kPersRed];
   __shared__ Args gg;                                          // this rank's global-memory Args
-  __shared__ Args gl;                                          // same, vectors in shared memory
   __shared__ int sh_last;
 
   const int T = blockDim.x, tid = threadIdx.x;
@@ -180,16 +183,16 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
   const int rk = blockIdx.x / nb, cta = blockIdx.x - rk * nb;
   const PersRank<Op>& pr = ranks[rk];
   const Op A = pr.A;
-  if (tid == 0) {
-    gg = pr.g;
-    gl = pr.g;
+  if (tid == 0) gg = pr.g;
+  __syncthreads();
+  Args gl = gg;                                                // same, vectors in shared memory (per thread)
+  {
     int slot = 0;
     for (int v = 0; v < 10; ++v)
       if (L.vmask & (1u << v)) { args_vec(gl, v) = smem + (size_t)slot * L.R * T; ++slot; }
     if (PM == 1) gl.dinv = smem + (size_t)slot * L.R * T;
     gl.d.world = 1;                                            // halo stores are done here, not in ew_body
   }
-  __syncthreads();
   const Args& g = gg;
   const i64 n = g.n;
   const int world = g.d.world, rank = g.d.rank;
@@ -243,6 +246,15 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
   PersRec pend[3];
   int npend = 0;
 
+  // does this CTA own rows of the first / last plane (it then reads ghost planes)?
+  bool touch_lo = false, touch_hi = false;
+  if (dist) {
+    for (int j = 0; j < L.R; ++j) {
+      const i64 r0 = ((i64)j * nb + cta) * T, r1 = min(n, r0 + T);
+      if (r0 < n && r0 < pl) touch_lo = true;
+      if (r0 < n && r1 > n - pl) touch_hi = true;
+    }
+  }
   // ---- sync point: every CTA of the rank has finished the stage; optionally the rank's
   //      record (NR sums) is formed and, on a partition, published with the halo epochs
   auto sync_point = [&](double (&red)[kPersRed], auto NRc, int kind, int k, bool rec_hist, int halo_n, int halo_ch) {
@@ -291,7 +303,9 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
         for (int j = 0; j < NR; ++j) __stcg(&part[(size_t)cta * kPersRed + j], v[j]);
       }
       if (dist) {
-        fence_acq_rel_sys();
+        // only a CTA that stored boundary planes into a peer needs the system-scope fence
+        if (halo_n > 0 && ((touch_lo && g.d.has_lo) || (touch_hi && g.d.has_hi))) fence_acq_rel_sys();
+        else fence_acq_rel_gpu();
         const u64 t = atomicAdd(reinterpret_cast<unsigned long long*>(bar), 1ull);
         sh_last = (t == target - 1) ? 1 : 0;
       } else {                                                 // release-add, no round trip
@@ -312,12 +326,10 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
             for (int b = tid; b < nb; b += 32) t += __ldcg(&part[(size_t)b * kPersRed + j]);
             tot[j] = warp_sum(t);
           }
-          if (tid < world) {
-            volatile double* dst = g.d.win[tid]->sums[slot][rank];
+          if (tid < world && (g.d.mode != 3 || tid == rank)) {   // lane r -> rank r's window (LL words)
+            u64* dst = g.d.win[tid]->ll[slot][rank];
 #pragma unroll
-            for (int j = 0; j < NR; ++j) dst[j] = tot[j];
-            fence_acq_rel_sys();
-            st_release_sys(&g.d.win[tid]->sflag[slot][rank], e);
+            for (int j = 0; j < NR; ++j) ll_store(dst + 2 * j, tot[j], e);
           }
         }
         if (halo_n > 0 && tid == 0) {
@@ -367,11 +379,10 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
         for (int j = 0; j < kPersRed; ++j) v[j] = 0.0;
         const int nr = pend[q].hist >> 8;
         if (tid < world) {
-          if (g.d.mode != 3) pers_wait_sys(&mywin->sflag[slot][tid], e, err);
           const int src = (g.d.mode == 3) ? rank : tid;        // stub: the local record stands in
 #pragma unroll
           for (int j = 0; j < kPersRed; ++j)
-            if (j < nr) v[j] = __ldcv(&mywin->sums[slot][src][j]);
+            if (j < nr) v[j] = ll_load(mywin->ll[slot][src], j, e, err);
         }
 #pragma unroll
         for (int j = 0; j < kPersRed; ++j) {
@@ -426,15 +437,6 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
     }
   };
 
-  // does this CTA own rows of the first / last plane (it then reads ghost planes)?
-  bool touch_lo = false, touch_hi = false;
-  if (dist) {
-    for (int j = 0; j < L.R; ++j) {
-      const i64 r0 = ((i64)j * nb + cta) * T, r1 = min(n, r0 + T);
-      if (r0 < n && r0 < pl) touch_lo = true;
-      if (r0 < n && r1 > n - pl) touch_hi = true;
-    }
-  }
   auto wait_halo = [&](int ch) {
     if (tid == 0) {
       const int par = (int)(hep[ch] & 1);
@@ -498,14 +500,18 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
       }
       // element c of an exported vector: rows of the CTA's own chunk come from shared memory
       // (same bits as the exported copy), the rest from L2, ghost planes from the window
-      auto ldv = [&](const VecIn& a, const double* loc, i64 r0, i64 c) -> double {
-        const i64 d = c - r0;
-        if (loc && d >= 0 && d < T && c < n) return loc[d];
+      // (one generic load through a selected pointer: no branch.  Global lines may sit in L1
+      // only since the last sync point, whose acquire fence invalidated it.)
+      const int ni = (int)n, pli = (int)pl;
+      auto ldv = [&](const VecIn& a, const double* loc, int r0, int c) -> double {
+        const double* p = a.v + c;
         if constexpr (SL) {
-          if (c < 0) return __ldcg(a.lo + (c + pl));
-          if (c >= n) return __ldcg(a.hi + (c - n));
+          p = (c < 0) ? a.lo + (c + pli) : p;
+          p = (c >= ni) ? a.hi + (c - ni) : p;
         }
-        return __ldcg(a.v + c);
+        const unsigned d = (unsigned)(c - r0);
+        p = (loc != nullptr && d < (unsigned)T && c < ni) ? loc + d : p;
+        return *p;
       };
       const VecIn loc0{args_vec(gl, SpInV<SP>::v0), nullptr, nullptr};
       const double* sl0 = loc0.v;
@@ -515,14 +521,14 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
       for (int j = 0; j < L.R; ++j) {
         const i64 row = ((i64)j * nb + cta) * T + tid;
         if (row >= n) continue;
-        const i64 li = (i64)j * T + tid;
-        const i64 r0 = ((i64)j * nb + cta) * T;
+        const int li = j * T + tid;
+        const int r0 = (j * nb + cta) * T;
         if (hist) {
           double y[NV + 2];
-          pers_row<NV + 2>(A, (int)row, smask[li], [&](i64 c, double (&v)[NV + 2]) {
-            v[0] = ldv(in0, sl0 + (i64)j * T, r0, c);
-            if constexpr (NV == 2) v[1] = ldv(in1, sl1 + (i64)j * T, r0, c);
-            const double xj = ldv(xin, gl.x + (i64)j * T, r0, c);
+          pers_row<NV + 2>(A, (int)row, smask[li], [&](int c, double (&v)[NV + 2]) {
+            v[0] = ldv(in0, sl0 + j * T, r0, c);
+            if constexpr (NV == 2) v[1] = ldv(in1, sl1 + j * T, r0, c);
+            const double xj = ldv(xin, gl.x + j * T, r0, c);
             v[NV] = xj;
             v[NV + 1] = has_xt ? sub_(xj, ldv(xtin, nullptr, r0, c)) : 0.0;
           }, y);
@@ -541,9 +547,9 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
           hs[3] = fma(ri, ri, hs[3]);
         } else {
           double y[NV];
-          pers_row<NV>(A, (int)row, smask[li], [&](i64 c, double (&v)[NV]) {
-            v[0] = ldv(in0, sl0 + (i64)j * T, r0, c);
-            if constexpr (NV == 2) v[1] = ldv(in1, sl1 + (i64)j * T, r0, c);
+          pers_row<NV>(A, (int)row, smask[li], [&](int c, double (&v)[NV]) {
+            v[0] = ldv(in0, sl0 + j * T, r0, c);
+            if constexpr (NV == 2) v[1] = ldv(in1, sl1 + j * T, r0, c);
           }, y);
           sp_epilogue<SP, PM, NV>(gl, loc0, li, y, r4, nullptr);
         }
