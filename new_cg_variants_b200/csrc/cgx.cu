@@ -1372,7 +1372,8 @@ extern "C" int cgx_set_stencil_slab(cgx_ctx* c, int64_t nx, int64_t ny, int64_t 
   d.world = world; d.rank = rank; d.mode = 1; d.saved_mode = 1;
   d.has_lo = rank > 0; d.has_hi = rank < world - 1;
   d.plane = nx * ny;
-  c->win_bytes = kWinHdrBytes + sizeof(double) * (size_t)kChan * 4 * (size_t)d.plane;
+  c->win_bytes = kWinHdrBytes + sizeof(double) * (size_t)kChan * 4 * (size_t)d.plane   // ghost planes (stream path)
+                 + sizeof(u64) * 3 * 4 * 2 * (size_t)d.plane;                       // LL ghost planes (persistent path)
   CU(cudaMalloc(&c->d_win, c->win_bytes));
   CU(cudaMemset(c->d_win, 0, c->win_bytes));
   CU(cudaDeviceSynchronize());
@@ -1441,6 +1442,10 @@ extern "C" int cgx_dist_commit(cgx_ctx* c, int mode, const char* nccl_libpath, c
   d.ghost = reinterpret_cast<double*>(c->d_win + kWinHdrBytes);
   d.ghost_lo = d.has_lo ? reinterpret_cast<double*>(c->peer_base[d.rank - 1] + kWinHdrBytes) : nullptr;
   d.ghost_hi = d.has_hi ? reinterpret_cast<double*>(c->peer_base[d.rank + 1] + kWinHdrBytes) : nullptr;
+  const size_t ll_at = kWinHdrBytes + sizeof(double) * (size_t)kChan * 4 * (size_t)d.plane;
+  d.ghl = reinterpret_cast<u64*>(c->d_win + ll_at);
+  d.ghl_lo = d.has_lo ? reinterpret_cast<u64*>(c->peer_base[d.rank - 1] + ll_at) : nullptr;
+  d.ghl_hi = d.has_hi ? reinterpret_cast<u64*>(c->peer_base[d.rank + 1] + ll_at) : nullptr;
   d.mode = mode; d.saved_mode = mode;
   if (mode == 2) {
     if (!nccl_id128) return fail(CGX_ERR_ARG, "cgx_dist_commit: mode 2 needs the NCCL unique id");

@@ -193,6 +193,11 @@ struct Dist {
   double* ghost;                   // local ghost planes [kChan][2 parity][2 side][plane]
   double* ghost_lo;                // ghost planes of the rank below (peer mapped) or null
   double* ghost_hi;
+  // persistent kernel: ghost planes as LL words (2 x u64 per value, tag = halo epoch):
+  // [3 channels][2 parity][2 side][2 * plane]; no flags, no fences, element-wise arrival
+  u64* ghl;
+  u64* ghl_lo;
+  u64* ghl_hi;
   double* nccl_in;                 // mode 2: [kSlots][kSumW] local partials / reduced totals
   double* nccl_out;
   i64 plane;                       // points per exchanged plane
@@ -220,6 +225,9 @@ __device__ __forceinline__ void wait_epoch(const u64* flag, u64 epoch, int* err)
     if (*(volatile int*)err) return;
     if (timer_ns() - t0 > 10000000000ull) { atomicExch(err, 1); return; }
   }
+}
+__host__ __device__ __forceinline__ size_t ghl_off(const Dist& d, int ch, int par, int side) {
+  return ((size_t)(ch * 2 + par) * 2 + side) * 2 * (size_t)d.plane;
 }
 __device__ __forceinline__ void ll_store(u64* dst, double v, u64 epoch) {
   const u64 b = (u64)__double_as_longlong(v), tag = (epoch & 0xffffffffull) << 32;

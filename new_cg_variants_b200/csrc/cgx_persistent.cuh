@@ -303,9 +303,7 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
         for (int j = 0; j < NR; ++j) __stcg(&part[(size_t)cta * kPersRed + j], v[j]);
       }
       if (dist) {
-        // only a CTA that stored boundary planes into a peer needs the system-scope fence
-        if (halo_n > 0 && ((touch_lo && g.d.has_lo) || (touch_hi && g.d.has_hi))) fence_acq_rel_sys();
-        else fence_acq_rel_gpu();
+        fence_acq_rel_gpu();           // (records and ghost planes travel as self-validating LL words)
         const u64 t = atomicAdd(reinterpret_cast<unsigned long long*>(bar), 1ull);
         sh_last = (t == target - 1) ? 1 : 0;
       } else {                                                 // release-add, no round trip
@@ -330,14 +328,6 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
             u64* dst = g.d.win[tid]->ll[slot][rank];
 #pragma unroll
             for (int j = 0; j < NR; ++j) ll_store(dst + 2 * j, tot[j], e);
-          }
-        }
-        if (halo_n > 0 && tid == 0) {
-          for (int c = 0; c < halo_n; ++c) {
-            const int ch = halo_ch + c;
-            const int par = (int)(hep[ch] & 1);
-            if (g.d.has_lo) st_release_sys(&g.d.win[rank - 1]->hflag[ch][par][1], hep[ch]);
-            if (g.d.has_hi) st_release_sys(&g.d.win[rank + 1]->hflag[ch][par][0], hep[ch]);
           }
         }
       }
@@ -423,27 +413,29 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
       if (hist) { xv = gl.x[j * T + tid]; pr.vecs[0][row] = xv; }
       if (dist) {
         if (g.d.has_lo && row < pl) {
-          g.d.ghost_lo[ghost_off(g.d, 0, hp0, 1) + row] = a0;
-          if (NV == 2) g.d.ghost_lo[ghost_off(g.d, 1, hp1, 1) + row] = a1;
-          if (hist) g.d.ghost_lo[ghost_off(g.d, 2, hp2, 1) + row] = xv;
+          ll_store(g.d.ghl_lo + ghl_off(g.d, 0, hp0, 1) + 2 * row, a0, hep[0]);
+          if (NV == 2) ll_store(g.d.ghl_lo + ghl_off(g.d, 1, hp1, 1) + 2 * row, a1, hep[1]);
+          if (hist) ll_store(g.d.ghl_lo + ghl_off(g.d, 2, hp2, 1) + 2 * row, xv, hep[2]);
         }
         if (g.d.has_hi && row >= n - pl) {
           const i64 o = row - (n - pl);
-          g.d.ghost_hi[ghost_off(g.d, 0, hp0, 0) + o] = a0;
-          if (NV == 2) g.d.ghost_hi[ghost_off(g.d, 1, hp1, 0) + o] = a1;
-          if (hist) g.d.ghost_hi[ghost_off(g.d, 2, hp2, 0) + o] = xv;
+          ll_store(g.d.ghl_hi + ghl_off(g.d, 0, hp0, 0) + 2 * o, a0, hep[0]);
+          if (NV == 2) ll_store(g.d.ghl_hi + ghl_off(g.d, 1, hp1, 0) + 2 * o, a1, hep[1]);
+          if (hist) ll_store(g.d.ghl_hi + ghl_off(g.d, 2, hp2, 0) + 2 * o, xv, hep[2]);
         }
       }
     }
   };
 
-  auto wait_halo = [&](int ch) {
+  // x_true ghost planes (channel 3) were pushed by the stream kernels when the problem was
+  // loaded: one flag wait for the whole launch
+  if (dist && hist && has_xt) {
     if (tid == 0) {
-      const int par = (int)(hep[ch] & 1);
-      if (touch_lo && g.d.has_lo) pers_wait_sys(&mywin->hflag[ch][par][0], hep[ch], err);
-      if (touch_hi && g.d.has_hi) pers_wait_sys(&mywin->hflag[ch][par][1], hep[ch], err);
+      if (touch_lo && g.d.has_lo) pers_wait_sys(&mywin->hflag[3][g.xt_par][0], g.xt_epoch, err);
+      if (touch_hi && g.d.has_hi) pers_wait_sys(&mywin->hflag[3][g.xt_par][1], g.xt_epoch, err);
     }
-  };
+    __syncthreads();
+  }
 
   for (int k = L.k0; k <= L.k1; ++k) {
     const int par = k & 1;
@@ -479,23 +471,15 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
 #pragma unroll
     for (int j = 0; j < kPersRed; ++j) red[j] = 0.0;
     {
-      if (dist) {
-        wait_halo(0);
-        if (NV == 2) wait_halo(1);
-        if (hist) wait_halo(2);
-        if (hist && has_xt && tid == 0) {          // x_true ghosts, pushed when the problem was loaded
-          if (touch_lo && g.d.has_lo) pers_wait_sys(&mywin->hflag[3][g.xt_par][0], g.xt_epoch, err);
-          if (touch_hi && g.d.has_hi) pers_wait_sys(&mywin->hflag[3][g.xt_par][1], g.xt_epoch, err);
-        }
-        __syncthreads();
-      }
       const int hp0 = (int)(hep[0] & 1), hp1 = (int)(hep[1] & 1), hp2 = (int)(hep[2] & 1);
       VecIn in0{pr.exp_[par][0], nullptr, nullptr}, in1{pr.exp_[par][1], nullptr, nullptr};
       VecIn xin{pr.vecs[0], nullptr, nullptr}, xtin{g.xtrue, nullptr, nullptr};
+      struct GhostLL { const u64* lo; const u64* hi; u64 ep; };
+      GhostLL q0{nullptr, nullptr, 0}, q1{nullptr, nullptr, 0}, qx{nullptr, nullptr, 0}, qn{nullptr, nullptr, 0};
       if (dist) {
-        in0.lo = g.d.ghost + ghost_off(g.d, 0, hp0, 0); in0.hi = g.d.ghost + ghost_off(g.d, 0, hp0, 1);
-        in1.lo = g.d.ghost + ghost_off(g.d, 1, hp1, 0); in1.hi = g.d.ghost + ghost_off(g.d, 1, hp1, 1);
-        xin.lo = g.d.ghost + ghost_off(g.d, 2, hp2, 0); xin.hi = g.d.ghost + ghost_off(g.d, 2, hp2, 1);
+        q0 = GhostLL{g.d.ghl + ghl_off(g.d, 0, hp0, 0), g.d.ghl + ghl_off(g.d, 0, hp0, 1), hep[0]};
+        q1 = GhostLL{g.d.ghl + ghl_off(g.d, 1, hp1, 0), g.d.ghl + ghl_off(g.d, 1, hp1, 1), hep[1]};
+        qx = GhostLL{g.d.ghl + ghl_off(g.d, 2, hp2, 0), g.d.ghl + ghl_off(g.d, 2, hp2, 1), hep[2]};
         xtin.lo = g.d.ghost + ghost_off(g.d, 3, g.xt_par, 0); xtin.hi = g.d.ghost + ghost_off(g.d, 3, g.xt_par, 1);
       }
       // element c of an exported vector: rows of the CTA's own chunk come from shared memory
@@ -503,14 +487,13 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
       // (one generic load through a selected pointer: no branch.  Global lines may sit in L1
       // only since the last sync point, whose acquire fence invalidated it.)
       const int ni = (int)n, pli = (int)pl;
-      auto ldv = [&](const VecIn& a, const double* loc, int r0, int c) -> double {
-        const double* p = a.v + c;
-        if constexpr (SL) {
-          p = (c < 0) ? a.lo + (c + pli) : p;
-          p = (c >= ni) ? a.hi + (c - ni) : p;
+      auto ldv = [&](const VecIn& a, const GhostLL& q, const double* loc, int r0, int c) -> double {
+        if constexpr (SL) {             // ghost planes: LL words polled element by element (or plain doubles)
+          if (c < 0) return q.lo ? ll_load(q.lo, c + pli, q.ep, err) : __ldcg(a.lo + (c + pli));
+          if (c >= ni) return q.hi ? ll_load(q.hi, c - ni, q.ep, err) : __ldcg(a.hi + (c - ni));
         }
         const unsigned d = (unsigned)(c - r0);
-        p = (loc != nullptr && d < (unsigned)T && c < ni) ? loc + d : p;
+        const double* p = (loc != nullptr && d < (unsigned)T) ? loc + d : a.v + c;
         return *p;
       };
       const VecIn loc0{args_vec(gl, SpInV<SP>::v0), nullptr, nullptr};
@@ -526,11 +509,11 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
         if (hist) {
           double y[NV + 2];
           pers_row<NV + 2>(A, (int)row, smask[li], [&](int c, double (&v)[NV + 2]) {
-            v[0] = ldv(in0, sl0 + j * T, r0, c);
-            if constexpr (NV == 2) v[1] = ldv(in1, sl1 + j * T, r0, c);
-            const double xj = ldv(xin, gl.x + j * T, r0, c);
+            v[0] = ldv(in0, q0, sl0 + j * T, r0, c);
+            if constexpr (NV == 2) v[1] = ldv(in1, q1, sl1 + j * T, r0, c);
+            const double xj = ldv(xin, qx, gl.x + j * T, r0, c);
             v[NV] = xj;
-            v[NV + 1] = has_xt ? sub_(xj, ldv(xtin, nullptr, r0, c)) : 0.0;
+            v[NV + 1] = has_xt ? sub_(xj, ldv(xtin, qn, nullptr, r0, c)) : 0.0;
           }, y);
           double ysp[NV];
 #pragma unroll
@@ -548,8 +531,8 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
         } else {
           double y[NV];
           pers_row<NV>(A, (int)row, smask[li], [&](int c, double (&v)[NV]) {
-            v[0] = ldv(in0, sl0 + j * T, r0, c);
-            if constexpr (NV == 2) v[1] = ldv(in1, sl1 + j * T, r0, c);
+            v[0] = ldv(in0, q0, sl0 + j * T, r0, c);
+            if constexpr (NV == 2) v[1] = ldv(in1, q1, sl1 + j * T, r0, c);
           }, y);
           sp_epilogue<SP, PM, NV>(gl, loc0, li, y, r4, nullptr);
         }
