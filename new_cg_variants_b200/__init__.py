@@ -9,6 +9,6 @@ keep the reference's Python signatures; the arithmetic runs in ``libcgx_b200.so`
 """
 from .operators import PoissonStencil, canonical_csr, poisson2d, poisson3d   # noqa: F401
 from .session import Session                                                  # noqa: F401
-from . import callbacks, cg_variants                                          # noqa: F401
+from . import callbacks, cg_variants, cg_variants_mpi4py, experiments              # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,129 @@
+"""The reference's distributed solver signature (scaling_experiments_mpi4py/cg_variants/*.py):
+
+    x_local, times = f(comm, A, b, max_iter)        f in {hs_cg, cg_cg, gv_cg, pr_cg, pipe_pr_cg}
+
+un-preconditioned, x0 = 0, exactly `max_iter` loop trips (`for k in range(max_iter)`,
+hs_cg.py:36, pr_cg.py:49), no convergence test, no history; `times` is a dict with the wall
+time under 'tot' on rank 0 and None elsewhere (hs_cg.py:13-16,66).
+
+Here `comm` is a `GpuComm` (one rank per GPU; `Get_size/Get_rank/Barrier` as mpi4py's) -- or
+anything with those three methods, e.g. a real `MPI.COMM_WORLD` -- and the rows are
+partitioned in contiguous blocks as in the reference (rank r owns rows r*m .. (r+1)*m-1).
+
+`A` may be
+  * a `PoissonStencil` (the global operator; partitioned into slabs over the ranks), or
+  * on one rank: a scipy sparse / dense matrix (e.g. the reference's model problem
+    `np.diag(Lambda)`, scaling_tests.py:31-53, as `model_problem(n)` builds it).
+`b` is this rank's slice `(n/P,)`.  The reference's solvers count `max_iter` updates of x; the
+numerical-experiment functions count `max_iter - 1`, hence the `+ 1` below.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import scipy.sparse as sps
+
+from .operators import PoissonStencil
+from .session import Session
+
+
+class GpuComm:
+    """mpi4py-shaped communicator over torch.distributed (or a single process)."""
+
+    def __init__(self, group=None):
+        try:
+            import torch.distributed as dist
+            self._dist = dist if dist.is_available() and dist.is_initialized() else None
+        except Exception:
+            self._dist = None
+        self.group = group
+
+    def Get_size(self):
+        return self._dist.get_world_size(self.group) if self._dist else 1
+
+    def Get_rank(self):
+        return self._dist.get_rank(self.group) if self._dist else 0
+
+    def Barrier(self):
+        if self._dist:
+            self._dist.barrier(self.group)
+
+
+_SESSIONS = {}
+
+
+def _operator_session(comm, A, m):
+    """One resident operator per (operator, partition) -- the reference builds A once and runs
+    five variants on it (scaling_tests.py:60-66)."""
+    size, rank = comm.Get_size(), comm.Get_rank()
+    key = (id(A), size, rank)
+    if key in _SESSIONS:
+        return _SESSIONS[key]
+    if isinstance(A, PoissonStencil):
+        if size == 1:
+            sess = Session(A)
+        else:
+            from .dist import DistSession
+            sess = DistSession(A, dinv=None, rank=rank, world=size, group=getattr(comm, "group", None))
+    elif size == 1:
+        sess = Session(A)
+    else:
+        raise NotImplementedError("on several GPUs the operator must be a PoissonStencil (row-partitioned into "
+                                  "slabs); general matrices -- including the reference's dense column blocks -- "
+                                  "run on one rank")
+    _SESSIONS[key] = sess
+    return sess
+
+
+def _run(tag, comm, A, b, max_iter):
+    size, rank = comm.Get_size(), comm.Get_rank()
+    b = np.ascontiguousarray(np.asarray(b, dtype=np.float64))
+    m = len(b)
+    times = {'tot': 0., 'c_ip': 0., 'c_mv': 0., 'w_mv': 0., 'w_ip': 0., 'w_vec': 0.} if rank == 0 else None
+    sess = _operator_session(comm, A, m)
+    x0 = np.zeros(m)
+    if size == 1:
+        sess.load_problem(b, x0, None)
+    else:
+        sess.load_problem_local(b, x0, None)
+    comm.Barrier()                                     # hs_cg.py:30-33: timing starts after a barrier
+    t0 = time.perf_counter()
+    sess.run(tag, int(max_iter) + 1, histories=())
+    comm.Barrier()
+    if rank == 0:
+        times['tot'] += time.perf_counter() - t0
+    x = sess.fetch(want_hist=False)[0] if size == 1 else sess.fetch_local(want_hist=False)[0]
+    return x, times
+
+
+def hs_cg(comm, A, b, max_iter):
+    return _run("hs", comm, A, b, max_iter)
+
+
+def cg_cg(comm, A, b, max_iter):
+    return _run("cg", comm, A, b, max_iter)
+
+
+def gv_cg(comm, A, b, max_iter):
+    return _run("gv", comm, A, b, max_iter)
+
+
+def pr_cg(comm, A, b, max_iter):
+    return _run("pr", comm, A, b, max_iter)
+
+
+def pipe_pr_cg(comm, A, b, max_iter):
+    return _run("pipe_pr", comm, A, b, max_iter)
+
+
+def model_problem(n, kappa=1e6, rho=0.9):
+    """scaling_tests.py:31-36,53: diagonal matrix of the model spectrum and b with x* = ones/sqrt(n)."""
+    lam = 1 / kappa + (1 - 1 / kappa) * np.arange(n) / (n - 1) * rho ** np.arange(n - 1, -1, -1, dtype='float')
+    return sps.diags(lam).tocsr(), lam / np.sqrt(n)
+
+
+def clear_sessions():
+    for s in _SESSIONS.values():
+        s.close()
+    _SESSIONS.clear()

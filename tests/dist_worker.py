@@ -57,6 +57,25 @@ def main():
                 ok = ok and same
             grp.close()
         dist.barrier()
+    # the reference's distributed signature f(comm, A, b, max_iter) -> (x_local, times)
+    from new_cg_variants_b200 import Session, cg_variants_mpi4py as m
+    comm = m.GpuComm()
+    r0, r1 = rank * (n // world), (rank + 1) * (n // world)
+    xs = {}
+    for fn in (m.hs_cg, m.pr_cg, m.pipe_pr_cg):
+        x_loc, times = fn(comm, S, b[r0:r1], 20)
+        parts = [None] * world
+        dist.all_gather_object(parts, x_loc)
+        xs[fn.__name__] = np.concatenate(parts)
+        assert (times is not None) == (rank == 0)
+    m.clear_sessions()
+    if rank == 0:
+        with Session(S) as one:
+            for name, tag in (("hs_cg", "hs"), ("pr_cg", "pr"), ("pipe_pr_cg", "pipe_pr")):
+                x1, _, _ = one.solve(tag, b, x0, 21, histories=())
+                same = np.allclose(xs[name], x1, rtol=1e-9, atol=1e-13)
+                print(f"[mpi4py-shaped] {name}: {'match' if same else 'MISMATCH'}", flush=True)
+                ok = ok and same
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

@@ -320,3 +320,48 @@ def test_csr_stream_kernel_equals_row_kernel(name):
     for tag in ("hs", "cg", "pr", "pipe_pr", "gv"):
         for h in orc.HISTORIES:      # same row sums; the fused dots are summed in another fixed order
             np.testing.assert_allclose(res[(1, tag)][1][h][:6], res[(0, tag)][1][h][:6], rtol=1e-9, err_msg=f"{tag}/{h}")
+
+
+# ------------------------------------------------ callers either side of the path
+def test_figure_gen_style_driver_end_to_end(tmp_path):
+    """experiments.test_matrix / parse_convergence_data (figure_gen.py:21-124 restated) on the
+    GPU path: .npy dictionaries in the reference's layout, table row within the parity bands
+    of the reference's published row."""
+    import json, os
+    from new_cg_variants_b200 import experiments as ex
+    table = json.load(open(os.path.join(helpers.GOLDEN, "table.json")))
+    for name, prec, max_iter in (("bcsstk03", "jacobi", 250), ("nos4", None, 150)):
+        A = helpers.load_matrix(name)
+        trials = ex.test_matrix(A, max_iter, name, preconditioner=prec, variants=ex.ALL_METHODS, data_dir=str(tmp_path))
+        assert set(trials) == {m.__name__ for m in ex.ALL_METHODS}
+        saved = np.load(tmp_path / f"{name}_{prec}" / "pr_pcg.npy", allow_pickle=True).item()
+        assert saved["name"] == "pr_pcg" and saved["max_iter"] == max_iter
+        assert np.array_equal(saved["error_A_norm"], trials["pr_pcg"]["error_A_norm"])
+        row, iters, acc = ex.parse_convergence_data(name, prec, ex.TABLE_METHODS, A=A, data_dir=str(tmp_path))
+        ref = table[f"{name}_{prec}"]
+        assert row.startswith("\\texttt{" + name) and f"& {A.shape[0]} & {A.nnz}" in row
+        for i_new, i_ref, a_new, a_ref in zip(iters, ref["iters"], acc, ref["acc"]):
+            if i_ref and i_new:
+                assert abs(i_new - i_ref) <= max(2, 0.12 * i_ref)
+            assert abs(a_new - a_ref) <= 1.0            # attainable accuracy: same decade as published
+
+
+def test_mpi4py_shaped_solvers_single_rank():
+    """scaling_experiments_mpi4py signature f(comm, A, b, max_iter) -> (x, times) on the reference's
+    model problem (n = 1536, 1500 iterations): final errors within x2 of the reference's own
+    (tests/golden/mpi_kat.json, produced by running its files with a one-rank fake mpi4py)."""
+    import json, os
+    from new_cg_variants_b200 import cg_variants_mpi4py as m
+    kat = json.load(open(os.path.join(helpers.GOLDEN, "mpi_kat.json")))
+    n, its = kat["pr"]["n"], kat["pr"]["max_iter"]
+    A, b = m.model_problem(n)
+    comm = m.GpuComm()
+    for tag, fn in (("hs", m.hs_cg), ("cg", m.cg_cg), ("gv", m.gv_cg), ("pr", m.pr_cg), ("pipe_pr", m.pipe_pr_cg)):
+        x, times = fn(comm, A, b, its)
+        err = float(np.linalg.norm(np.ones(n) / np.sqrt(n) - x))
+        assert times["tot"] > 0 and x.shape == (n,)
+        assert 0.5 <= err / kat[tag]["error"] <= 2.0, (tag, err, kat[tag]["error"])
+        # `max_iter` counts updates of x: one more than the numerical-experiment functions
+        ref = orc.solve_mpi_style(tag, A.diagonal(), b.copy(), its)
+        np.testing.assert_allclose(x, ref, rtol=0, atol=4 * max(err, 1e-12))
+    m.clear_sessions()
