@@ -517,13 +517,18 @@ static void launch_spmv(cgx_ctx* c, Args g, const double* vin, double* vout) {
     if constexpr (v0 >= 0) {
       const bool ghosts_ok = c->dist.world <= 1 || (c->gmap_ok[0] && (nv == 1 || c->gmap_ok[1]));
       if (c->op_kind == 2 && c->use_tma && c->tmap_ok[v0] && (v1 < 0 || c->tmap_ok[v1 < 0 ? 0 : v1]) && ghosts_ok) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        // grid = the CTAs that are actually co-resident (one wave): the kernel splits the work
+        // evenly over gridDim.x, so a partial second wave would cost a full extra pass
+        static int per_sm = 0;
+        if (!per_sm) {
           cudaFuncSetAttribute(stencil_tma_kernel<MODE, PM, MEUR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)tma_smem_bytes(nv));
-          attr_set = true;
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stencil_tma_kernel<MODE, PM, MEUR>, kTmaThreads,
+                                                        tma_smem_bytes(nv));
+          if (per_sm < 1) per_sm = 1;
         }
-        stencil_tma_kernel<MODE, PM, MEUR><<<c->tma_grid[nv - 1], kTmaThreads, tma_smem_bytes(nv), c->stream>>>(
+        const int tgrid = std::min(c->tma_grid[nv - 1], per_sm * c->sm_count);
+        stencil_tma_kernel<MODE, PM, MEUR><<<tgrid, kTmaThreads, tma_smem_bytes(nv), c->stream>>>(
             c->tmap[v0], c->tmap[v1 < 0 ? v0 : v1], c->gmap[0], c->gmap[nv - 1], c->geom, g);
         done = true;
       }
