@@ -96,9 +96,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_problem(grid):
+def build_problem(grid, dim=3):
     from new_cg_variants_b200 import PoissonStencil
-    S = PoissonStencil(grid, grid, grid, dim=3)
+    S = PoissonStencil(grid, grid, grid, dim=3) if dim == 3 else PoissonStencil(grid, grid, 1, dim=2)
     n = S.shape[0]
     x_true = np.ones(n) / np.sqrt(n)           # figure_gen.py:31-34
     b = S @ x_true
@@ -124,7 +124,7 @@ def run_reference(args, rank, world):
     from oracle import cg_oracle as orc
     from threadpoolctl import threadpool_info
     t0 = time.time()
-    A = orc.poisson3d(args.grid)
+    A = orc.poisson3d(args.grid) if args.dim == 3 else orc.poisson2d(args.grid)
     x_true, b, x0 = orc.setup_problem(A)
     dinv = orc.jacobi_dinv(A)
     build_s = time.time() - t0
@@ -139,14 +139,14 @@ def run_reference(args, rank, world):
     blas = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     n = A.shape[0]
     line = {
-        "impl": "reference", "metric": f"CG iterations/s ({REF_FUN.get(args.variant, args.variant)}, Jacobi, 3-D Poisson {args.grid}^3)",
+        "impl": "reference", "metric": f"CG iterations/s ({REF_FUN.get(args.variant, args.variant)}, Jacobi, {args.dim}-D Poisson {args.grid}^{args.dim})",
         "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"poisson3d_{args.grid} {REF_FUN.get(args.variant, args.variant)} jacobi (scipy CSR, nnz={A.nnz})",
+        "config": {"workload": f"poisson{args.dim}d_{args.grid} {REF_FUN.get(args.variant, args.variant)} jacobi (scipy CSR, nnz={A.nnz})",
                    "iters_per_step": its, "n": n},
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": blas, "kind": "port",
-                         "sample": f"{args.steps} x {its} iterations of the numpy/scipy restatement on the full {args.grid}^3 CSR matrix "
+                         "sample": f"{args.steps} x {its} iterations of the numpy/scipy restatement on the full {args.grid}^{args.dim} CSR matrix "
                                    f"(scipy SpMV single-threaded, OpenBLAS dots {blas} threads, host has {os.cpu_count()} cpus; "
                                    f"matrix build {build_s:.1f}s untimed)"},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -159,7 +159,7 @@ def run_reference(args, rank, world):
 def cpu_baseline_sample(args):
     from oracle import cg_oracle as orc
     from threadpoolctl import threadpool_info
-    A = orc.poisson3d(args.grid)
+    A = orc.poisson3d(args.grid) if args.dim == 3 else orc.poisson2d(args.grid)
     x_true, b, x0 = orc.setup_problem(A)
     dinv = orc.jacobi_dinv(A)
     its = args.cpu_iters
@@ -173,7 +173,7 @@ def cpu_baseline_sample(args):
     blas = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     return {"value": its / best, "unit": "iterations/s", "cores": blas, "kind": "port",
             "sample": f"min of 2 runs of {its} iterations of oracle/cg_oracle.py ({REF_FUN.get(args.variant, args.variant)}, callbacks=[], "
-                      f"precomputed dinv) on the full {args.grid}^3 scipy CSR matrix; scipy SpMV single-threaded, "
+                      f"precomputed dinv) on the full {args.grid}^{args.dim} scipy CSR matrix; scipy SpMV single-threaded, "
                       f"OpenBLAS {blas} threads, host {os.cpu_count()} cpus"}
 
 
@@ -187,7 +187,7 @@ def run_ours(args, rank, world, local_rank):
         from new_cg_variants_b200.dist import DistSession      # row-partitioned multi-GPU path
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    S, b, x0, x_true, dinv = build_problem(args.grid)
+    S, b, x0, x_true, dinv = build_problem(args.grid, args.dim)
     n = S.shape[0]
     its = args.iters
     variant = args.variant
@@ -305,11 +305,11 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         b_iter = 8.0 * n * W_V[variant]
         line = {
-            "metric": f"CG iterations/s ({REF_FUN.get(variant, variant)}, Jacobi, 3-D Poisson {args.grid}^3)",
+            "metric": f"CG iterations/s ({REF_FUN.get(variant, variant)}, Jacobi, {args.dim}-D Poisson {args.grid}^{args.dim})",
             "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"poisson3d_{args.grid} {REF_FUN.get(variant, variant)} jacobi (matrix-free 7-point stencil)",
+            "config": {"workload": f"poisson{args.dim}d_{args.grid} {REF_FUN.get(variant, variant)} jacobi (matrix-free {2 * args.dim + 1}-point stencil)",
                        "n": n, "iters_per_step": its, "path": args.path, "partition": f"z-slabs x{world}",
                        "l2": "no flush needed: one iteration streams %.2f GB >> 126 MB L2" % (b_iter / 1e9)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -349,6 +349,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", default="pr", choices=sorted(W_V))
     ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--dim", type=int, default=3, choices=[2, 3],
+                    help="3: BASELINE configs[3] (default, the headline); 2 with --grid 4096: configs[2]")
     ap.add_argument("--iters", type=int, default=200, help="CG iterations per step (our arm)")
     ap.add_argument("--ref-iters", type=int, default=3, help="CG iterations per step (reference arm)")
     ap.add_argument("--cpu-iters", type=int, default=10, help="iterations of the cpu_baseline sample")

@@ -118,6 +118,8 @@ struct cgx_ctx {
   int pm = 0;
   // TMA-staged stencil path
   bool use_tma = false;
+  int dbg = 0;                     // option "debug_skip" (timing experiments only)
+  bool halo_ll = false;            // multi-GPU: the fused SpMV passes are TMA kernels -> LL ghost planes
   bool no_tma = false;             // cgx_set_option("tma", 0): force the generic stencil kernel
   bool no_csr_stream = false;      // cgx_set_option("csr_stream", 0): one thread per row
   TmaGeom geom{};
@@ -423,6 +425,8 @@ static Args make_args(cgx_ctx* c) {
   g.hist = c->d_hist; g.hist_len = c->hist_len; g.hist_mask = c->hist_mask;
   g.n = c->n; g.k = c->cur_k;
   g.d = c->dist;
+  g.halo_ll = c->halo_ll ? 1 : 0;
+  g.dbg = c->dbg;
   return g;
 }
 
@@ -515,8 +519,7 @@ static void launch_spmv(cgx_ctx* c, Args g, const double* vin, double* vout) {
     ProfScope ps(c, PC_SP0 + MODE);
     bool done = false;
     if constexpr (v0 >= 0) {
-      const bool ghosts_ok = c->dist.world <= 1 || (c->gmap_ok[0] && (nv == 1 || c->gmap_ok[1]));
-      if (c->op_kind == 2 && c->use_tma && c->tmap_ok[v0] && (v1 < 0 || c->tmap_ok[v1 < 0 ? 0 : v1]) && ghosts_ok) {
+      if (c->op_kind == 2 && c->use_tma && c->tmap_ok[v0] && (v1 < 0 || c->tmap_ok[v1 < 0 ? 0 : v1])) {
         // grid = the CTAs that are actually co-resident (one wave): the kernel splits the work
         // evenly over gridDim.x, so a partial second wave would cost a full extra pass
         static int per_sm = 0;
@@ -529,7 +532,7 @@ static void launch_spmv(cgx_ctx* c, Args g, const double* vin, double* vout) {
         }
         const int tgrid = std::min(c->tma_grid[nv - 1], per_sm * c->sm_count);
         stencil_tma_kernel<MODE, PM, MEUR><<<tgrid, kTmaThreads, tma_smem_bytes(nv), c->stream>>>(
-            c->tmap[v0], c->tmap[v1 < 0 ? v0 : v1], c->gmap[0], c->gmap[nv - 1], c->geom, g);
+            c->tmap[v0], c->tmap[v1 < 0 ? v0 : v1], c->geom, g);
         done = true;
       }
     }
@@ -577,6 +580,7 @@ static void launch_halo_push(cgx_ctx* c, Args g, const double* v, int ch) {
   Plan p;
   p.hout_n = 1; p.hout_ch = ch;
   plan_apply(c, g, p);
+  g.halo_ll = 0;                      // plain ghost planes + halo epoch flags (generic consumers)
   halo_push_kernel<<<grid_for(c, c->dist.plane), kBlock, 0, c->stream>>>(g, v);
   c->launches++;
   plan_commit(c, g, p);
@@ -623,17 +627,21 @@ static bool tma_prepare_geom(cgx_ctx* c) {
 
 static int setup_tma(cgx_ctx* c, unsigned need) {
   c->use_tma = false;
+  c->halo_ll = false;
   for (auto& ok : c->tmap_ok) ok = false;
-  for (auto& ok : c->gmap_ok) ok = false;
   if (!tma_prepare_geom(c)) return CGX_OK;
   const StencilOp& S = c->sten;
   for (int i = 0; i < V_COUNT; ++i)
     if ((need & (1u << i)) && c->vec[i]) c->tmap_ok[i] = tma_encode_dims(c->vec[i], S.nx, S.ny, S.nz, &c->tmap[i]);
-  if (c->dist.world > 1 && c->dist.ghost)
-    for (int ch = 0; ch < 2; ++ch)       // ghost planes of channel ch: z = parity*2 + side
-      c->gmap_ok[ch] = tma_encode_dims(c->dist.ghost + ghost_off(c->dist, ch, 0, 0), S.nx, S.ny, 4, &c->gmap[ch]);
-  else
-    for (int ch = 0; ch < 2; ++ch) { c->gmap[ch] = c->tmap[V_X]; }   // never dereferenced
+  // every fused SpMV pass of the variant must take the TMA kernel for the LL ghost planes
+  bool all_ok = true;
+  for (int i = 0; i < V_COUNT; ++i)
+    if ((need & (1u << i)) && c->vec[i] && !c->tmap_ok[i]) all_ok = false;
+  c->halo_ll = c->dist.world > 1 && all_ok;
+  if (c->dist.world > 1 && !all_ok) {                 // mixed would mix the two ghost formats: all generic
+    for (auto& ok : c->tmap_ok) ok = false;
+    return CGX_OK;
+  }
   c->use_tma = true;
   return CGX_OK;
 }
@@ -1266,6 +1274,7 @@ extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
   if (!strcmp(name, "persistent_threshold")) { c->pers_threshold = value; return CGX_OK; }
   if (!strcmp(name, "pers_threads")) { c->pers_threads = value; return CGX_OK; }
   if (!strcmp(name, "pers_ctas")) { c->pers_ctas = value; return CGX_OK; }
+  if (!strcmp(name, "debug_skip")) { c->dbg = value; return CGX_OK; }
   if (!strcmp(name, "stub_allreduce")) {
     // timing experiment (SURVEY.md section 8d "allreduce-hiding metric"): value != 0 replaces the
     // scalar exchange by a local stand-in; value == 0 restores the mode chosen at commit
@@ -1496,7 +1505,7 @@ extern "C" int cgx_spmv_host(cgx_ctx* c, const double* v, double* y, int64_t n) 
     CU(cudaFuncSetAttribute(stencil_tma_kernel<SP_PIPE_N, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)tma_smem_bytes(1)));
     stencil_tma_kernel<SP_PIPE_N, 0, false><<<c->tma_grid[0], kTmaThreads, tma_smem_bytes(1), c->stream>>>(
-        tm, tm, tm, tm, c->geom, g);
+        tm, tm, c->geom, g);
     c->launches++;
   } else {
     launch_spmv<SP_PLAIN, 0, false>(c, g, dv, dy);

@@ -231,16 +231,17 @@ __host__ __device__ __forceinline__ size_t ghl_off(const Dist& d, int ch, int pa
 }
 __device__ __forceinline__ void ll_store(u64* dst, double v, u64 epoch) {
   const u64 b = (u64)__double_as_longlong(v), tag = (epoch & 0xffffffffull) << 32;
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"((b & 0xffffffffull) | tag) : "memory");
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 1), "l"((b >> 32) | tag) : "memory");
+  // one 16-byte store (dst is 16-byte aligned); each 8-byte half validates itself
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"((b & 0xffffffffull) | tag),
+               "l"((b >> 32) | tag) : "memory");
 }
 __device__ __forceinline__ u64 ll_poll(const u64* src, u64 tag32, int* err) {
   u64 w;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
   if ((w >> 32) == tag32) return w;
   const u64 t0 = timer_ns();
   for (;;) {
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
     if ((w >> 32) == tag32) return w;
     if (*(volatile int*)err) return w;
     if (timer_ns() - t0 > 10000000000ull) { atomicExch(err, 1); return w; }
@@ -251,6 +252,45 @@ __device__ __forceinline__ double ll_load(const u64* rec, int j, u64 epoch, int*
   const u64 tag = epoch & 0xffffffffull;
   const u64 lo = ll_poll(rec + 2 * j, tag, err), hi = ll_poll(rec + 2 * j + 1, tag, err);
   return __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+}
+// both words of value j with ONE 16-byte load, re-polled until both carry the tag
+__device__ __forceinline__ double ll_load16(const u64* rec, int j, u64 epoch, int* err) {
+  const u64 tag = epoch & 0xffffffffull;
+  const u64* src = rec + 2 * j;
+  u64 lo, hi;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+  if ((lo >> 32) != tag || (hi >> 32) != tag) {
+    const u64 t0 = timer_ns();
+    for (;;) {
+      asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+      if ((lo >> 32) == tag && (hi >> 32) == tag) break;
+      if (*(volatile int*)err) break;
+      if (timer_ns() - t0 > 10000000000ull) { atomicExch(err, 1); break; }
+    }
+  }
+  return __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+}
+// Warp-collective: all-rank totals of the record of `epoch` (NQ = 4 or 8 sums, the first `nr`
+// are live).  Lane l fetches value (l & 3) [+4] of rank (l >> 2): every word of the record is
+// in flight at once -- one L2 round trip instead of one per value -- and the sums are formed in
+// rank order by shuffles, identically in every warp of every GPU.  only_rank >= 0: timing stub
+// (that rank's record times the number of ranks).
+template <int NQ>
+__device__ __forceinline__ void ll_totals(WinHdr* w, int slot, u64 epoch, int world, int nr, int only_rank,
+                                          double (&acc)[NQ]) {
+  const int lane = threadIdx.x & 31, r = lane >> 2, j = lane & 3;
+#pragma unroll
+  for (int h = 0; h < NQ / 4; ++h) {
+    const int jj = j + 4 * h;
+    double v = 0.0;
+    if (r < world && jj < nr && (only_rank < 0 || r == only_rank)) v = ll_load16(w->ll[slot][r], jj, epoch, &w->error);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double t = 0.0;
+      for (int rr = 0; rr < world; ++rr) t += __shfl_sync(0xffffffffu, v, rr * 4 + q);
+      acc[4 * h + q] = (only_rank >= 0) ? t * (double)world : t;
+    }
+  }
 }
 __host__ __device__ __forceinline__ size_t ghost_off(const Dist& d, int ch, int par, int side) {
   return ((size_t)(ch * 2 + par) * 2 + side) * (size_t)d.plane;

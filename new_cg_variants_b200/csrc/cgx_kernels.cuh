@@ -97,6 +97,8 @@ struct Args {
   int xt_par;                      // ghost planes of x_true (channel 3), pushed when the problem is loaded
   u64 xt_epoch;
   int meur;                        // Meurant predictor (kernels that are not templated on it)
+  int halo_ll;                     // the consumer is the TMA stencil kernel: boundary planes travel as LL words
+  int dbg;                         // timing experiments (cgx_set_option "debug_skip"): 1 = no halo traffic
 };
 
 // An SpMV input vector: the owned slab and (multi-GPU) the ghost planes below and above.
@@ -207,7 +209,7 @@ __device__ __forceinline__ void dist_publish(const Args& g, const double* acc) {
       for (int j = 0; j < NR; ++j) dst[j] = acc[j];
     }
   }
-  if (g.hout_n > 0) {                 // the halo planes are bulk data: fence, then their epochs
+  if (g.hout_n > 0 && !g.halo_ll) {   // plain ghost planes are bulk data: fence, then their epochs
     __threadfence_system();
     dist_publish_halo_flags(g);
   }
@@ -225,28 +227,9 @@ __device__ __forceinline__ int fk_width(int kind) {
   }
 }
 __device__ __forceinline__ void dist_totals(const Args& g, u64 e, int nr, double (&acc)[kNRed]) {
-  const int lane = threadIdx.x & 31;
   const int slot = (int)(e % kSlots);
-  double v[kNRed] = {0.0, 0.0, 0.0, 0.0};
-  WinHdr* w = g.d.win[g.d.rank];
-  if (g.d.mode == 1) {
-    if (lane < g.d.world) {
-#pragma unroll
-      for (int j = 0; j < kNRed; ++j)
-        if (j < nr) v[j] = ll_load(w->ll[slot][lane], j, e, &w->error);
-    }
-#pragma unroll
-    for (int j = 0; j < kNRed; ++j) {
-      double t = 0.0;
-      for (int r = 0; r < g.d.world; ++r) t += __shfl_sync(0xffffffffu, v[j], r);
-      acc[j] = t;
-    }
-  } else if (g.d.mode == 3) {
-    // timing stub ("stub_allreduce"): no exchange, no wait -- the local record times the
-    // number of ranks stands in for the total (numerically meaningless)
-#pragma unroll
-    for (int j = 0; j < kNRed; ++j)
-      acc[j] = (j < nr) ? ll_load(w->ll[slot][g.d.rank], j, e, &w->error) * (double)g.d.world : 0.0;
+  if (g.d.mode == 1 || g.d.mode == 3) {
+    ll_totals<kNRed>(g.d.win[g.d.rank], slot, e, g.d.world, nr, g.d.mode == 3 ? g.d.rank : -1, acc);
   } else {
 #pragma unroll
     for (int j = 0; j < kNRed; ++j) acc[j] = __ldcv(g.d.nccl_out + (size_t)slot * kSumW + j);
@@ -277,8 +260,23 @@ __device__ __forceinline__ void dist_scalars(const Args& g, bool meurant, double
 // ghost planes of the rank below / above (peer memory; 16-byte stores, plane is even).
 template <int W>
 __device__ __forceinline__ void halo_store(const Args& g, int c, i64 i, const Pk<W>& v) {
-  if (g.d.world > 1) {
+  if (g.d.world > 1 && !(g.dbg & 1)) {
     const i64 pl = g.d.plane;
+    if (g.halo_ll) {
+      // LL words (value halves tagged with the halo epoch): no flag, no fence -- a system-scope
+      // fence after bulk peer stores costs several microseconds per launch (tools/dist_probe.py)
+      if (g.d.has_lo && i < pl) {
+        u64* q = g.d.ghl_lo + ghl_off(g.d, g.hout_ch + c, g.hout_par, 1) + 2 * i;
+#pragma unroll
+        for (int l = 0; l < W; ++l) ll_store(q + 2 * l, v.v[l], g.hout_epoch);
+      }
+      if (g.d.has_hi && i >= g.n - pl) {
+        u64* q = g.d.ghl_hi + ghl_off(g.d, g.hout_ch + c, g.hout_par, 0) + 2 * (i - (g.n - pl));
+#pragma unroll
+        for (int l = 0; l < W; ++l) ll_store(q + 2 * l, v.v[l], g.hout_epoch);
+      }
+      return;
+    }
     if (g.d.has_lo && i < pl) stp<W>(g.d.ghost_lo + ghost_off(g.d, g.hout_ch + c, g.hout_par, 1), i, v);
     if (g.d.has_hi && i >= g.n - pl)
       stp<W>(g.d.ghost_hi + ghost_off(g.d, g.hout_ch + c, g.hout_par, 0), i - (g.n - pl), v);
@@ -424,28 +422,57 @@ template <> struct EwKind<EW_PR> { static constexpr int FK = FK_PR_NU; };
 template <> struct EwKind<EW_PIPE_R> { static constexpr int FK = FK_PIPE; };
 template <> struct EwKind<EW_PIPE_N> { static constexpr int FK = FK_PIPE; };
 
+// L2 prefetch of the operands of element i of stage KID (partitioned runs: issued before the
+// CTA folds the all-rank scalar records, so the HBM latency of the first sweep overlaps the
+// exchange instead of following it).
+template <int KID, int PM>
+__device__ __forceinline__ void ew_prefetch(const Args& g, i64 i) {
+  auto pf = [&](const double* p) { if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i)); };
+  if constexpr (PM == 1) pf(g.dinv);
+  pf(g.r);
+  if constexpr (KID == EW_HS1) { pf(g.s); }
+  else if constexpr (KID == EW_HS2) { pf(g.x); pf(g.p); }
+  else {
+    pf(g.x); pf(g.rt); pf(g.p); pf(g.s);
+    if constexpr (KID == EW_CG) pf(g.w);
+    if constexpr (KID == EW_GV) { pf(g.st); pf(g.w); pf(g.wt); pf(g.u); pf(g.t); }
+    if constexpr (KID == EW_PIPE_R || KID == EW_PIPE_N) { pf(g.st); pf(g.w); pf(g.u); }
+    if constexpr (KID == EW_PIPE_N && PM != 0) pf(g.wt);
+  }
+}
+
 template <int KID, int PM, bool MEURANT>
 __global__ void __launch_bounds__(kBlock) ew_kernel(const Args g) {
   const bool dist = g.d.world > 1;
-  double a, b;
-  if (dist) dist_scalars(g, MEURANT, a, b);
-  else { a = g.sc->a; b = g.sc->b; }
-  double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
   const i64 nv = g.n >> 1;
   const i64 stride = (i64)gridDim.x * kBlock;
+  double a, b;
+  if (dist) {
+    const i64 rot0 = (g.hout_n > 0 && g.d.has_hi) ? nv - (g.d.plane >> 1) : 0;
+    i64 i0 = (i64)blockIdx.x * kBlock + threadIdx.x;
+    if (i0 < nv) { i0 += rot0; if (i0 >= nv) i0 -= nv; ew_prefetch<KID, PM>(g, 2 * i0); }
+    dist_scalars(g, MEURANT, a, b);
+  } else { a = g.sc->a; b = g.sc->b; }
+  double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
   // Only the CTAs that stored boundary planes into a peer need a system-scope fence before
   // they take their ticket (a fence.sys in each of ~1200 CTAs costs tens of microseconds).
   bool peer = false;
   const i64 lo_end = g.d.has_lo ? g.d.plane : 0, hi_begin = g.d.has_hi ? g.n - g.d.plane : g.n;
+  // Partitioned run: rotate the row order so that the boundary planes (last plane, then first
+  // plane) are updated FIRST -- their halo copies then cross NVLink while the interior is
+  // still being streamed, and the neighbour's SpMV pass finds them waiting.
+  const i64 rot = (dist && g.hout_n > 0 && g.d.has_hi) ? nv - (g.d.plane >> 1) : 0;
   for (i64 i = (i64)blockIdx.x * kBlock + threadIdx.x; i < nv; i += stride) {
-    ew_body<KID, PM, 2>(g, 2 * i, a, b, red);
-    peer |= (2 * i < lo_end) | (2 * i + 2 > hi_begin);
+    i64 ph = i + rot;
+    if (ph >= nv) ph -= nv;
+    ew_body<KID, PM, 2>(g, 2 * ph, a, b, red);
+    peer |= (2 * ph < lo_end) | (2 * ph + 2 > hi_begin);
   }
   if ((g.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     ew_body<KID, PM, 1>(g, g.n - 1, a, b, red);
     peer = true;
   }
-  const bool cta_peer = dist && g.hout_n > 0 && __syncthreads_or(peer ? 1 : 0);
+  const bool cta_peer = dist && g.hout_n > 0 && !g.halo_ll && __syncthreads_or(peer ? 1 : 0);
 
   constexpr int NR = EwTraits<KID>::NR;
   if constexpr (NR > 0) {
@@ -457,7 +484,7 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(const Args g) {
       else apply_finalize(EwKind<KID>::FK, MEURANT, g.sc, acc, g.k);
     }, cta_peer);
   } else {
-    if (dist && g.hout_n > 0)
+    if (dist && g.hout_n > 0 && !g.halo_ll)
       grid_last_finalize(g.ticket, [&]() { dist_publish<0>(g, nullptr); }, cta_peer);
   }
 }

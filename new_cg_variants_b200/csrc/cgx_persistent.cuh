@@ -364,21 +364,11 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
       const int slot = (int)(e % kSlots);
       __syncthreads();
       if (tid < 32) {
-        double v[kPersRed];
+        double tot[kPersRed];
+        ll_totals<kPersRed>(mywin, slot, e, world, pend[q].hist >> 8, g.d.mode == 3 ? rank : -1, tot);
+        if (tid == 0) {
 #pragma unroll
-        for (int j = 0; j < kPersRed; ++j) v[j] = 0.0;
-        const int nr = pend[q].hist >> 8;
-        if (tid < world) {
-          const int src = (g.d.mode == 3) ? rank : tid;        // stub: the local record stands in
-#pragma unroll
-          for (int j = 0; j < kPersRed; ++j)
-            if (j < nr) v[j] = ll_load(mywin->ll[slot][src], j, e, err);
-        }
-#pragma unroll
-        for (int j = 0; j < kPersRed; ++j) {
-          double t = 0.0;
-          for (int r = 0; r < world; ++r) t += __shfl_sync(0xffffffffu, v[j], r);
-          if (tid == 0) sh_acc[j] = t;
+          for (int j = 0; j < kPersRed; ++j) sh_acc[j] = tot[j];
         }
       }
       __syncthreads();

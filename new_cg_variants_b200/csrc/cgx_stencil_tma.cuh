@@ -96,7 +96,6 @@ struct TmaGeom {
 template <int MODE, int PM, bool MEUR>
 __global__ void __launch_bounds__(kTmaThreads, (NV_OF(MODE) == 2) ? 2 : 4)
 stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
-                   const __grid_constant__ CUtensorMap tg0, const __grid_constant__ CUtensorMap tg1,
                    const TmaGeom G, const Args g) {
   constexpr int NV = (MODE == SP_PIPE_R) ? 2 : 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -146,27 +145,64 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         return;
       }
       double* dst = smem + (size_t)slot * NV * kPlaneStride;
-      if (z < 0 || z >= G.nz) {                     // ghost plane: written by a neighbour rank
-        const int side = z < 0 ? 0 : 1;
-        WinHdr* w = g.d.win[g.d.rank];
-        for (int c = 0; c < NV; ++c) wait_epoch(&w->hflag[g.hin_ch + c][g.hin_par][side], g.hin_epoch, &w->error);
-        asm volatile("fence.proxy.async;" ::: "memory");
-        mbar_arrive_expect_tx(&bar[slot], kBytes);
-        tma_load_3d(dst, &tg0, x0 - 2, y0 - 1, g.hin_par * 2 + side, &bar[slot]);
-        if constexpr (NV == 2) tma_load_3d(dst + kPlaneStride, &tg1, x0 - 2, y0 - 1, g.hin_par * 2 + side, &bar[slot]);
-        return;
-      }
+      if (z < 0 || z >= G.nz) return;               // ghost plane: filled by fill_ghost (all threads)
       mbar_arrive_expect_tx(&bar[slot], kBytes);
       tma_load_3d(dst, &tm0, x0 - 2, y0 - 1, z, &bar[slot]);
       if constexpr (NV == 2) tma_load_3d(dst + kPlaneStride, &tm1, x0 - 2, y0 - 1, z, &bar[slot]);
     };
     auto wait_load = [&](uint32_t li) { mbar_wait(&bar[li % kRing], (li / kRing) & 1u); };
+    // Ghost plane of a slab (multi-GPU): the neighbour rank's vector pass stored it into this
+    // rank's window as LL words (each 8-byte word = half a double + the halo epoch).  All
+    // threads poll their elements and write the tile -- zero outside the domain, like the TMA
+    // fill -- into the ring slot; no flag, no fence.  Uniform call (every thread of the CTA).
+    auto is_ghost = [&](int z) { return (z < 0 && G.has_zlo) || (z >= G.nz && G.has_zhi); };
+    auto fill_ghost = [&](int z, uint32_t li) {
+      const int slot = li % kRing;
+      const int side = z < 0 ? 0 : 1;
+      WinHdr* w = g.d.win[g.d.rank];
+      double* dst = smem + (size_t)slot * NV * kPlaneStride;
+#pragma unroll
+      constexpr int kPer = (kPlane + kTmaThreads - 1) / kTmaThreads;      // elements per thread
+      const u64 tag = g.hin_epoch & 0xffffffffull;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const u64* q = g.d.ghl + ghl_off(g.d, g.hin_ch + v, g.hin_par, side);
+        u64 lo[kPer], hi[kPer];
+        const u64* src[kPer];
+        // all loads first (16 bytes = both words of a value), then validate / re-poll
+#pragma unroll
+        for (int m = 0; m < kPer; ++m) {
+          const int idx = tid + m * kTmaThreads;
+          const int py = idx / kPX, px = idx - py * kPX;
+          const int gx = x0 - 2 + px, gyy = y0 - 1 + py;
+          src[m] = (idx < kPlane && gx >= 0 && gx < G.nx && gyy >= 0 && gyy < G.ny) ? q + 2 * (gyy * G.nx + gx) : nullptr;
+          lo[m] = hi[m] = tag << 32;                                       // outside the domain: +0.0, "valid"
+          if (g.dbg & 1) src[m] = nullptr;                                 // timing experiment: no halo traffic
+          if (src[m])
+            asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo[m]), "=l"(hi[m]) : "l"(src[m]) : "memory");
+        }
+#pragma unroll
+        for (int m = 0; m < kPer; ++m) {
+          const int idx = tid + m * kTmaThreads;
+          if (src[m] && ((lo[m] >> 32) != tag || (hi[m] >> 32) != tag)) {
+            lo[m] = ll_poll(src[m], tag, &w->error);
+            hi[m] = ll_poll(src[m] + 1, tag, &w->error);
+          }
+          if (idx < kPlane)
+            dst[v * kPlaneStride + idx] = __longlong_as_double((long long)((lo[m] & 0xffffffffull) | (hi[m] << 32)));
+        }
+      }
+      __syncthreads();
+      if (tid == 0) mbar_arrive(&bar[slot]);
+    };
 
     if (tid == 0) {
       issue(z0 - 1, Lbase);
       issue(z0, Lbase + 1);
       issue(z0 + 1, Lbase + 2);
     }
+    if (is_ghost(z0 - 1)) fill_ghost(z0 - 1, Lbase);
+    if (is_ghost(z0 + 1)) fill_ghost(z0 + 1, Lbase + 2);
     wait_load(Lbase);
     wait_load(Lbase + 1);
 
@@ -194,6 +230,7 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     for (int z = z0; z < z1; ++z) {
       const uint32_t j = (uint32_t)(z - z0);
       if (tid == 0 && z + 2 <= z1) issue(z + 2, Lbase + j + 3);    // slot of plane z-2: free
+      if (z + 2 <= z1 && is_ghost(z + 2)) fill_ghost(z + 2, Lbase + j + 3);
       double rv[kPtsPerThread], dvv[kPtsPerThread];
       const i64 ibase = (i64)z * plane_pts + (i64)gy * G.nx + x0 + lx;
 #pragma unroll
