@@ -218,10 +218,15 @@ __device__ __forceinline__ u64 timer_ns() {
 }
 // Bounded wait for *flag >= epoch.  A peer that never arrives must surface as an error
 // (CGX_ERR_CUDA after the next synchronisation), not as a hung GPU.
+// (the clock and the error flag are looked at once per 64 polls: reading %globaltimer in every
+// spin would put a microsecond of granularity on each cross-GPU dependency)
 __device__ __forceinline__ void wait_epoch(const u64* flag, u64 epoch, int* err) {
   if (ld_acquire_sys(flag) >= epoch) return;
   const u64 t0 = timer_ns();
-  while (ld_acquire_sys(flag) < epoch) {
+  for (;;) {
+#pragma unroll 1
+    for (int spin = 0; spin < 64; ++spin)
+      if (ld_acquire_sys(flag) >= epoch) return;
     if (*(volatile int*)err) return;
     if (timer_ns() - t0 > 10000000000ull) { atomicExch(err, 1); return; }
   }
@@ -241,8 +246,11 @@ __device__ __forceinline__ u64 ll_poll(const u64* src, u64 tag32, int* err) {
   if ((w >> 32) == tag32) return w;
   const u64 t0 = timer_ns();
   for (;;) {
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
-    if ((w >> 32) == tag32) return w;
+#pragma unroll 1
+    for (int spin = 0; spin < 64; ++spin) {
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+      if ((w >> 32) == tag32) return w;
+    }
     if (*(volatile int*)err) return w;
     if (timer_ns() - t0 > 10000000000ull) { atomicExch(err, 1); return w; }
   }
@@ -261,14 +269,22 @@ __device__ __forceinline__ double ll_load16(const u64* rec, int j, u64 epoch, in
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
   if ((lo >> 32) != tag || (hi >> 32) != tag) {
     const u64 t0 = timer_ns();
-    for (;;) {
-      asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
-      if ((lo >> 32) == tag && (hi >> 32) == tag) break;
-      if (*(volatile int*)err) break;
+    bool ok = false;
+    while (!ok) {
+#pragma unroll 1
+      for (int spin = 0; spin < 64 && !ok; ++spin) {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+        ok = (lo >> 32) == tag && (hi >> 32) == tag;
+      }
+      if (ok || *(volatile int*)err) break;
       if (timer_ns() - t0 > 10000000000ull) { atomicExch(err, 1); break; }
     }
   }
   return __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+}
+// Out-of-line variant for rarely taken paths (keeps the polling loop out of hot code).
+__device__ __noinline__ double ll_load16_cold(const u64* rec, int j, u64 epoch, int* err) {
+  return ll_load16(rec, j, epoch, err);
 }
 // Warp-collective: all-rank totals of the record of `epoch` (NQ = 4 or 8 sums, the first `nr`
 // are live).  Lane l fetches value (l & 3) [+4] of rank (l >> 2): every word of the record is

@@ -79,8 +79,11 @@ __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_re
 __device__ __forceinline__ void pers_wait_gpu(const u64* p, u64 target, int* err) {
   if (ld_relaxed_gpu(p) < target) {
     const u64 t0 = timer_ns();
-    while (ld_relaxed_gpu(p) < target) {
-      if (*(volatile int*)err) break;
+    bool ok = false;
+    while (!ok) {
+#pragma unroll 1
+      for (int spin = 0; spin < 64 && !ok; ++spin) ok = ld_relaxed_gpu(p) >= target;
+      if (ok || *(volatile int*)err) break;
       if (timer_ns() - t0 > 10000000000ull) { atomicExch(err, 1); break; }
     }
   }
@@ -89,8 +92,11 @@ __device__ __forceinline__ void pers_wait_gpu(const u64* p, u64 target, int* err
 __device__ __forceinline__ void pers_wait_sys(const u64* p, u64 target, int* err) {
   if (ld_relaxed_sys(p) < target) {
     const u64 t0 = timer_ns();
-    while (ld_relaxed_sys(p) < target) {
-      if (*(volatile int*)err) break;
+    bool ok = false;
+    while (!ok) {
+#pragma unroll 1
+      for (int spin = 0; spin < 64 && !ok; ++spin) ok = ld_relaxed_sys(p) >= target;
+      if (ok || *(volatile int*)err) break;
       if (timer_ns() - t0 > 10000000000ull) { atomicExch(err, 1); break; }
     }
   }
@@ -479,8 +485,8 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
       const int ni = (int)n, pli = (int)pl;
       auto ldv = [&](const VecIn& a, const GhostLL& q, const double* loc, int r0, int c) -> double {
         if constexpr (SL) {             // ghost planes: LL words polled element by element (or plain doubles)
-          if (c < 0) return q.lo ? ll_load(q.lo, c + pli, q.ep, err) : __ldcg(a.lo + (c + pli));
-          if (c >= ni) return q.hi ? ll_load(q.hi, c - ni, q.ep, err) : __ldcg(a.hi + (c - ni));
+          if (c < 0) return q.lo ? ll_load16_cold(q.lo, c + pli, q.ep, err) : __ldcg(a.lo + (c + pli));
+          if (c >= ni) return q.hi ? ll_load16_cold(q.hi, c - ni, q.ep, err) : __ldcg(a.hi + (c - ni));
         }
         const unsigned d = (unsigned)(c - r0);
         const double* p = (loc != nullptr && d < (unsigned)T) ? loc + d : a.v + c;
