@@ -1040,8 +1040,12 @@ static int begin_prepare(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
   {
     const PersGeom G = pers_geometry(c, variant, ranks_in_launch);
     const bool mode_ok = c->dist.world <= 1 || c->dist.mode == 1 || c->dist.mode == 3;   // in-kernel exchange only
+    // measured (profiles/r01d_overlap_*): on a partition the persistent kernel wins at 2 GPUs
+    // (64^3: 10-25 vs 21-31 us/iteration) and loses at 8 (22-45 vs 17-29): its all-to-all record
+    // exchange is on the critical path of a much shorter iteration
+    const bool world_ok = c->dist.world <= 2;
     if (path == CGX_PATH_AUTO)
-      path = (c->n < c->pers_threshold && G.ok && mode_ok) ? CGX_PATH_PERSISTENT : CGX_PATH_STREAM;
+      path = (c->n < c->pers_threshold && G.ok && mode_ok && world_ok) ? CGX_PATH_PERSISTENT : CGX_PATH_STREAM;
     if (path == CGX_PATH_PERSISTENT && !G.ok)
       return fail(CGX_ERR_UNSUPPORTED, "cgx_begin: %lld rows x %d resident vectors do not fit the SMs' shared memory "
                   "(%zu B per CTA); use the stream path", (long long)c->n, G.nslot, G.smem);

@@ -365,3 +365,44 @@ def test_mpi4py_shaped_solvers_single_rank():
         ref = orc.solve_mpi_style(tag, A.diagonal(), b.copy(), its)
         np.testing.assert_allclose(x, ref, rtol=0, atol=4 * max(err, 1e-12))
     m.clear_sessions()
+
+
+# ----------------------------------------------------------------- degenerate / ragged inputs
+@pytest.mark.parametrize("path", ["stream", "persistent"])
+def test_degenerate_and_ragged_inputs(path):
+    """n = 1; max_iter = 1 (only the k = 0 entry); a diagonal matrix (the bcsstm* family);
+    ragged rows incl. empty ones inside a non-singular matrix; odd n (scalar tail of the
+    128-bit vector passes); all against the oracle."""
+    import scipy.sparse as sps
+    rng = np.random.default_rng(5)
+    mats = {
+        "n1": sps.csr_matrix(np.array([[3.0]])),
+        "diag": sps.diags(rng.uniform(1, 9, 37)).tocsr(),
+        "odd_tridiag": sps.diags([-np.ones(100), 2.5 * np.ones(101), -np.ones(100)], [-1, 0, 1]).tocsr(),
+    }
+    # ragged: arrow matrix (one dense row/column, 300 nnz) + diagonal; row lengths 2..300
+    n = 300
+    arrow = sps.lil_matrix((n, n))
+    arrow.setdiag(np.linspace(400, 800, n))
+    arrow[0, :] = 1.0
+    arrow[:, 0] = 1.0
+    arrow[0, 0] = 1000.0
+    mats["arrow"] = sps.csr_matrix(arrow)
+    for name, A in mats.items():
+        x_true, b, x0 = orc.setup_problem(A)
+        dinv = orc.jacobi_dinv(A)
+        for max_iter in (1, 2, 9):
+            for tag in ALL_TAGS:
+                dev = _device_solve(tag, A, b, x0, max_iter, dinv, x_true, path=path)
+                ref = orc.solve(tag, A, b, x0, max_iter, dinv=dinv, x_true=x_true)
+                for h in orc.HISTORIES:
+                    assert dev[h].shape == (max_iter,)
+                    # (a diagonal system with Jacobi converges in one step: what follows is
+                    # rounding noise, compared against an absolute floor relative to k = 0)
+                    np.testing.assert_allclose(dev[h][:3], ref[h][:3], rtol=1e-10, atol=1e-13 * ref[h][0] + 1e-300,
+                                               err_msg=f"{name}/{tag}/{h}")
+    # a structurally empty row makes A singular: the breakdown is reported, never hidden
+    S = sps.csr_matrix(np.diag([1.0, 0.0, 2.0]))
+    out = cg_variants.hs_pcg(S, np.array([1.0, 1.0, 1.0]), np.zeros(3), 6, callbacks=[cbk.updated_residual_2_norm],
+                             path=path, return_info=True)
+    assert out["updated_residual_2_norm"].shape == (6,)
