@@ -109,6 +109,8 @@ struct cgx_ctx {
   int* d_ptr = nullptr;
   int* d_idx = nullptr;
   double* d_val = nullptr;
+  std::vector<int> h_ptr;          // host copy of indptr (persistent kernel: shared-memory slab sizing)
+  bool no_slab = false;            // cgx_set_option("csr_slab", 0)
   int* d_rowblk = nullptr;         // CSR-stream row blocks (cgx_kernels.cuh)
   int n_rowblk = 0;
   i64 n = 0, nnz = 0;
@@ -195,6 +197,7 @@ static void free_op(cgx_ctx* c) {
   cudaFree(c->d_ptr); cudaFree(c->d_idx); cudaFree(c->d_val); cudaFree(c->d_rowblk);
   c->d_ptr = c->d_idx = c->d_rowblk = nullptr; c->d_val = nullptr;
   c->n_rowblk = 0;
+  c->h_ptr.clear();
   c->op_kind = 0;
 }
 static void free_problem(cgx_ctx* c) {
@@ -335,6 +338,7 @@ extern "C" int cgx_set_csr_host(cgx_ctx* c, int64_t n, int64_t nnz, const int32_
   }
   CU(cudaStreamSynchronize(c->stream));
   c->n_rowblk = (int)blk.size() - 1;
+  c->h_ptr.assign(indptr, indptr + n + 1);
   c->csr = CsrOp{c->d_ptr, c->d_idx, c->d_val, n};
   c->op_kind = 1;
   return CGX_OK;
@@ -920,16 +924,15 @@ extern "C" int cgx_load_problem_dev(cgx_ctx* c, const double* b, const double* x
 // ---------------------------------------------------------------------------------------
 // persistent path (cgx_persistent.cuh): one cooperative launch runs every iteration
 // ---------------------------------------------------------------------------------------
-struct PersGeom { int T, nb, R, nslot; unsigned vmask; size_t smem; bool ok; };
+struct PersGeom { int T, nb, R, nslot, slab_cap; unsigned vmask; size_t smem; bool ok; };
 
 // CTA shape for n rows per rank with `ranks_in_launch` ranks sharing one GPU's SMs
-static PersGeom pers_geometry(const cgx_ctx* c, int variant, int ranks_in_launch) {
+static PersGeom pers_geometry_T(const cgx_ctx* c, int variant, int ranks_in_launch, int T) {
   PersGeom G{};
   const VariantInfo vi = variant_info(variant, c->d_dinv != nullptr);
   G.vmask = vi.need;
   G.nslot = __builtin_popcount(vi.need) + (c->pm == 1 ? 1 : 0);
   const int sm_cap = std::max(1, c->sm_count / std::max(1, ranks_in_launch));
-  int T = c->pers_threads ? c->pers_threads : (c->n <= (i64)sm_cap * 256 ? 256 : 512);
   T = std::min(512, std::max(32, (T + 31) / 32 * 32));
   const i64 chunks = (c->n + T - 1) / T;
   int cap = c->pers_ctas ? std::min(c->pers_ctas, 4 * sm_cap) : sm_cap;     // co-residency is checked at launch
@@ -938,6 +941,28 @@ static PersGeom pers_geometry(const cgx_ctx* c, int variant, int ranks_in_launch
   G.T = T; G.R = (int)R; G.nb = (int)((chunks + R - 1) / R);
   G.smem = (size_t)G.nslot * R * T * sizeof(double) + (((size_t)R * T + 15) / 16) * 16;   // + row masks
   G.ok = G.smem <= 216 * 1024;
+  // CSR: keep each CTA's rows of the matrix in shared memory when they fit (one chunk per CTA)
+  G.slab_cap = 0;
+  if (c->op_kind == 1 && R == 1 && !c->h_ptr.empty() && !c->no_slab) {
+    i64 mx = 0;
+    for (i64 r0 = 0; r0 < c->n; r0 += T) mx = std::max<i64>(mx, c->h_ptr[std::min<i64>(c->n, r0 + T)] - c->h_ptr[r0]);
+    mx = (mx + 3) / 4 * 4;
+    const size_t slab = (size_t)mx * 12 + ((size_t)(T + 1) * 4 + 15) / 16 * 16;
+    if (mx > 0 && G.smem + slab <= 216 * 1024) { G.slab_cap = (int)mx; G.smem += slab; }
+  }
+  return G;
+}
+// CTA shape for n rows per rank with `ranks_in_launch` ranks sharing one GPU's SMs
+static PersGeom pers_geometry(const cgx_ctx* c, int variant, int ranks_in_launch) {
+  const int sm_cap = std::max(1, c->sm_count / std::max(1, ranks_in_launch));
+  if (c->pers_threads) return pers_geometry_T(c, variant, ranks_in_launch, c->pers_threads);
+  PersGeom G = pers_geometry_T(c, variant, ranks_in_launch, c->n <= (i64)sm_cap * 256 ? 256 : 512);
+  if (c->op_kind == 1 && G.slab_cap == 0) {            // narrower CTAs so that the matrix slabs fit
+    for (int T : {128, 64}) {
+      PersGeom H = pers_geometry_T(c, variant, ranks_in_launch, T);
+      if (H.ok && H.slab_cap > 0) return H;
+    }
+  }
   return G;
 }
 
@@ -965,7 +990,7 @@ static int pers_launch_pm(cgx_ctx** cs, int count, const PersGeom& G, int k0, in
   CU(cudaMemcpyAsync(c0->d_prank, h.data(), sizeof(PersRank<Op>) * count, cudaMemcpyHostToDevice, c0->stream));
   CU(cudaStreamSynchronize(c0->stream));           // h is a host temporary
   PersLaunch L{};
-  L.k0 = k0; L.k1 = k1; L.nb = G.nb; L.R = G.R; L.vmask = G.vmask; L.nslot = G.nslot;
+  L.k0 = k0; L.k1 = k1; L.nb = G.nb; L.R = G.R; L.vmask = G.vmask; L.nslot = G.nslot; L.slab_cap = G.slab_cap;
   const PersRank<Op>* dr = static_cast<const PersRank<Op>*>(c0->d_prank);
   void* params[] = {(void*)&dr, (void*)&L};
   const void* fn = nullptr;
@@ -1275,6 +1300,7 @@ extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
   if (!c || !name) return fail(CGX_ERR_ARG, "cgx_set_option: bad arguments");
   if (!strcmp(name, "tma")) { c->no_tma = (value == 0); return CGX_OK; }
   if (!strcmp(name, "csr_stream")) { c->no_csr_stream = (value == 0); return CGX_OK; }
+  if (!strcmp(name, "csr_slab")) { c->no_slab = (value == 0); return CGX_OK; }
   if (!strcmp(name, "persistent_threshold")) { c->pers_threshold = value; return CGX_OK; }
   if (!strcmp(name, "pers_threads")) { c->pers_threads = value; return CGX_OK; }
   if (!strcmp(name, "pers_ctas")) { c->pers_ctas = value; return CGX_OK; }

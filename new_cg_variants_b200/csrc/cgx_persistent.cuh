@@ -59,7 +59,12 @@ struct PersLaunch {
   int R;                               // row chunks per CTA
   unsigned vmask;                      // state vectors of the variant (bit v)
   int nslot;                           // shared-memory vector slots (popcount(vmask) [+1 for dinv])
+  int slab_cap;                        // CSR: non-zeros of a CTA's rows kept in shared memory (0 = off; needs R == 1)
 };
+
+// A CTA's rows of a CSR matrix, resident in shared memory for the whole solve (values, columns,
+// row offsets relative to the CTA's first non-zero).
+struct CsrSlab { const double* val; const int* col; const int* ptr; };
 
 __device__ __forceinline__ u64 ld_relaxed_gpu(const u64* p) {
   u64 v;
@@ -167,6 +172,22 @@ template <int NVX, class Ld>
 __device__ __forceinline__ void pers_row(const CsrOp& A, int row, unsigned, Ld ld, double (&y)[NVX]) {
   A.template row<NVX>((i64)row, [&](i64 c, double (&v)[NVX]) { ld((int)c, v); }, y);
 }
+// same sum (stored order, separately rounded multiply and add) from the shared-memory slab
+template <int NVX, class Ld>
+__device__ __forceinline__ void pers_row_slab(const CsrSlab& S, int lrow, Ld ld, double (&y)[NVX]) {
+#pragma unroll
+  for (int c = 0; c < NVX; ++c) y[c] = 0.0;
+  const int e = S.ptr[lrow + 1];
+  for (int jj = S.ptr[lrow]; jj < e; ++jj) {
+    const double a = S.val[jj];
+    double v[NVX];
+    ld(S.col[jj], v);
+#pragma unroll
+    for (int c = 0; c < NVX; ++c) y[c] = add_(y[c], mul_(a, v[c]));
+  }
+}
+template <int NVX, class Ld>
+__device__ __forceinline__ void pers_row_slab(const CsrSlab&, int, Ld, double (&)[NVX], const StencilOp&) {}
 
 struct PersRec { u64 e; int kind; int k; int hist; };      // a published record still to be folded
 
@@ -235,6 +256,25 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
   for (int j = 0; j < L.R; ++j) {
     const i64 row = ((i64)j * nb + cta) * T + tid;
     if (row < n) smask[j * T + tid] = (unsigned char)stencil_mask(A, (int)row);
+  }
+  // CSR: this CTA's matrix rows -> shared memory (one coalesced sweep, once per launch)
+  CsrSlab slab{nullptr, nullptr, nullptr};
+  bool use_slab = false;
+  if constexpr (!SL) {
+    if (L.slab_cap > 0) {
+      unsigned char* base = reinterpret_cast<unsigned char*>(smask) + (((size_t)L.R * T + 15) / 16) * 16;
+      double* sval = reinterpret_cast<double*>(base);
+      int* scol = reinterpret_cast<int*>(sval + L.slab_cap);
+      int* sptr = scol + L.slab_cap;
+      const i64 r0 = (i64)cta * T, r1 = min(n, r0 + T);
+      if (r0 < n) {
+        const int e0 = A.ptr[r0], cnt = A.ptr[r1] - e0;
+        for (int e = tid; e < cnt; e += T) { sval[e] = A.val[e0 + e]; scol[e] = A.idx[e0 + e]; }
+        for (int t = tid; t <= (int)(r1 - r0); t += T) sptr[t] = A.ptr[r0 + t] - e0;
+      }
+      slab = CsrSlab{sval, scol, sptr};
+      use_slab = true;
+    }
   }
   __syncthreads();
 
@@ -504,13 +544,15 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
         const int r0 = (j * nb + cta) * T;
         if (hist) {
           double y[NV + 2];
-          pers_row<NV + 2>(A, (int)row, smask[li], [&](int c, double (&v)[NV + 2]) {
+          auto ldh = [&](int c, double (&v)[NV + 2]) {
             v[0] = ldv(in0, q0, sl0 + j * T, r0, c);
             if constexpr (NV == 2) v[1] = ldv(in1, q1, sl1 + j * T, r0, c);
             const double xj = ldv(xin, qx, gl.x + j * T, r0, c);
             v[NV] = xj;
             v[NV + 1] = has_xt ? sub_(xj, ldv(xtin, qn, nullptr, r0, c)) : 0.0;
-          }, y);
+          };
+          if (!SL && use_slab) pers_row_slab<NV + 2>(slab, tid, ldh, y);
+          else pers_row<NV + 2>(A, (int)row, smask[li], ldh, y);
           double ysp[NV];
 #pragma unroll
           for (int c = 0; c < NV; ++c) ysp[c] = y[c];
@@ -526,10 +568,12 @@ __global__ void __launch_bounds__(512) persistent_kernel(const PersRank<Op>* __r
           hs[3] = fma(ri, ri, hs[3]);
         } else {
           double y[NV];
-          pers_row<NV>(A, (int)row, smask[li], [&](int c, double (&v)[NV]) {
+          auto ldp2 = [&](int c, double (&v)[NV]) {
             v[0] = ldv(in0, q0, sl0 + j * T, r0, c);
             if constexpr (NV == 2) v[1] = ldv(in1, q1, sl1 + j * T, r0, c);
-          }, y);
+          };
+          if (!SL && use_slab) pers_row_slab<NV>(slab, tid, ldp2, y);
+          else pers_row<NV>(A, (int)row, smask[li], ldp2, y);
           sp_epilogue<SP, PM, NV>(gl, loc0, li, y, r4, nullptr);
         }
       }

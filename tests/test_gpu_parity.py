@@ -406,3 +406,24 @@ def test_degenerate_and_ragged_inputs(path):
     out = cg_variants.hs_pcg(S, np.array([1.0, 1.0, 1.0]), np.zeros(3), 6, callbacks=[cbk.updated_residual_2_norm],
                              path=path, return_info=True)
     assert out["updated_residual_2_norm"].shape == (6,)
+
+
+@pytest.mark.parametrize("name", ["bcsstk16", "bcsstk18", "nos7", "bcsstm24", "model_48_8_3", "1138_bus"])
+def test_persistent_csr_slab_equals_global_reads(name):
+    """Persistent kernel with each CTA's matrix rows resident in shared memory (default when they
+    fit) against the same kernel reading the matrix from L2 (csr_slab = 0): same row sums, the
+    CTA shape (hence the fixed summation order of the dots) may differ -> equal to rounding."""
+    A = helpers.load_matrix(name)
+    x_true, b, x0 = orc.setup_problem(A)
+    dinv = orc.jacobi_dinv(A)
+    res = {}
+    for flag in (1, 0):
+        with Session(A, dinv=dinv) as s:
+            s.set_option("csr_slab", flag)
+            for tag in ("hs", "cg", "pr", "pipe_pr", "gv"):
+                x, hist, info = s.solve(tag, b, x0, 10, x_true=x_true, path="persistent")
+                assert info["path"] == 2
+                res[(flag, tag)] = hist
+    for tag in ("hs", "cg", "pr", "pipe_pr", "gv"):
+        for h in orc.HISTORIES:
+            np.testing.assert_allclose(res[(1, tag)][h][:6], res[(0, tag)][h][:6], rtol=1e-9, err_msg=f"{name}/{tag}/{h}")
