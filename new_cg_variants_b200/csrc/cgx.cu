@@ -110,6 +110,7 @@ struct cgx_ctx {
   int* d_idx = nullptr;
   double* d_val = nullptr;
   std::vector<int> h_ptr;          // host copy of indptr (persistent kernel: shared-memory slab sizing)
+  bool no_elide = false;           // cgx_set_option("cg_elide", 0)
   bool no_slab = false;            // cgx_set_option("csr_slab", 0)
   int* d_rowblk = nullptr;         // CSR-stream row blocks (cgx_kernels.cuh)
   int n_rowblk = 0;
@@ -121,6 +122,7 @@ struct cgx_ctx {
   // TMA-staged stencil path
   bool use_tma = false;
   int dbg = 0;                     // option "debug_skip" (timing experiments only)
+  bool cg_elide = false;           // CG-CG: r~ / GV: w~ not stored (EW_*_E / SP_*_E)
   bool halo_ll = false;            // multi-GPU: the fused SpMV passes are TMA kernels -> LL ghost planes
   bool no_tma = false;             // cgx_set_option("tma", 0): force the generic stencil kernel
   bool no_csr_stream = false;      // cgx_set_option("csr_stream", 0): one thread per row
@@ -504,6 +506,8 @@ template <int MODE> struct SpInput { static constexpr int v0 = -1, v1 = -1; };
 template <> struct SpInput<SP_HS> { static constexpr int v0 = V_P, v1 = -1; };
 template <> struct SpInput<SP_PR> { static constexpr int v0 = V_P, v1 = -1; };
 template <> struct SpInput<SP_CG> { static constexpr int v0 = V_RT, v1 = -1; };
+template <> struct SpInput<SP_CG_E> { static constexpr int v0 = V_R, v1 = -1; };
+template <> struct SpInput<SP_GV_E> { static constexpr int v0 = V_W, v1 = -1; };
 template <> struct SpInput<SP_GV> { static constexpr int v0 = V_WT, v1 = -1; };
 template <> struct SpInput<SP_PIPE_R> { static constexpr int v0 = V_ST, v1 = V_RT; };
 template <> struct SpInput<SP_PIPE_N> { static constexpr int v0 = V_ST, v1 = -1; };
@@ -520,7 +524,7 @@ static void launch_spmv(cgx_ctx* c, Args g, const double* vin, double* vout) {
   p.hin_n = nv; p.hin_ch = 0;
   plan_apply(c, g, p);
   {
-    ProfScope ps(c, PC_SP0 + MODE);
+    ProfScope ps(c, PC_SP0 + (MODE == SP_CG_E ? (int)SP_CG : MODE == SP_GV_E ? (int)SP_GV : MODE));
     bool done = false;
     if constexpr (v0 >= 0) {
       if (c->op_kind == 2 && c->use_tma && c->tmap_ok[v0] && (v1 < 0 || c->tmap_ok[v1 < 0 ? 0 : v1])) {
@@ -571,7 +575,7 @@ static void launch_ew(cgx_ctx* c, Args g) {
   plan_apply(c, g, p);
   {
     const int grid = grid_for(c, (c->n + 1) / 2);
-    ProfScope ps(c, PC_EW0 + KID);
+    ProfScope ps(c, PC_EW0 + (KID == EW_CG_E ? (int)EW_CG : KID == EW_GV_E ? (int)EW_GV : KID));
     ew_kernel<KID, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(g);
     c->launches++;
   }
@@ -748,9 +752,21 @@ static void iter_stage_pm(cgx_ctx* c, int s, const Args& g) {
       else launch_spmv<SP_HS, PM, false>(c, g, nullptr, nullptr);
       break;
     case CGX_CG:
+      if constexpr (PM != 1) {
+        if (c->cg_elide) {
+          if (s == 0) launch_ew<EW_CG_E, PM, false>(c, g); else launch_spmv<SP_CG_E, PM, false>(c, g, nullptr, nullptr);
+          break;
+        }
+      }
       if (s == 0) launch_ew<EW_CG, PM, false>(c, g); else launch_spmv<SP_CG, PM, false>(c, g, nullptr, nullptr);
       break;
     case CGX_GV:
+      if constexpr (PM != 1) {
+        if (c->cg_elide) {
+          if (s == 0) launch_ew<EW_GV_E, PM, false>(c, g); else launch_spmv<SP_GV_E, PM, false>(c, g, nullptr, nullptr);
+          break;
+        }
+      }
       if (s == 0) launch_ew<EW_GV, PM, false>(c, g); else launch_spmv<SP_GV, PM, false>(c, g, nullptr, nullptr);
       break;
     case CGX_PR:
@@ -1082,6 +1098,9 @@ static int begin_prepare(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
       for (int b = 0; b < (vi.pipe && vi.recompute ? 2 : 1); ++b)
         if (!c->d_exp[a][b]) CU(cudaMalloc(&c->d_exp[a][b], sizeof(double) * c->n));
   c->path = path;
+  c->cg_elide = (variant == CGX_CG || variant == CGX_GV) && path == CGX_PATH_STREAM && c->op_kind == 2 && c->use_tma &&
+                c->tmap_ok[variant == CGX_CG ? V_R : V_W] &&
+                c->pm != 1 && !c->no_elide;
   c->launches_run = 0; c->loop_ms = 0.0;
   c->pend.clear();
   return CGX_OK;
@@ -1301,6 +1320,7 @@ extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
   if (!strcmp(name, "tma")) { c->no_tma = (value == 0); return CGX_OK; }
   if (!strcmp(name, "csr_stream")) { c->no_csr_stream = (value == 0); return CGX_OK; }
   if (!strcmp(name, "csr_slab")) { c->no_slab = (value == 0); return CGX_OK; }
+  if (!strcmp(name, "cg_elide")) { c->no_elide = (value == 0); return CGX_OK; }
   if (!strcmp(name, "persistent_threshold")) { c->pers_threshold = value; return CGX_OK; }
   if (!strcmp(name, "pers_threads")) { c->pers_threads = value; return CGX_OK; }
   if (!strcmp(name, "pers_ctas")) { c->pers_ctas = value; return CGX_OK; }
@@ -1376,6 +1396,11 @@ extern "C" int cgx_fetch_vector_host(cgx_ctx* c, const char* name, double* out) 
     if (!strcmp(name, kVecNames[i])) {
       if (!c->vec[i]) return fail(CGX_ERR_ARG, "cgx_fetch_vector_host: vector '%s' is not part of the last variant's state", name);
       CU(cudaSetDevice(c->device));
+      if (((i == V_RT && c->variant == CGX_CG) || (i == V_WT && c->variant == CGX_GV)) && c->cg_elide && c->cur_k > 0) {
+        // r~ (CG-CG) / w~ (GV) was elided in the loop: it is M r / M w
+        launch_scale(c, c->d_dinv, c->vec[i == V_RT ? V_R : V_W], c->vec[i]);
+        CU(cudaStreamSynchronize(c->stream));
+      }
       CU(cudaMemcpy(out, c->vec[i], sizeof(double) * c->n, cudaMemcpyDeviceToHost));
       return CGX_OK;
     }

@@ -120,13 +120,18 @@ enum {
   EW_GV,        // [deferred p,s,st,u] ; x,r,rt,w ; wt = M w ; nu,eta
   EW_PR,        // x,r,rt ; p ; nu = rt.r
   EW_PIPE_R,    // pipe family with recompute of w (pipe_pr, pipe_pr_m)
-  EW_PIPE_N     // pipe family without recompute (pipe_p, pipe_p_m)
+  EW_PIPE_N,    // pipe family without recompute (pipe_p, pipe_p_m)
+  EW_CG_E       // EW_CG with r~ elided: identity / constant-diagonal Jacobi and the TMA stencil pass,
+                // which then multiplies M r on the fly (r~ = M r is recomputed every iteration in CG-CG,
+                // cg_cg.py:132, so the products are the same bits; 3 of 14 words per row less)
+  , EW_GV_E     // EW_GV with w~ elided on the same grounds (w~ = M w, gv_cg.py:160): 2 of 21 words less
 };
-enum { SP_PLAIN = 0, SP_HS, SP_CG, SP_GV, SP_PR, SP_PIPE_R, SP_PIPE_N, SP_RESID };
+enum { SP_PLAIN = 0, SP_HS, SP_CG, SP_GV, SP_PR, SP_PIPE_R, SP_PIPE_N, SP_RESID, SP_CG_E, SP_GV_E };
 
 template <int KID> struct EwTraits { static constexpr int NR = 0; };
 template <> struct EwTraits<EW_HS1> { static constexpr int NR = 1; };
 template <> struct EwTraits<EW_GV> { static constexpr int NR = 2; };
+template <> struct EwTraits<EW_GV_E> { static constexpr int NR = 2; };
 template <> struct EwTraits<EW_PR> { static constexpr int NR = 1; };
 template <> struct EwTraits<EW_PIPE_R> { static constexpr int NR = 4; };
 template <> struct EwTraits<EW_PIPE_N> { static constexpr int NR = 4; };
@@ -342,6 +347,36 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
     stp<W>(g.p, i, p); stp<W>(g.s, i, s); stp<W>(g.x, i, x); stp<W>(g.r, i, r);
     stp<W>(g.rt, i, rt);
     halo_store<W>(g, 0, i, rt);
+  } else if constexpr (KID == EW_CG_E) {     // EW_CG without the r~ stream (PM 0 / 2 only)
+    Pk<W> x = ldp<W>(g.x, i), r = ldp<W>(g.r, i), p = ldp<W>(g.p, i), s = ldp<W>(g.s, i), w = ldp<W>(g.w, i);
+#pragma unroll
+    for (int l = 0; l < W; ++l) {
+      p.v[l] = axpy_(M(r.v[l], l), b, p.v[l]);          // r~_{k-1} = M r_{k-1}, the bits EW_CG stored
+      s.v[l] = axpy_(w.v[l], b, s.v[l]);
+      x.v[l] = axpy_(x.v[l], a, p.v[l]);
+      r.v[l] = axmy_(r.v[l], a, s.v[l]);
+    }
+    stp<W>(g.p, i, p); stp<W>(g.s, i, s); stp<W>(g.x, i, x); stp<W>(g.r, i, r);
+    halo_store<W>(g, 0, i, r);                           // the stencil pass scales it
+  } else if constexpr (KID == EW_GV_E) {     // EW_GV without the w~ stream (PM 0 / 2 only)
+    Pk<W> x = ldp<W>(g.x, i), r = ldp<W>(g.r, i), rt = ldp<W>(g.rt, i), p = ldp<W>(g.p, i),
+          s = ldp<W>(g.s, i), st = ldp<W>(g.st, i), w = ldp<W>(g.w, i), u = ldp<W>(g.u, i), t = ldp<W>(g.t, i);
+#pragma unroll
+    for (int l = 0; l < W; ++l) {
+      p.v[l] = axpy_(rt.v[l], b, p.v[l]);
+      s.v[l] = axpy_(w.v[l], b, s.v[l]);
+      st.v[l] = axpy_(M(w.v[l], l), b, st.v[l]);        // w~_{k-1} = M w_{k-1}, the bits EW_GV stored
+      u.v[l] = axpy_(t.v[l], b, u.v[l]);
+      x.v[l] = axpy_(x.v[l], a, p.v[l]);
+      r.v[l] = axmy_(r.v[l], a, s.v[l]);
+      rt.v[l] = axmy_(rt.v[l], a, st.v[l]);
+      w.v[l] = axmy_(w.v[l], a, u.v[l]);
+      red[0] = fma(r.v[l], rt.v[l], red[0]);
+      red[1] = fma(w.v[l], rt.v[l], red[1]);
+    }
+    stp<W>(g.p, i, p); stp<W>(g.s, i, s); stp<W>(g.st, i, st); stp<W>(g.u, i, u);
+    stp<W>(g.x, i, x); stp<W>(g.r, i, r); stp<W>(g.rt, i, rt); stp<W>(g.w, i, w);
+    halo_store<W>(g, 0, i, w);                           // the stencil pass scales it
   } else if constexpr (KID == EW_GV) {       // gv_cg.py:165-168 (deferred), :151-154,160,162-163
     Pk<W> x = ldp<W>(g.x, i), r = ldp<W>(g.r, i), rt = ldp<W>(g.rt, i), p = ldp<W>(g.p, i),
           s = ldp<W>(g.s, i), st = ldp<W>(g.st, i), w = ldp<W>(g.w, i), wt = ldp<W>(g.wt, i),
@@ -418,6 +453,7 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
 template <int KID> struct EwKind { static constexpr int FK = FK_NONE; };
 template <> struct EwKind<EW_HS1> { static constexpr int FK = FK_HS_NU; };
 template <> struct EwKind<EW_GV> { static constexpr int FK = FK_CGGV; };
+template <> struct EwKind<EW_GV_E> { static constexpr int FK = FK_CGGV; };
 template <> struct EwKind<EW_PR> { static constexpr int FK = FK_PR_NU; };
 template <> struct EwKind<EW_PIPE_R> { static constexpr int FK = FK_PIPE; };
 template <> struct EwKind<EW_PIPE_N> { static constexpr int FK = FK_PIPE; };
@@ -433,9 +469,11 @@ __device__ __forceinline__ void ew_prefetch(const Args& g, i64 i) {
   if constexpr (KID == EW_HS1) { pf(g.s); }
   else if constexpr (KID == EW_HS2) { pf(g.x); pf(g.p); }
   else {
-    pf(g.x); pf(g.rt); pf(g.p); pf(g.s);
-    if constexpr (KID == EW_CG) pf(g.w);
+    pf(g.x); pf(g.p); pf(g.s);
+    if constexpr (KID != EW_CG_E) pf(g.rt);
+    if constexpr (KID == EW_CG || KID == EW_CG_E) pf(g.w);
     if constexpr (KID == EW_GV) { pf(g.st); pf(g.w); pf(g.wt); pf(g.u); pf(g.t); }
+    if constexpr (KID == EW_GV_E) { pf(g.st); pf(g.w); pf(g.u); pf(g.t); }
     if constexpr (KID == EW_PIPE_R || KID == EW_PIPE_N) { pf(g.st); pf(g.w); pf(g.u); }
     if constexpr (KID == EW_PIPE_N && PM != 0) pf(g.wt);
   }
@@ -495,6 +533,7 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(const Args g) {
 template <int MODE> struct SpTraits { static constexpr int NR = 0, FK = FK_NONE, NV = 1; };
 template <> struct SpTraits<SP_HS> { static constexpr int NR = 1, FK = FK_HS_MU, NV = 1; };
 template <> struct SpTraits<SP_CG> { static constexpr int NR = 2, FK = FK_CGGV, NV = 1; };
+template <> struct SpTraits<SP_CG_E> { static constexpr int NR = 2, FK = FK_CGGV, NV = 1; };
 template <> struct SpTraits<SP_PR> { static constexpr int NR = 3, FK = FK_PR_SP, NV = 1; };
 template <> struct SpTraits<SP_PIPE_R> { static constexpr int NR = 0, FK = FK_NONE, NV = 2; };
 
@@ -531,6 +570,8 @@ __device__ __forceinline__ void sp_epilogue(const Args& g, const VecIn& in0, i64
   } else if constexpr (MODE == SP_HS) {        // hs_cg.py:123-124
     g.s[i] = y[0];
     red[0] = fma(in0.v[i], y[0], red[0]);
+  } else if constexpr (MODE == SP_CG_E || MODE == SP_GV_E) {      // TMA stencil kernel only (see cgx_stencil_tma.cuh)
+    (void)y;
   } else if constexpr (MODE == SP_CG) {        // cg_cg.py:133-135
     g.w[i] = y[0];
     const double rti = in0.v[i];

@@ -250,7 +250,7 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
           const int gx = x0 + px;
           if (gx < G.nx) {
             const int c = (ly + 1) * kPX + (px + 2);
-            double y[NV], ctr[NV];
+            double y[NV], ctr[NV], raw[NV];
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
               const double* qm = pm + v * kPlaneStride;
@@ -261,15 +261,22 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
               // started at +0.0 (such a sum can never be -0.0), so no select is needed and the
               // bits equal scipy's sum over the stored entries only.  Absent z-planes are not
               // loaded at all (stale shared memory): those two terms keep their select.
+              // SP_CG_E: the tile holds r; the operand is r~ = M r, formed here (the product
+              // EW_CG would have stored), so r~ is neither written nor read from HBM
+              auto in = [&](double q) {
+                if constexpr ((MODE == SP_CG_E || MODE == SP_GV_E) && PM == 2) return mul_(g.dinv_s, q);
+                else return q;
+              };
               double acc = 0.0, t;
-              t = add_(acc, mul_(G.off, qm[c]));        acc = has_zm ? t : acc;
-              acc = add_(acc, mul_(G.off, qc[c - kPX]));
-              acc = add_(acc, mul_(G.off, qc[c - 1]));
-              ctr[v] = qc[c];
+              t = add_(acc, mul_(G.off, in(qm[c])));        acc = has_zm ? t : acc;
+              acc = add_(acc, mul_(G.off, in(qc[c - kPX])));
+              acc = add_(acc, mul_(G.off, in(qc[c - 1])));
+              raw[v] = qc[c];
+              ctr[v] = in(raw[v]);
               acc = add_(acc, mul_(G.diag, ctr[v]));
-              acc = add_(acc, mul_(G.off, qc[c + 1]));
-              acc = add_(acc, mul_(G.off, qc[c + kPX]));
-              t = add_(acc, mul_(G.off, qp[c]));        acc = has_zp ? t : acc;
+              acc = add_(acc, mul_(G.off, in(qc[c + 1])));
+              acc = add_(acc, mul_(G.off, in(qc[c + kPX])));
+              t = add_(acc, mul_(G.off, in(qp[c])));        acc = has_zp ? t : acc;
               y[v] = acc;
             }
             const i64 i = ibase + 32 * m;
@@ -281,11 +288,15 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             if constexpr (MODE == SP_HS) {                 // hs_cg.py:123-124
               g.s[i] = y[0];
               red[0] = fma(ctr[0], y[0], red[0]);
+            } else if constexpr (MODE == SP_CG_E) {        // cg_cg.py:133-135 with r from the tile
+              g.w[i] = y[0];
+              red[0] = fma(raw[0], ctr[0], red[0]);
+              red[1] = fma(y[0], ctr[0], red[1]);
             } else if constexpr (MODE == SP_CG) {          // cg_cg.py:133-135
               g.w[i] = y[0];
               red[0] = fma(rv[m], ctr[0], red[0]);
               red[1] = fma(y[0], ctr[0], red[1]);
-            } else if constexpr (MODE == SP_GV) {          // gv_cg.py:161
+            } else if constexpr (MODE == SP_GV || MODE == SP_GV_E) {          // gv_cg.py:161
               g.t[i] = y[0];
             } else if constexpr (MODE == SP_PR) {          // pr_cg.py:152-156
               g.s[i] = y[0];

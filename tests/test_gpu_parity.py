@@ -427,3 +427,34 @@ def test_persistent_csr_slab_equals_global_reads(name):
     for tag in ("hs", "cg", "pr", "pipe_pr", "gv"):
         for h in orc.HISTORIES:
             np.testing.assert_allclose(res[(1, tag)][h][:6], res[(0, tag)][h][:6], rtol=1e-9, err_msg=f"{name}/{tag}/{h}")
+
+
+@pytest.mark.parametrize("shape", [(64, 24, 20), (130, 9, 7), (256, 16, 1)])
+def test_cg_cg_with_elided_rt_is_bitwise_identical(shape):
+    """CG-CG on the TMA stencil path does not store r~ (= M r, recomputed every iteration in the
+    reference, cg_cg.py:132): the stencil pass multiplies it on the fly.  Same products, same
+    summation orders -> the solve is BITWISE the one that streams r~ (cg_elide = 0)."""
+    nx, ny, nz = shape
+    S = PoissonStencil(nx, ny, nz, dim=2 if nz == 1 else 3)
+    n = S.shape[0]
+    x_true = np.ones(n) / np.sqrt(n)
+    b, x0 = S @ x_true, np.zeros(n)
+    for dinv in (1 / S.diagonal(), None):
+        res = {}
+        for flag in (1, 0):
+            with Session(S, dinv=dinv) as s:
+                s.set_option("cg_elide", flag)
+                x, hist, info = s.solve("cg", b, x0, 25, x_true=x_true, path="stream")
+                res[flag] = (x, hist, s.vector("rt"), s.vector("w"))
+                x, hist, info = s.solve("gv", b, x0, 25, x_true=x_true, path="stream")       # same for GV's w~
+                res[("gv", flag)] = (x, hist, s.vector("wt"), s.vector("t"))
+        for a, b_ in ((res[1], res[0]), (res[("gv", 1)], res[("gv", 0)])):
+            assert np.array_equal(a[0], b_[0])
+            for h in orc.HISTORIES:
+                assert np.array_equal(a[1][h], b_[1][h], equal_nan=True), h
+            assert np.array_equal(a[2], b_[2]) and np.array_equal(a[3], b_[3])
+    # a Jacobi VECTOR (non-constant diagonal) keeps the r~ stream
+    with Session(S, dinv=1 / (S.diagonal() + np.arange(n) % 3)) as s:
+        x, hist, info = s.solve("cg", b, x0, 12, x_true=x_true, path="stream")
+        ref = orc.solve("cg", S.tocsr(), b, x0, 12, dinv=1 / (S.diagonal() + np.arange(n) % 3), x_true=x_true)
+        np.testing.assert_allclose(hist["updated_residual_2_norm"][:8], ref["updated_residual_2_norm"][:8], rtol=1e-10)
