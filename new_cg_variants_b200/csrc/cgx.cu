@@ -618,15 +618,20 @@ static bool tma_prepare_geom(cgx_ctx* c) {
   G.ntx = (S.nx + kTX - 1) / kTX; G.nty = (S.ny + kTY - 1) / kTY;
   G.has_zlo = S.has_zlo; G.has_zhi = S.has_zhi;
   G.diag = S.diag; G.off = S.off;
+  G.march_y = 0;
+  if (S.nz == 1 && !S.has_zlo && !S.has_zhi && G.nty > 1) {   // 2-D: march down the y-tiles of a column
+    G.march_y = 1;
+    G.nz = G.nty;
+    G.nty = 1;
+  }
   // resident CTAs: shared memory bound (227 KB/SM), 8 x 256 threads at most
-  const int cols = G.ntx * G.nty;
   int per_sm1 = std::min(8, (int)(227 * 1024 / (tma_smem_bytes(1) + 1024)));
   int per_sm2 = std::min(8, (int)(227 * 1024 / (tma_smem_bytes(2) + 1024)));
   const int cap1 = c->sm_count * per_sm1, cap2 = c->sm_count * per_sm2;
   // one CTA per resident slot; the kernel cuts the (column, plane) sequence evenly between
   // them (>= 4 planes per CTA when the problem is large enough to keep the z-halo small)
   G.lz = 0; G.nchunks = 0;
-  const i64 total = (i64)cols * S.nz;
+  const i64 total = (i64)(G.ntx * G.nty) * G.nz;
   const i64 want = std::max<i64>(1, (total + 3) / 4);
   c->tma_grid[0] = (int)std::min<i64>(want, cap1);
   c->tma_grid[1] = (int)std::min<i64>(want, cap2);

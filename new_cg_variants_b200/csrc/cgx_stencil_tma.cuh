@@ -87,6 +87,9 @@ struct TmaGeom {
   int nx, ny, nz;
   int ntx, nty, nchunks, lz;     // tiles in x, y; z-chunks; planes per chunk
   int has_zlo, has_zhi;
+  int march_y;                   // 2-D grid: the "planes" of the march are the y-tiles (8 rows each) of a
+                                 // column of x-tiles, so consecutive tiles pipeline through the ring like
+                                 // z-planes do (nz = number of y-tiles, nty = 1; no z neighbours)
   double diag, off;
 };
 
@@ -147,8 +150,9 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
       double* dst = smem + (size_t)slot * NV * kPlaneStride;
       if (z < 0 || z >= G.nz) return;               // ghost plane: filled by fill_ghost (all threads)
       mbar_arrive_expect_tx(&bar[slot], kBytes);
-      tma_load_3d(dst, &tm0, x0 - 2, y0 - 1, z, &bar[slot]);
-      if constexpr (NV == 2) tma_load_3d(dst + kPlaneStride, &tm1, x0 - 2, y0 - 1, z, &bar[slot]);
+      const int ty0 = G.march_y ? z * kTY : y0, tz = G.march_y ? 0 : z;
+      tma_load_3d(dst, &tm0, x0 - 2, ty0 - 1, tz, &bar[slot]);
+      if constexpr (NV == 2) tma_load_3d(dst + kPlaneStride, &tm1, x0 - 2, ty0 - 1, tz, &bar[slot]);
     };
     auto wait_load = [&](uint32_t li) { mbar_wait(&bar[li % kRing], (li / kRing) & 1u); };
     // Ghost plane of a slab (multi-GPU): the neighbour rank's vector pass stored it into this
@@ -206,8 +210,8 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     wait_load(Lbase);
     wait_load(Lbase + 1);
 
-    const int gy = y0 + ly;
-    const bool row_ok = gy < G.ny;
+    int gy = y0 + ly;                                  // (march_y: set per step)
+    bool row_ok = gy < G.ny;
 
     // Operands that do not go through shared memory (r for the fused dots, a Jacobi vector)
     // are fetched ONE PLANE AHEAD into registers: their global-load latency is covered by a
@@ -217,10 +221,12 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     constexpr bool kNeedD = (MODE == SP_PR && PM == 1);
     double rv_n[kPtsPerThread], dvv_n[kPtsPerThread];
     auto fetch_direct = [&](int z) {
-      const i64 ib = (i64)z * plane_pts + (i64)gy * G.nx + x0 + lx;
+      const int gyz = G.march_y ? z * kTY + ly : gy;
+      const bool rok = gyz < G.ny;
+      const i64 ib = (G.march_y ? 0 : (i64)z * plane_pts) + (i64)gyz * G.nx + x0 + lx;
 #pragma unroll
       for (int m = 0; m < kPtsPerThread; ++m) {
-        const bool ok = row_ok && (x0 + lx + 32 * m) < G.nx;
+        const bool ok = rok && (x0 + lx + 32 * m) < G.nx;
         rv_n[m] = (kNeedR && ok) ? g.r[ib + 32 * m] : 0.0;
         dvv_n[m] = (kNeedD && ok) ? g.dinv[ib + 32 * m] : 0.0;
       }
@@ -232,7 +238,8 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
       if (tid == 0 && z + 2 <= z1) issue(z + 2, Lbase + j + 3);    // slot of plane z-2: free
       if (z + 2 <= z1 && is_ghost(z + 2)) fill_ghost(z + 2, Lbase + j + 3);
       double rv[kPtsPerThread], dvv[kPtsPerThread];
-      const i64 ibase = (i64)z * plane_pts + (i64)gy * G.nx + x0 + lx;
+      if (G.march_y) { gy = z * kTY + ly; row_ok = gy < G.ny; }
+      const i64 ibase = (G.march_y ? 0 : (i64)z * plane_pts) + (i64)gy * G.nx + x0 + lx;
 #pragma unroll
       for (int m = 0; m < kPtsPerThread; ++m) { rv[m] = rv_n[m]; dvv[m] = dvv_n[m]; }
       if constexpr (kNeedR || kNeedD) { if (z + 1 < z1) fetch_direct(z + 1); }
@@ -240,8 +247,8 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
       const double* pm = smem + (size_t)((Lbase + j) % kRing) * NV * kPlaneStride;
       const double* pc = smem + (size_t)((Lbase + j + 1) % kRing) * NV * kPlaneStride;
       const double* pp = smem + (size_t)((Lbase + j + 2) % kRing) * NV * kPlaneStride;
-      const bool has_zm = (z > 0) || G.has_zlo;
-      const bool has_zp = (z < G.nz - 1) || G.has_zhi;
+      const bool has_zm = !G.march_y && ((z > 0) || G.has_zlo);
+      const bool has_zp = !G.march_y && ((z < G.nz - 1) || G.has_zhi);
 
       if (row_ok) {
 #pragma unroll
