@@ -218,10 +218,10 @@ class DistSession(_RankBase):
         return self.info
 
     def solve_local(self, variant, b_loc, x0_loc, max_iter, x_true_loc=None, histories=(), return_x=True,
-                    path="auto"):
+                    path="auto", x_out=None):
         """The C-ABI round trip with this rank's HOST slices (cgx_solve_host)."""
         mask = _mask(histories)
-        x = np.empty(self.n) if return_x else None
+        x = x_out if x_out is not None else (np.empty(self.n) if return_x else None)
         hist = np.zeros((len(_lib.HIST_NAMES), int(max_iter))) if mask else None
         info = _lib.CgxInfo()
         rc = self._lib.cgx_solve_host(self._ctx, _lib.VARIANT_IDS[variant], _lib.dptr(b_loc), _lib.dptr(x0_loc),
@@ -247,16 +247,16 @@ class DistSession(_RankBase):
         parts = exchange_bytes(x_local.tobytes(), self.group)
         return np.concatenate([np.frombuffer(p, dtype=np.float64) for p in parts])
 
-    def e2e_bench(self, variant, b_loc, x0_loc, max_iter, steps, barrier):
+    def e2e_bench(self, variant, b_loc, x0_loc, max_iter, steps, barrier, x_out=None):
         """End-to-end timing through cgx_solve_host with (pinned) host slices: wall clock
         between two barriers, max over ranks taken by the caller's barrier."""
         import time
         for _ in range(2):
-            self.solve_local(variant, b_loc, x0_loc, max_iter, return_x=True)
+            self.solve_local(variant, b_loc, x0_loc, max_iter, return_x=True, x_out=x_out)
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            _, _, info = self.solve_local(variant, b_loc, x0_loc, max_iter, return_x=True)
+            _, _, info = self.solve_local(variant, b_loc, x0_loc, max_iter, return_x=True, x_out=x_out)
         barrier()
         dt = time.perf_counter() - t0
         return {"value": (max_iter - 1) * steps / dt, "unit": "iterations/s",

@@ -154,9 +154,10 @@ class Session:
         return out
 
     def solve(self, variant, b, x0, max_iter, x_true=None, histories=_lib.HIST_NAMES, path="auto",
-              return_x=True):
+              return_x=True, x_out=None):
         """The reference call in one C-ABI round trip (host buffers in, host buffers out).
 
+        ``x_out``: optional caller-owned (e.g. pinned) float64 array that receives x.
         Returns (x, {history name: (max_iter,) array}, info)."""
         b = _f64(b, self.n, "b")
         x0 = _f64(x0, self.n, "x0")
@@ -164,7 +165,11 @@ class Session:
         mask = 0
         for h in histories:
             mask |= _lib.HIST_BITS[h]
-        x = np.empty(self.n) if return_x else None
+        if x_out is not None:
+            assert x_out.dtype == np.float64 and x_out.flags.c_contiguous and x_out.shape == (self.n,)
+            x = x_out
+        else:
+            x = np.empty(self.n) if return_x else None
         hist = np.zeros((len(_lib.HIST_NAMES), int(max_iter))) if mask else None
         info = _lib.CgxInfo()
         rc = self._lib.cgx_solve_host(self._ctx, _lib.VARIANT_IDS[variant], _lib.dptr(b), _lib.dptr(x0),
