@@ -165,8 +165,6 @@ struct cgx_ctx {
   int scpar = 0;
   struct Pend { u64 e; int kind; int k; };
   std::vector<Pend> pend;
-  CUtensorMap gmap[kChan];
-  bool gmap_ok[kChan] = {};
   // mode 2: NCCL allreduce of the records on a side stream
   void* nccl_comm = nullptr;
   cudaStream_t comm_stream = nullptr;
@@ -630,7 +628,6 @@ static bool tma_prepare_geom(cgx_ctx* c) {
   const int cap1 = c->sm_count * per_sm1, cap2 = c->sm_count * per_sm2;
   // one CTA per resident slot; the kernel cuts the (column, plane) sequence evenly between
   // them (>= 4 planes per CTA when the problem is large enough to keep the z-halo small)
-  G.lz = 0; G.nchunks = 0;
   const i64 total = (i64)(G.ntx * G.nty) * G.nz;
   const i64 want = std::max<i64>(1, (total + 3) / 4);
   c->tma_grid[0] = (int)std::min<i64>(want, cap1);

@@ -80,12 +80,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 }
 
 // Geometry of one launch.  zlo/zhi: does a plane exist below z=0 / above z=nz-1 of THIS
-// slab (multi-GPU partition).  Those ghost planes live in the rank's window, written by the
-// neighbours, and are fetched through a second tensor map (nx, ny, 4) whose z coordinate is
-// parity*2 + side, after the halo epoch of that side has been published.
+// slab (multi-GPU partition).  Those ghost planes live in the rank's window as LL words,
+// stored by the neighbours' vector passes, and are copied into the ring slot by fill_ghost.
 struct TmaGeom {
   int nx, ny, nz;
-  int ntx, nty, nchunks, lz;     // tiles in x, y; z-chunks; planes per chunk
+  int ntx, nty;                  // tiles in x, y
   int has_zlo, has_zhi;
   int march_y;                   // 2-D grid: the "planes" of the march are the y-tiles (8 rows each) of a
                                  // column of x-tiles, so consecutive tiles pipeline through the ring like
