@@ -145,6 +145,9 @@ int cgx_get_scalars(cgx_ctx* ctx, double* out9);
  *      "csr_stream" = 0 the thread-per-row CSR kernel, so that two SpMV implementations can
  *      be compared bit for bit; "persistent_threshold" = rows below which CGX_PATH_AUTO
  *      takes the persistent kernel ("pers_threads" / "pers_ctas" override its CTA shape);
+ *      "csr_slab" = 0 keeps the persistent kernel's matrix in L2 instead of shared memory;
+ *      "cg_elide" = 0 makes CG-CG / GV stream r~ / w~ on the TMA stencil path instead of
+ *      forming them on the fly; "tma_min_planes" = planes per CTA the stencil grid aims for;
  *      "stub_allreduce" = 1 replaces the multi-GPU scalar
  *      exchange by a local stand-in (timing experiment: exposed allreduce time). */
 int cgx_set_option(cgx_ctx* ctx, const char* name, int value);

@@ -123,6 +123,7 @@ struct cgx_ctx {
   bool use_tma = false;
   int dbg = 0;                     // option "debug_skip" (timing experiments only)
   bool cg_elide = false;           // CG-CG: r~ / GV: w~ not stored (EW_*_E / SP_*_E)
+  int tma_min_planes = 4;          // option "tma_min_planes": planes per CTA the stencil grid aims for at least
   bool halo_ll = false;            // multi-GPU: the fused SpMV passes are TMA kernels -> LL ghost planes
   bool no_tma = false;             // cgx_set_option("tma", 0): force the generic stencil kernel
   bool no_csr_stream = false;      // cgx_set_option("csr_stream", 0): one thread per row
@@ -629,7 +630,8 @@ static bool tma_prepare_geom(cgx_ctx* c) {
   // one CTA per resident slot; the kernel cuts the (column, plane) sequence evenly between
   // them (>= 4 planes per CTA when the problem is large enough to keep the z-halo small)
   const i64 total = (i64)(G.ntx * G.nty) * G.nz;
-  const i64 want = std::max<i64>(1, (total + 3) / 4);
+  const i64 mp = std::max(1, c->tma_min_planes);
+  const i64 want = std::max<i64>(1, (total + mp - 1) / mp);
   c->tma_grid[0] = (int)std::min<i64>(want, cap1);
   c->tma_grid[1] = (int)std::min<i64>(want, cap2);
   return true;
@@ -1327,6 +1329,7 @@ extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
   if (!strcmp(name, "pers_threads")) { c->pers_threads = value; return CGX_OK; }
   if (!strcmp(name, "pers_ctas")) { c->pers_ctas = value; return CGX_OK; }
   if (!strcmp(name, "debug_skip")) { c->dbg = value; return CGX_OK; }
+  if (!strcmp(name, "tma_min_planes")) { c->tma_min_planes = value; return CGX_OK; }
   if (!strcmp(name, "stub_allreduce")) {
     // timing experiment (SURVEY.md section 8d "allreduce-hiding metric"): value != 0 replaces the
     // scalar exchange by a local stand-in; value == 0 restores the mode chosen at commit

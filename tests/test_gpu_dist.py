@@ -26,7 +26,8 @@ def _problem(S):
 
 
 @pytest.mark.parametrize("shape,world", [((16, 12, 8), 2), ((130, 10, 9), 3), ((258, 9, 12), 4),
-                                         ((20, 18, 16), 8), ((64, 1, 40), 4), ((7, 6, 10), 2)])
+                                         ((20, 18, 16), 8), ((64, 1, 40), 4), ((7, 6, 10), 2),
+                                         ((32, 6, 3), 3), ((128, 8, 5), 4)])       # one-plane slabs too
 def test_partitioned_run_matches_single_gpu(shape, world):
     """Every variant, Jacobi and identity: histories of the G-slab run agree with the
     single-context run to rounding over the first iterations (only the summation order of
@@ -105,7 +106,8 @@ def test_two_processes_two_gpus_match_emulation():
     assert "dist_worker ok" in out.stdout
 
 
-@pytest.mark.parametrize("shape,world", [((16, 12, 8), 2), ((64, 10, 9), 3), ((20, 18, 16), 8), ((64, 64, 16), 4)])
+@pytest.mark.parametrize("shape,world", [((16, 12, 8), 2), ((64, 10, 9), 3), ((20, 18, 16), 8), ((64, 64, 16), 4),
+                                         ((32, 6, 3), 3)])
 def test_partitioned_persistent_kernel(shape, world):
     """The persistent kernel on a partition: all ranks inside ONE cooperative launch (CTA range
     r*nb..(r+1)*nb-1 acts as rank r; windows, ghost planes and flags as between GPUs).  Against
