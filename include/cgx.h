@@ -151,6 +151,9 @@ int cgx_get_scalars(cgx_ctx* ctx, double* out9);
  *      "stub_allreduce" = 1 replaces the multi-GPU scalar
  *      exchange by a local stand-in (timing experiment: exposed allreduce time). */
 int cgx_set_option(cgx_ctx* ctx, const char* name, int value);
+/* timing experiments: 16 %globaltimer stamps written by the last vector pass under
+ * cgx_set_option("debug_skip", 2): [0] kernel start, [1] scalars folded, [2] CTA 0 done (ns). */
+int cgx_debug_times(cgx_ctx* ctx, uint64_t* out16);
 
 /* ---- optional per-kernel-class device timing of the iteration loop (CUDA event pair
  *      around every launch; used by bench.py for the roofline of the dominant kernel,

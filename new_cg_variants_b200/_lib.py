@@ -61,6 +61,7 @@ PROTOTYPES = {
     "cgx_get_info": (C.c_int, [_P, C.POINTER(CgxInfo)]),
     "cgx_get_scalars": (C.c_int, [_P, c_double_p]),
     "cgx_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "cgx_debug_times": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "cgx_set_profile": (C.c_int, [_P, C.c_int]),
     "cgx_get_profile": (C.c_int, [_P, C.c_int, c_double_p, C.POINTER(C.c_int64)]),
     "cgx_profile_class_name": (C.c_char_p, [C.c_int]),

@@ -122,6 +122,7 @@ struct cgx_ctx {
   // TMA-staged stencil path
   bool use_tma = false;
   int dbg = 0;                     // option "debug_skip" (timing experiments only)
+  u64* d_dbg_t = nullptr;          // 16 time stamps (dbg & 2)
   bool cg_elide = false;           // CG-CG: r~ / GV: w~ not stored (EW_*_E / SP_*_E)
   int tma_min_planes = 4;          // option "tma_min_planes": planes per CTA the stencil grid aims for at least
   bool halo_ll = false;            // multi-GPU: the fused SpMV passes are TMA kernels -> LL ghost planes
@@ -253,6 +254,8 @@ extern "C" int cgx_ctx_create(int device, cgx_ctx** out) {
   CU(cudaMalloc(&c->d_ppart, sizeof(double) * 2 * kPersMaxGrid * kPersRed));
   CU(cudaMalloc(&c->d_pbar, sizeof(u64) * 2));
   CU(cudaMemset(c->d_pbar, 0, sizeof(u64) * 2));
+  CU(cudaMalloc(&c->d_dbg_t, sizeof(u64) * 16));
+  CU(cudaMemset(c->d_dbg_t, 0, sizeof(u64) * 16));
   CU(cudaMalloc(&c->d_pout, sizeof(PersOut)));
   CU(cudaMemset(c->d_pout, 0, sizeof(PersOut)));
   CU(cudaMalloc(&c->d_prank, std::max(sizeof(PersRank<CsrOp>), sizeof(PersRank<StencilOp>)) * kMaxWorld));
@@ -285,7 +288,7 @@ extern "C" int cgx_ctx_destroy(cgx_ctx* c) {
   dist_release(c);
   free_state(c); free_problem(c); free_op(c);
   cudaFree(c->d_dinv); cudaFree(c->d_sc); cudaFree(c->d_partials); cudaFree(c->d_ticket);
-  cudaFree(c->d_ppart); cudaFree(c->d_pbar); cudaFree(c->d_pout); cudaFree(c->d_prank);
+  cudaFree(c->d_ppart); cudaFree(c->d_pbar); cudaFree(c->d_pout); cudaFree(c->d_prank); cudaFree(c->d_dbg_t);
   for (auto& e : c->ev) cudaEventDestroy(e);
   for (auto& e : c->prof_events) cudaEventDestroy(e);
   cudaStreamDestroy(c->own_stream);
@@ -432,6 +435,7 @@ static Args make_args(cgx_ctx* c) {
   g.d = c->dist;
   g.halo_ll = c->halo_ll ? 1 : 0;
   g.dbg = c->dbg;
+  g.dbg_t = c->d_dbg_t;
   return g;
 }
 
@@ -1339,6 +1343,14 @@ extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
     return CGX_OK;
   }
   return fail(CGX_ERR_ARG, "cgx_set_option: unknown option '%s'", name);
+}
+
+// timing experiments: the 16 %globaltimer stamps kernels wrote under option debug_skip & 2
+extern "C" int cgx_debug_times(cgx_ctx* c, uint64_t* out16) {
+  if (!c || !out16) return fail(CGX_ERR_ARG, "cgx_debug_times: bad arguments");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy(out16, c->d_dbg_t, sizeof(u64) * 16, cudaMemcpyDeviceToHost));
+  return CGX_OK;
 }
 
 extern "C" int cgx_set_profile(cgx_ctx* c, int on) {

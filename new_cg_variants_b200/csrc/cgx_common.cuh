@@ -282,6 +282,20 @@ __device__ __forceinline__ double ll_load16(const u64* rec, int j, u64 epoch, in
   }
   return __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
 }
+// Split form of ll_load16: issue the 16-byte load now, validate (and re-poll) later, so that
+// several records and other loads are in flight together.
+struct LLReq { const u64* src; u64 lo, hi; };
+__device__ __forceinline__ void ll_issue(LLReq& r) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(r.lo), "=l"(r.hi) : "l"(r.src) : "memory");
+}
+__device__ __forceinline__ double ll_finish(LLReq& r, u64 epoch, int* err) {
+  const u64 tag = epoch & 0xffffffffull;
+  if ((r.lo >> 32) != tag || (r.hi >> 32) != tag) {
+    r.lo = ll_poll(r.src, tag, err);
+    r.hi = ll_poll(r.src + 1, tag, err);
+  }
+  return __longlong_as_double((long long)((r.lo & 0xffffffffull) | (r.hi << 32)));
+}
 // Out-of-line variant for rarely taken paths (keeps the polling loop out of hot code).
 __device__ __noinline__ double ll_load16_cold(const u64* rec, int j, u64 epoch, int* err) {
   return ll_load16(rec, j, epoch, err);

@@ -98,7 +98,8 @@ struct Args {
   u64 xt_epoch;
   int meur;                        // Meurant predictor (kernels that are not templated on it)
   int halo_ll;                     // the consumer is the TMA stencil kernel: boundary planes travel as LL words
-  int dbg;                         // timing experiments (cgx_set_option "debug_skip"): 1 = no halo traffic
+  int dbg;                         // timing experiments (cgx_set_option "debug_skip"): 1 = no halo traffic, 2 = time stamps
+  u64* dbg_t;                      // dbg & 2: CTA 0 writes %globaltimer at kernel start / after the scalar fold / at its end
 };
 
 // An SpMV input vector: the owned slab and (multi-GPU) the ghost planes below and above.
@@ -244,21 +245,56 @@ __device__ __forceinline__ void dist_totals(const Args& g, u64 e, int nr, double
 // Every CTA of a kernel that needs alpha/beta: fold the pending reductions into the scalars
 // (redundantly, identical bits everywhere); CTA 0 persists the result in the other parity.
 __device__ __forceinline__ void dist_scalars(const Args& g, bool meurant, double& a, double& b) {
-  __shared__ Scal sh_sc;
+  __shared__ double sh_ab[2];
+  const bool stamp = (g.dbg & 2) && blockIdx.x == 0 && threadIdx.x == 0;
   if (threadIdx.x < 32) {
+    // Peer-to-peer records: every word of every pending record is requested FIRST (lane l: value
+    // l & 3 of rank l >> 2), then the persisted scalars are loaded, then the records are
+    // validated, summed in rank order and folded -- one memory round trip for the whole fold
+    // (the in-kernel time stamps showed 1.2-1.9 us per record when they were fetched in turn).
+    const bool ll = g.d.mode == 1 || g.d.mode == 3;
+    const int lane = threadIdx.x, r = lane >> 2, j = lane & 3;
+    const int only = g.d.mode == 3 ? g.d.rank : -1;
+    WinHdr* w = g.d.win[g.d.rank];
+    LLReq rq[3];
+    bool on[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      on[q] = ll && q < g.npend && r < g.d.world && j < fk_width(g.pend_kind[q]) && (only < 0 || r == only);
+      rq[q].src = w->ll[(int)(g.pend_e[q] % kSlots)][r < kMaxWorld ? r : 0] + 2 * j;
+      rq[q].lo = rq[q].hi = 0;
+      if (on[q]) ll_issue(rq[q]);
+    }
     Scal s = g.sc[g.scpar];
-    for (int q = 0; q < g.npend; ++q) {
-      double acc[kNRed];
-      dist_totals(g, g.pend_e[q], fk_width(g.pend_kind[q]), acc);
-      apply_finalize(g.pend_kind[q], meurant, &s, acc, g.pend_k[q]);
+    if (stamp) g.dbg_t[4] = (u64)clock64();
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (q < g.npend) {
+        double acc[kNRed];
+        if (ll) {
+          const double v = on[q] ? ll_finish(rq[q], g.pend_e[q], &w->error) : 0.0;
+#pragma unroll
+          for (int c = 0; c < kNRed; ++c) {
+            double t = 0.0;
+            for (int rr = 0; rr < g.d.world; ++rr) t += __shfl_sync(0xffffffffu, v, rr * 4 + c);
+            acc[c] = (only >= 0) ? t * (double)g.d.world : t;
+          }
+        } else {
+          dist_totals(g, g.pend_e[q], fk_width(g.pend_kind[q]), acc);
+        }
+        if (stamp) g.dbg_t[5 + 2 * q] = (u64)clock64();
+        apply_finalize(g.pend_kind[q], meurant, &s, acc, g.pend_k[q]);
+        if (stamp) g.dbg_t[6 + 2 * q] = (u64)clock64();
+      }
     }
     if (threadIdx.x == 0) {
-      sh_sc = s;
+      sh_ab[0] = s.a; sh_ab[1] = s.b;
       if (blockIdx.x == 0 && g.npend) g.sc[g.scpar ^ 1] = s;
     }
   }
+  if (stamp) g.dbg_t[9] = (u64)clock64();
   __syncthreads();
-  a = sh_sc.a; b = sh_sc.b;
+  a = sh_ab[0]; b = sh_ab[1];
 }
 
 // The SpMV-input vector a vector pass produces: also store its first / last plane into the
@@ -485,12 +521,20 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(const Args g) {
   const i64 nv = g.n >> 1;
   const i64 stride = (i64)gridDim.x * kBlock;
   double a, b;
+  const bool stamp = (g.dbg & 2) && blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamp) g.dbg_t[0] = (u64)clock64();
   if (dist) {
     const i64 rot0 = (g.hout_n > 0 && g.d.has_hi) ? nv - (g.d.plane >> 1) : 0;
     i64 i0 = (i64)blockIdx.x * kBlock + threadIdx.x;
-    if (i0 < nv) { i0 += rot0; if (i0 >= nv) i0 -= nv; ew_prefetch<KID, PM>(g, 2 * i0); }
+    const bool pf = i0 < nv;
+    if (pf) { i0 += rot0; if (i0 >= nv) i0 -= nv; }
+    // warps 1..7 prefetch while warp 0 folds the records (its own prefetch follows its loads, so
+    // the few record loads are not queued behind the prefetch burst)
+    if (pf && threadIdx.x >= 32) ew_prefetch<KID, PM>(g, 2 * i0);
     dist_scalars(g, MEURANT, a, b);
+    if (pf && threadIdx.x < 32) ew_prefetch<KID, PM>(g, 2 * i0);
   } else { a = g.sc->a; b = g.sc->b; }
+  if (stamp) g.dbg_t[1] = (u64)clock64();
   double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
   // Only the CTAs that stored boundary planes into a peer need a system-scope fence before
   // they take their ticket (a fence.sys in each of ~1200 CTAs costs tens of microseconds).
@@ -511,6 +555,7 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(const Args g) {
     peer = true;
   }
   const bool cta_peer = dist && g.hout_n > 0 && !g.halo_ll && __syncthreads_or(peer ? 1 : 0);
+  if (stamp) g.dbg_t[2] = (u64)clock64();
 
   constexpr int NR = EwTraits<KID>::NR;
   if constexpr (NR > 0) {
