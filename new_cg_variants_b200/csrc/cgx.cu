@@ -124,6 +124,7 @@ struct cgx_ctx {
   int dbg = 0;                     // option "debug_skip" (timing experiments only)
   u64* d_dbg_t = nullptr;          // 16 time stamps (dbg & 2)
   bool cg_elide = false;           // CG-CG: r~ / GV: w~ not stored (EW_*_E / SP_*_E)
+  bool one_wave = false;           // option "ew_one_wave": single-GPU vector passes also launch one resident wave
   int tma_min_planes = 4;          // option "tma_min_planes": planes per CTA the stencil grid aims for at least
   bool halo_ll = false;            // multi-GPU: the fused SpMV passes are TMA kernels -> LL ghost planes
   bool no_tma = false;             // cgx_set_option("tma", 0): force the generic stencil kernel
@@ -577,7 +578,16 @@ static void launch_ew(cgx_ctx* c, Args g) {
   p.hout_n = (KID == EW_HS1) ? 0 : (KID == EW_PIPE_R ? 2 : 1);
   plan_apply(c, g, p);
   {
-    const int grid = grid_for(c, (c->n + 1) / 2);
+    // One resident wave: on a partition every CTA folds the all-rank records before it streams
+    // (2-4 us); with 1184 CTAs at 3 resident per SM that prologue was paid by three successive
+    // waves (+10 us per launch, found with the in-kernel clock stamps).  Grid-stride covers the rows.
+    static int per_sm = 0;
+    if (!per_sm) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ew_kernel<KID, PM, MEUR>, kBlock, 0);
+      if (per_sm < 1) per_sm = 1;
+    }
+    int grid = grid_for(c, (c->n + 1) / 2);
+    if (c->dist.world > 1 || c->one_wave) grid = std::min(grid, per_sm * c->sm_count);
     ProfScope ps(c, PC_EW0 + (KID == EW_CG_E ? (int)EW_CG : KID == EW_GV_E ? (int)EW_GV : KID));
     ew_kernel<KID, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(g);
     c->launches++;
@@ -1334,6 +1344,7 @@ extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
   if (!strcmp(name, "pers_ctas")) { c->pers_ctas = value; return CGX_OK; }
   if (!strcmp(name, "debug_skip")) { c->dbg = value; return CGX_OK; }
   if (!strcmp(name, "tma_min_planes")) { c->tma_min_planes = value; return CGX_OK; }
+  if (!strcmp(name, "ew_one_wave")) { c->one_wave = value != 0; return CGX_OK; }
   if (!strcmp(name, "stub_allreduce")) {
     // timing experiment (SURVEY.md section 8d "allreduce-hiding metric"): value != 0 replaces the
     // scalar exchange by a local stand-in; value == 0 restores the mode chosen at commit
