@@ -43,7 +43,7 @@ def _fingerprint() -> str:
     files.append(os.path.join(ROOT, "include", "cgx.h"))
     for path in files:
         with open(path, "rb") as fh:
-            h.update(path.encode())
+            h.update(os.path.basename(path).encode())      # (not the absolute path: the tree moves between boxes)
             h.update(fh.read())
     return h.hexdigest()
 
