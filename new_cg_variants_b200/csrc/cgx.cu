@@ -587,7 +587,9 @@ static void launch_ew(cgx_ctx* c, Args g) {
       if (per_sm < 1) per_sm = 1;
     }
     int grid = grid_for(c, (c->n + 1) / 2);
-    if (c->dist.world > 1 || c->one_wave) grid = std::min(grid, per_sm * c->sm_count);
+    // (one GPU: measured neutral to slightly negative for the long passes, -4 % per iteration
+    // for HS-CG's two short ones -- tools/onewave_probe.py)
+    if (c->dist.world > 1 || c->one_wave || KID == EW_HS1 || KID == EW_HS2) grid = std::min(grid, per_sm * c->sm_count);
     ProfScope ps(c, PC_EW0 + (KID == EW_CG_E ? (int)EW_CG : KID == EW_GV_E ? (int)EW_GV : KID));
     ew_kernel<KID, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(g);
     c->launches++;
