@@ -2,7 +2,7 @@
 """bench.py -- headline benchmark of the B200 CG path (contract: see DESIGN.md "Measurement").
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--variant pr] [--grid 256] [--iters 200]
+                    [--variant pr] [--grid 256] [--dim 3] [--iters 200]
 
 Workload (BASELINE.json configs[3], the one the metric is quoted on): 3-D Poisson 7-point,
 256^3 grid (16.8 M unknowns), Jacobi-preconditioned, x_true = 1/sqrt(n), b = A x_true,
@@ -13,7 +13,8 @@ included).  N GPUs shard the grid into z-slabs (strong scaling, one problem).
            launch stream (max over ranks), instrumentation off (the reference's
            callbacks=[] timing protocol)
   e2e    : the same through the C-ABI call with HOST buffers (cgx_solve_host): pinned
-           b/x0 copied in, x copied out, inside the timed region (wall clock + sync)
+           b/x0 copied in, x copied out (into a pinned buffer), inside the timed region
+           (wall clock + sync)
   roofline / cpu_baseline : see DESIGN.md
 """
 from __future__ import annotations
