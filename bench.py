@@ -39,7 +39,8 @@ W_V = {"hs": 13, "cg": 14, "pr": 14, "m": 14, "gv": 21, "pipe_pr": 23, "pipe_p":
 # more when a Jacobi vector is read) -- DESIGN.md "Kernels"
 CLASS_WORDS = {"ew_hs1": (3, 1), "ew_hs2": (5, 1), "ew_cg": (11, 1), "ew_gv": (19, 1), "ew_pr": (9, 1),
                "ew_pipe_r": (14, 1), "ew_pipe_n": (18, 1), "sp_hs": (2, 0), "sp_cg": (3, 0), "sp_gv": (2, 0),
-               "sp_pr": (3, 1), "sp_pipe_r": (4, 0), "sp_pipe_n": (2, 0)}
+               "sp_pr": (3, 1), "sp_pipe_r": (4, 0), "sp_pipe_n": (2, 0),
+               "pr_fused": (10, 0)}        # one launch per PR-CG iteration: R x,r,p,s,rt  W x,r,p,s,rt
 # with a constant Jacobi diagonal (or none) on the TMA stencil path CG-CG does not stream r~ and
 # GV does not stream w~ (DESIGN.md "Kernels"): their kernels then move fewer words
 CLASS_WORDS_ELIDED = {"ew_cg": (9, 0), "sp_cg": (2, 0), "ew_gv": (17, 0)}

@@ -12,6 +12,7 @@ import os
 import shutil
 import subprocess
 import sys
+import time
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
@@ -19,13 +20,27 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcgx_b200.so")
 STAMP = LIB_PATH + ".stamp"
 
-SOURCES = ["cgx.cu"]
+OBJ_DIR = os.path.join(PKG_DIR, "_obj")
+
+# translation units: (object name, source, extra defines).  The stage launchers are compiled once
+# per preconditioner mode and the persistent kernels once per operator kind, only so that the
+# template instantiations build in parallel (one nvcc process per unit).
+UNITS = [
+    ("cgx_iter_pm0", "cgx_iter.cu", ["-DCGX_PM=0"]),
+    ("cgx_iter_pm1", "cgx_iter.cu", ["-DCGX_PM=1"]),
+    ("cgx_iter_pm2", "cgx_iter.cu", ["-DCGX_PM=2"]),
+    *[(f"cgx_pers_{nm}_pm{pm}", "cgx_pers.cu", [f"-DCGX_PERS_OP={op}", f"-DCGX_PERS_PM={pm}"])
+      for op, nm in ((2, "sten"), (1, "csr")) for pm in (0, 1, 2)],
+    ("cgx_fused", "cgx_fused.cu", []),
+    ("cgx", "cgx.cu", []),
+]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr", "--extended-lambda",
     "-Xptxas", "-v",
+    "-Xfatbin", "-compress-all",
 ]
 
 
@@ -39,6 +54,7 @@ def _nvcc() -> str:
 def _fingerprint() -> str:
     h = hashlib.sha256()
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(repr(UNITS).encode())
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
     files.append(os.path.join(ROOT, "include", "cgx.h"))
     for path in files:
@@ -53,14 +69,52 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP):
         if open(STAMP).read().strip() == fp:
             return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", LIB_PATH,
-           *[os.path.join(CSRC, s) for s in SOURCES]]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    log = proc.stdout + proc.stderr
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = _nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+
+    def compile_unit(unit):
+        name, source, defs = unit
+        obj = os.path.join(OBJ_DIR, name + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *defs, "-I", os.path.join(ROOT, "include"), "-c", "-o", obj,
+               os.path.join(CSRC, source)]
+        # incremental rebuilds: an object is reused when the PREPROCESSED unit is unchanged
+        pre = subprocess.run([nvcc, "-E", "-std=c++17", "--expt-relaxed-constexpr", "--extended-lambda",
+                              "-gencode", "arch=compute_100a,code=sm_100a", *defs,
+                              "-I", os.path.join(ROOT, "include"), os.path.join(CSRC, source)],
+                             capture_output=True, text=True)
+        key = hashlib.sha256((" ".join(cmd[1:]) + pre.stdout).encode()).hexdigest() if pre.returncode == 0 else None
+        keyfile = obj + ".key"
+        if (not force and key and os.path.exists(obj) and os.path.exists(keyfile)
+                and open(keyfile).read() == key):
+            old = open(obj + ".log").read() if os.path.exists(obj + ".log") else ""
+            return obj, old + f"[{name}: up to date]\n", 0
+        if os.path.exists(keyfile):
+            os.unlink(keyfile)
+        t0 = time.time()
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode == 0 and key:
+            with open(keyfile, "w") as fh:
+                fh.write(key)
+            with open(obj + ".log", "w") as fh:
+                fh.write(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        return obj, " ".join(cmd) + "\n" + proc.stdout + proc.stderr + f"\n[{name}: {time.time() - t0:.0f} s]\n", proc.returncode
+
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_unit, UNITS))
+    log = "\n".join(r[1] for r in results)
+    failed = [r for r in results if r[2] != 0]
+    if not failed:
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
+               "-o", LIB_PATH, *[r[0] for r in results]]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        log += "\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr
+        if proc.returncode != 0:
+            failed = [(LIB_PATH, proc.stdout + proc.stderr, proc.returncode)]
     with open(os.path.join(PKG_DIR, "build.log"), "w") as fh:
-        fh.write(" ".join(cmd) + "\n" + log)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + log[-6000:])
+        fh.write(log)
+    if failed:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(f[1][-6000:] for f in failed))
     if verbose:
         print(log)
     with open(STAMP, "w") as fh:

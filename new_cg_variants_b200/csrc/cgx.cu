@@ -1,25 +1,8 @@
 // cgx.cu -- host side of libcgx_b200.so: context, device memory, the native iteration
 // loop and the C ABI of include/cgx.h.  No torch, no cuBLAS/cuSPARSE, no CPU fallback.
-#include <cuda_runtime.h>
-
 #include <dlfcn.h>
 
-#include <algorithm>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <functional>
-#include <string>
-#include <type_traits>
-#include <vector>
-
-#include "../../include/cgx.h"
-#include "cgx_kernels.cuh"
-#include "cgx_stencil_tma.cuh"
-#include "cgx_persistent.cuh"
-
-using namespace cgx;
+#include "cgx_launch.cuh"
 
 // cuTensorMapEncodeTiled is resolved through the runtime so the library has no link-time
 // dependency on libcuda (it must load on the GPU-less build box for the ABI tests).
@@ -44,7 +27,8 @@ static EncodeTiledFn get_encode_tiled() {
 // ---------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 
-static int fail(int code, const char* fmt, ...) {
+
+int cgx_fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -54,28 +38,11 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-#define CU(call)                                                                        \
-  do {                                                                                  \
-    cudaError_t e_ = (call);                                                            \
-    if (e_ != cudaSuccess)                                                              \
-      return fail(CGX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
-                  __FILE__, __LINE__);                                                  \
-  } while (0)
-
 // ---------------------------------------------------------------------------------------
 // NCCL (mode 2 of the scalar exchange) -- resolved with dlopen from the library the caller
 // names (torch's bundled libnccl.so.2); the .so itself does not link NCCL.
 // ---------------------------------------------------------------------------------------
-struct Nid { char b[128]; };        // ncclUniqueId (passed by value)
-struct NcclApi {
-  void* h = nullptr;
-  int (*GetUniqueId)(void*) = nullptr;
-  int (*CommInitRank)(void**, int, Nid, int) = nullptr;
-  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
-  int (*CommDestroy)(void*) = nullptr;
-  const char* (*GetErrorString)(int) = nullptr;
-};
-static NcclApi g_nccl;
+NcclApi g_nccl;
 static int nccl_load(const char* path) {
   if (g_nccl.h) return CGX_OK;
   void* h = dlopen(path && *path ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
@@ -91,110 +58,7 @@ static int nccl_load(const char* path) {
   return CGX_OK;
 }
 
-// ---------------------------------------------------------------------------------------
-// context
-// ---------------------------------------------------------------------------------------
-enum { V_X = 0, V_R, V_RT, V_P, V_S, V_ST, V_W, V_WT, V_U, V_T, V_COUNT };
-static const char* kVecNames[V_COUNT] = {"x", "r", "rt", "p", "s", "st", "w", "wt", "u", "t"};
-
-struct cgx_ctx {
-  int device = 0;
-  int sm_count = 148;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-  // operator
-  int op_kind = 0;  // 0 none, 1 csr, 2 stencil
-  CsrOp csr{};
-  StencilOp sten{};
-  int* d_ptr = nullptr;
-  int* d_idx = nullptr;
-  double* d_val = nullptr;
-  std::vector<int> h_ptr;          // host copy of indptr (persistent kernel: shared-memory slab sizing)
-  bool no_elide = false;           // cgx_set_option("cg_elide", 0)
-  bool no_slab = false;            // cgx_set_option("csr_slab", 0)
-  int* d_rowblk = nullptr;         // CSR-stream row blocks (cgx_kernels.cuh)
-  int n_rowblk = 0;
-  i64 n = 0, nnz = 0;
-  // preconditioner: pm = 0 identity, 1 Jacobi vector, 2 Jacobi with a constant diagonal
-  double* d_dinv = nullptr;
-  double dinv_s = 1.0;
-  int pm = 0;
-  // TMA-staged stencil path
-  bool use_tma = false;
-  int dbg = 0;                     // option "debug_skip" (timing experiments only)
-  u64* d_dbg_t = nullptr;          // 16 time stamps (dbg & 2)
-  bool cg_elide = false;           // CG-CG: r~ / GV: w~ not stored (EW_*_E / SP_*_E)
-  bool one_wave = false;           // option "ew_one_wave": single-GPU vector passes also launch one resident wave
-  int tma_min_planes = 4;          // option "tma_min_planes": planes per CTA the stencil grid aims for at least
-  bool halo_ll = false;            // multi-GPU: the fused SpMV passes are TMA kernels -> LL ghost planes
-  bool no_tma = false;             // cgx_set_option("tma", 0): force the generic stencil kernel
-  bool no_csr_stream = false;      // cgx_set_option("csr_stream", 0): one thread per row
-  TmaGeom geom{};
-  int tma_grid[2] = {0, 0};        // grid size for 1 / 2 right-hand sides
-  CUtensorMap tmap[10];
-  bool tmap_ok[10] = {};
-  // problem
-  double* d_b = nullptr;
-  double* d_x0 = nullptr;
-  double* d_xtrue = nullptr;
-  bool own_problem = false, has_xtrue = false, problem_loaded = false;
-  // state
-  double* vec[V_COUNT] = {};
-  Scal* d_sc = nullptr;            // [2]: multi-GPU runs alternate (Args::scpar)
-  double* d_partials = nullptr;
-  unsigned* d_ticket = nullptr;
-  double* d_hist = nullptr;
-  int hist_len = 0;
-  unsigned hist_mask = 0;
-  bool ran = false;
-  i64 launches = 0;
-  // per-kernel-class profiling
-  bool profile = false;
-  std::vector<cudaEvent_t> prof_events;
-  std::vector<int> prof_cls;
-  size_t prof_used = 0;
-  double prof_ms[16] = {};
-  i64 prof_n[16] = {};
-  // multi-GPU (dist.world > 1): window, peers, epochs (cgx_common.cuh "Row-partitioned ...")
-  Dist dist{};
-  unsigned char* d_win = nullptr;
-  size_t win_bytes = 0;
-  unsigned char* peer_base[kMaxWorld] = {};
-  bool peer_ipc[kMaxWorld] = {};
-  bool dist_ready = false;
-  cudaStream_t own_stream = nullptr;      // c->stream may be a group's shared stream
-  u64 epoch = 0;                           // last scalar-exchange epoch produced
-  u64 hepoch[kChan] = {};                  // last halo epoch produced per channel
-  int scpar = 0;
-  struct Pend { u64 e; int kind; int k; };
-  std::vector<Pend> pend;
-  // mode 2: NCCL allreduce of the records on a side stream
-  void* nccl_comm = nullptr;
-  cudaStream_t comm_stream = nullptr;
-  cudaEvent_t ev_prod[kSlots] = {}, ev_red[kSlots] = {};
-  double* d_nccl = nullptr;                // [2][kSlots][kSumW]: in, out
-  // persistent path
-  double* d_ppart = nullptr;               // [2][kPersMaxGrid][kPersRed]
-  u64* d_pbar = nullptr;                   // sync-point counter
-  PersOut* d_pout = nullptr;
-  void* d_prank = nullptr;                 // PersRank<Op>[kMaxWorld] (rank 0 of a group holds all)
-  double* d_exp[2][2] = {};                // exported SpMV inputs [parity][rhs]
-  int pers_threshold = 1 << 19;            // AUTO: rows below which the persistent kernel runs
-  int pers_threads = 0, pers_ctas = 0;     // 0 = choose (options "pers_threads", "pers_ctas")
-  // current run
-  int variant = 0, max_iter = 0, cur_k = 0, path = CGX_PATH_STREAM;
-  i64 launches_run = 0;
-  double setup_ms = 0.0, loop_ms = 0.0;
-};
-
-static int grid_for(const cgx_ctx* c, i64 work_items) {
-  i64 g = (work_items + kBlock - 1) / kBlock;
-  i64 cap = (i64)c->sm_count * 8;   // 8 resident CTAs of 256 threads per SM
-  if (cap > kMaxGrid) cap = kMaxGrid;
-  if (g > cap) g = cap;
-  if (g < 1) g = 1;
-  return (int)g;
-}
+const char* const kVecNames[V_COUNT] = {"x", "r", "rt", "p", "s", "st", "w", "wt", "u", "t"};
 
 static void free_op(cgx_ctx* c) {
   cudaFree(c->d_ptr); cudaFree(c->d_idx); cudaFree(c->d_val); cudaFree(c->d_rowblk);
@@ -210,6 +74,7 @@ static void free_problem(cgx_ctx* c) {
 }
 static void free_state(cgx_ctx* c) {
   for (int i = 0; i < V_COUNT; ++i) { cudaFree(c->vec[i]); c->vec[i] = nullptr; }
+  for (auto& q : c->alt) { cudaFree(q); q = nullptr; }
   for (auto& pp : c->d_exp) for (auto& q : pp) { cudaFree(q); q = nullptr; }
   cudaFree(c->d_hist); c->d_hist = nullptr; c->hist_len = 0;
   c->ran = false;
@@ -255,6 +120,8 @@ extern "C" int cgx_ctx_create(int device, cgx_ctx** out) {
   CU(cudaMalloc(&c->d_ppart, sizeof(double) * 2 * kPersMaxGrid * kPersRed));
   CU(cudaMalloc(&c->d_pbar, sizeof(u64) * 2));
   CU(cudaMemset(c->d_pbar, 0, sizeof(u64) * 2));
+  CU(cudaMalloc(&c->d_tma_err, sizeof(int)));
+  CU(cudaMemset(c->d_tma_err, 0, sizeof(int)));
   CU(cudaMalloc(&c->d_dbg_t, sizeof(u64) * 16));
   CU(cudaMemset(c->d_dbg_t, 0, sizeof(u64) * 16));
   CU(cudaMalloc(&c->d_pout, sizeof(PersOut)));
@@ -289,7 +156,7 @@ extern "C" int cgx_ctx_destroy(cgx_ctx* c) {
   dist_release(c);
   free_state(c); free_problem(c); free_op(c);
   cudaFree(c->d_dinv); cudaFree(c->d_sc); cudaFree(c->d_partials); cudaFree(c->d_ticket);
-  cudaFree(c->d_ppart); cudaFree(c->d_pbar); cudaFree(c->d_pout); cudaFree(c->d_prank); cudaFree(c->d_dbg_t);
+  cudaFree(c->d_ppart); cudaFree(c->d_pbar); cudaFree(c->d_pout); cudaFree(c->d_prank); cudaFree(c->d_dbg_t); cudaFree(c->d_tma_err);
   for (auto& e : c->ev) cudaEventDestroy(e);
   for (auto& e : c->prof_events) cudaEventDestroy(e);
   cudaStreamDestroy(c->own_stream);
@@ -390,30 +257,10 @@ extern "C" int cgx_set_jacobi_host(cgx_ctx* c, const double* dinv, int64_t n) {
   return CGX_OK;
 }
 
-// ---------------------------------------------------------------------------------------
-// launch bookkeeping
-// ---------------------------------------------------------------------------------------
-// Optional per-kernel-class timing (cgx_set_profile): an event pair around every launch of
-// the iteration loop, resolved after the stream has drained.  Off in timed runs.
-enum { PC_EW0 = 0, PC_SP0 = 7, PC_INSTR = 15, PC_COUNT = 16 };
 static const char* kClassNames[PC_COUNT] = {
     "ew_hs1", "ew_hs2", "ew_cg", "ew_gv", "ew_pr", "ew_pipe_r", "ew_pipe_n",
     "sp_plain", "sp_hs", "sp_cg", "sp_gv", "sp_pr", "sp_pipe_r", "sp_pipe_n", "sp_resid",
-    "instrument"};
-
-struct ProfScope {
-  cgx_ctx* c; int cls; size_t slot = 0; bool on;
-  ProfScope(cgx_ctx* c_, int cls_) : c(c_), cls(cls_), on(c_->profile) {
-    if (!on) return;
-    if (c->prof_used + 2 > c->prof_events.size()) {
-      for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); c->prof_events.push_back(e); }
-    }
-    slot = c->prof_used; c->prof_used += 2;
-    c->prof_cls.push_back(cls);
-    cudaEventRecord(c->prof_events[slot], c->stream);
-  }
-  ~ProfScope() { if (on) cudaEventRecord(c->prof_events[slot + 1], c->stream); }
-};
+    "instrument", "pr_fused"};
 static void prof_resolve(cgx_ctx* c) {
   for (size_t i = 0; i < c->prof_cls.size(); ++i) {
     float ms = 0.f;
@@ -424,7 +271,7 @@ static void prof_resolve(cgx_ctx* c) {
   c->prof_cls.clear(); c->prof_used = 0;
 }
 
-static Args make_args(cgx_ctx* c) {
+Args make_args(cgx_ctx* c) {
   Args g{};
   g.x = c->vec[V_X]; g.r = c->vec[V_R]; g.rt = c->vec[V_RT]; g.p = c->vec[V_P];
   g.s = c->vec[V_S]; g.st = c->vec[V_ST]; g.w = c->vec[V_W]; g.wt = c->vec[V_WT];
@@ -440,18 +287,10 @@ static Args make_args(cgx_ctx* c) {
   return g;
 }
 
-// What one launch does in the multi-GPU protocol (cgx_common.cuh "Row-partitioned ..."):
-struct Plan {
-  bool consume = false;      // needs alpha/beta: folds every pending reduction into the scalars
-  int produce = FK_NONE;     // publishes a reduction record of this kind (FK_*; -1: instrumentation)
-  int hout_n = 0, hout_ch = 0;   // writes boundary planes of `hout_n` SpMV inputs into the neighbours
-  int hin_n = 0, hin_ch = 0;     // reads ghost planes
-};
-enum { FK_INSTR = 100 };
 
 // before the launch: fill the per-launch fields of g; mode 2: make the stream wait for the
 // NCCL reductions this kernel folds
-static void plan_apply(cgx_ctx* c, Args& g, const Plan& p) {
+void plan_apply(cgx_ctx* c, Args& g, const Plan& p) {
   if (c->dist.world <= 1) return;
   g.d = c->dist;
   g.scpar = c->scpar;
@@ -478,7 +317,7 @@ static void plan_apply(cgx_ctx* c, Args& g, const Plan& p) {
   g.xt_par = (int)(g.xt_epoch & 1);
 }
 // after the launch: advance the epochs; mode 2: enqueue the allreduce of the new record
-static void plan_commit(cgx_ctx* c, const Args& g, const Plan& p) {
+void plan_commit(cgx_ctx* c, const Args& g, const Plan& p) {
   if (c->dist.world <= 1) return;
   if (p.consume && !c->pend.empty()) { c->scpar ^= 1; c->pend.clear(); }
   if (p.produce != FK_NONE) {
@@ -496,7 +335,7 @@ static void plan_commit(cgx_ctx* c, const Args& g, const Plan& p) {
   for (int i = 0; i < p.hout_n; ++i) c->hepoch[p.hout_ch + i]++;
 }
 
-static VecIn vec_in(cgx_ctx* c, const double* v, int ch, const Args& g) {
+VecIn vec_in(cgx_ctx* c, const double* v, int ch, const Args& g) {
   VecIn a{v, nullptr, nullptr};
   if (c->dist.world > 1 && c->dist.ghost) {
     a.lo = c->dist.ghost + ghost_off(c->dist, ch, g.hin_par, 0);
@@ -505,100 +344,21 @@ static VecIn vec_in(cgx_ctx* c, const double* v, int ch, const Args& g) {
   return a;
 }
 
-// which state vector a fused SpMV pass reads (second one for the 2-RHS pass)
-template <int MODE> struct SpInput { static constexpr int v0 = -1, v1 = -1; };
-template <> struct SpInput<SP_HS> { static constexpr int v0 = V_P, v1 = -1; };
-template <> struct SpInput<SP_PR> { static constexpr int v0 = V_P, v1 = -1; };
-template <> struct SpInput<SP_CG> { static constexpr int v0 = V_RT, v1 = -1; };
-template <> struct SpInput<SP_CG_E> { static constexpr int v0 = V_R, v1 = -1; };
-template <> struct SpInput<SP_GV_E> { static constexpr int v0 = V_W, v1 = -1; };
-template <> struct SpInput<SP_GV> { static constexpr int v0 = V_WT, v1 = -1; };
-template <> struct SpInput<SP_PIPE_R> { static constexpr int v0 = V_ST, v1 = V_RT; };
-template <> struct SpInput<SP_PIPE_N> { static constexpr int v0 = V_ST, v1 = -1; };
 
-static size_t tma_smem_bytes(int nv) { return (size_t)kRing * nv * kPlaneStride * sizeof(double) + 128; }
-
-// Fused SpMV pass of stage MODE (vin/vout only for SP_PLAIN / SP_RESID).
-template <int MODE, int PM, bool MEUR>
-static void launch_spmv(cgx_ctx* c, Args g, const double* vin, double* vout) {
-  constexpr int v0 = SpInput<MODE>::v0, v1 = SpInput<MODE>::v1;
-  constexpr int nv = (v1 >= 0) ? 2 : 1;
-  Plan p;
-  p.produce = SpTraits<MODE>::FK;
-  p.hin_n = nv; p.hin_ch = 0;
-  plan_apply(c, g, p);
-  {
-    ProfScope ps(c, PC_SP0 + (MODE == SP_CG_E ? (int)SP_CG : MODE == SP_GV_E ? (int)SP_GV : MODE));
-    bool done = false;
-    if constexpr (v0 >= 0) {
-      if (c->op_kind == 2 && c->use_tma && c->tmap_ok[v0] && (v1 < 0 || c->tmap_ok[v1 < 0 ? 0 : v1])) {
-        // grid = the CTAs that are actually co-resident (one wave): the kernel splits the work
-        // evenly over gridDim.x, so a partial second wave would cost a full extra pass
-        static int per_sm = 0;
-        if (!per_sm) {
-          cudaFuncSetAttribute(stencil_tma_kernel<MODE, PM, MEUR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)tma_smem_bytes(nv));
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stencil_tma_kernel<MODE, PM, MEUR>, kTmaThreads,
-                                                        tma_smem_bytes(nv));
-          if (per_sm < 1) per_sm = 1;
-        }
-        const int tgrid = std::min(c->tma_grid[nv - 1], per_sm * c->sm_count);
-        stencil_tma_kernel<MODE, PM, MEUR><<<tgrid, kTmaThreads, tma_smem_bytes(nv), c->stream>>>(
-            c->tmap[v0], c->tmap[v1 < 0 ? v0 : v1], c->geom, g);
-        done = true;
-      }
-    }
-    if (!done) {
-      const double* a0 = v0 >= 0 ? c->vec[v0 < 0 ? 0 : v0] : vin;
-      const double* a1 = v1 >= 0 ? c->vec[v1 < 0 ? 0 : v1] : nullptr;
-      const VecIn in0 = vec_in(c, a0, 0, g), in1 = vec_in(c, a1, 1, g);
-      if (c->op_kind == 1) {
-        if (!c->no_csr_stream) {
-          const int grid = std::max(1, std::min(c->n_rowblk, c->sm_count * 8));
-          csr_stream_kernel<MODE, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(c->csr, c->d_rowblk, c->n_rowblk, g,
-                                                                           in0, in1, vout);
-        } else {
-          spmv_kernel<CsrOp, MODE, PM, MEUR><<<grid_for(c, c->n), kBlock, 0, c->stream>>>(c->csr, g, in0, in1, vout);
-        }
-      } else {
-        spmv_kernel<StencilOp, MODE, PM, MEUR><<<grid_for(c, c->n), kBlock, 0, c->stream>>>(c->sten, g, in0, in1, vout);
-      }
-    }
-    c->launches++;
-  }
-  plan_commit(c, g, p);
+int ctx_occupancy(cgx_ctx* c, const void* fn, int threads, size_t smem) {
+  auto it = c->occ.find({fn, smem});
+  if (it != c->occ.end()) return it->second;
+  int per_sm = 0;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+  if (per_sm < 1) per_sm = 1;
+  c->occ[{fn, smem}] = per_sm;
+  return per_sm;
 }
 
-template <int KID, int PM, bool MEUR>
-static void launch_ew(cgx_ctx* c, Args g) {
-  Plan p;
-  p.consume = true;
-  p.produce = EwKind<KID>::FK;
-  p.hout_ch = 0;
-  p.hout_n = (KID == EW_HS1) ? 0 : (KID == EW_PIPE_R ? 2 : 1);
-  plan_apply(c, g, p);
-  {
-    // One resident wave: on a partition every CTA folds the all-rank records before it streams
-    // (2-4 us); with 1184 CTAs at 3 resident per SM that prologue was paid by three successive
-    // waves (+10 us per launch, found with the in-kernel clock stamps).  Grid-stride covers the rows.
-    static int per_sm = 0;
-    if (!per_sm) {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ew_kernel<KID, PM, MEUR>, kBlock, 0);
-      if (per_sm < 1) per_sm = 1;
-    }
-    int grid = grid_for(c, (c->n + 1) / 2);
-    // (one GPU: measured neutral to slightly negative for the long passes, -4 % per iteration
-    // for HS-CG's two short ones -- tools/onewave_probe.py)
-    if (c->dist.world > 1 || c->one_wave || KID == EW_HS1 || KID == EW_HS2) grid = std::min(grid, per_sm * c->sm_count);
-    ProfScope ps(c, PC_EW0 + (KID == EW_CG_E ? (int)EW_CG : KID == EW_GV_E ? (int)EW_GV : KID));
-    ew_kernel<KID, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(g);
-    c->launches++;
-  }
-  plan_commit(c, g, p);
-}
 
 // multi-GPU: push the boundary planes of v into the neighbours' ghost planes of channel ch
-static void launch_halo_push(cgx_ctx* c, Args g, const double* v, int ch) {
+void launch_halo_push(cgx_ctx* c, Args g, const double* v, int ch) {
   if (c->dist.world <= 1) return;
   Plan p;
   p.hout_n = 1; p.hout_ch = ch;
@@ -610,7 +370,7 @@ static void launch_halo_push(cgx_ctx* c, Args g, const double* v, int ch) {
 }
 
 // ---- TMA stencil path: descriptors and work decomposition -------------------------------
-static bool tma_encode_dims(double* ptr, i64 nx, i64 ny, i64 nz, CUtensorMap* out) {
+bool tma_encode_dims(double* ptr, i64 nx, i64 ny, i64 nz, CUtensorMap* out) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc || !ptr) return false;
   cuuint64_t gdim[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
@@ -633,6 +393,7 @@ static bool tma_prepare_geom(cgx_ctx* c) {
   G.ntx = (S.nx + kTX - 1) / kTX; G.nty = (S.ny + kTY - 1) / kTY;
   G.has_zlo = S.has_zlo; G.has_zhi = S.has_zhi;
   G.diag = S.diag; G.off = S.off;
+  G.err = c->d_tma_err;
   G.march_y = 0;
   if (S.nz == 1 && !S.has_zlo && !S.has_zhi && G.nty > 1) {   // 2-D: march down the y-tiles of a column
     G.march_y = 1;
@@ -674,7 +435,7 @@ static int setup_tma(cgx_ctx* c, unsigned need) {
   return CGX_OK;
 }
 
-static void launch_instrument(cgx_ctx* c, Args g) {
+void launch_instrument(cgx_ctx* c, Args g) {
   const int grid = grid_for(c, c->n);
   Plan p;
   p.produce = FK_INSTR;
@@ -700,7 +461,7 @@ static void launch_instrument(cgx_ctx* c, Args g) {
   plan_commit(c, g, p);
 }
 // multi-GPU: the history entry of the instrumentation record just produced
-static void launch_hist_consume(cgx_ctx* c, Args g) {
+void launch_hist_consume(cgx_ctx* c, Args g) {
   if (c->dist.world <= 1) return;
   g.d = c->dist;
   g.pend_e[0] = c->epoch;
@@ -718,12 +479,7 @@ static void launch_scale(cgx_ctx* c, const double* dinv, const double* v, double
   c->launches++;
 }
 
-struct VariantInfo {
-  bool meurant, pipe, recompute;
-  int cls;                 // init_scalars class
-  unsigned need;           // bitmask of state vectors
-};
-static VariantInfo variant_info(int v, bool prec) {
+VariantInfo variant_info(int v, bool prec) {
   auto bit = [](int i) { return 1u << i; };
   const unsigned base = bit(V_X) | bit(V_R) | bit(V_RT) | bit(V_P) | bit(V_S);
   switch (v) {
@@ -746,73 +502,16 @@ static VariantInfo variant_info(int v, bool prec) {
 // from one host thread (cgx_group_*), or every rank from its own process.
 // ---------------------------------------------------------------------------------------
 static int iter_stage_count(const cgx_ctx* c) {
-  int ns = (c->variant == CGX_HS) ? 3 : 2;
+  int ns = core_stages(c);
   if (c->hist_mask) ns += (c->dist.world > 1) ? 3 : 1;
   return ns;
 }
 
-template <int PM>
-static void iter_stage_pm(cgx_ctx* c, int s, const Args& g) {
-  const int core = (c->variant == CGX_HS) ? 3 : 2;
-  if (s >= core) {
-    const int t = s - core;
-    if (c->dist.world > 1) {
-      if (t == 0) launch_halo_push(c, g, c->vec[V_X], 2);
-      else if (t == 1) launch_instrument(c, g);
-      else launch_hist_consume(c, g);
-    } else {
-      launch_instrument(c, g);
-    }
-    return;
-  }
-  switch (c->variant) {
-    case CGX_HS:
-      if (s == 0) launch_ew<EW_HS1, PM, false>(c, g);
-      else if (s == 1) launch_ew<EW_HS2, PM, false>(c, g);
-      else launch_spmv<SP_HS, PM, false>(c, g, nullptr, nullptr);
-      break;
-    case CGX_CG:
-      if constexpr (PM != 1) {
-        if (c->cg_elide) {
-          if (s == 0) launch_ew<EW_CG_E, PM, false>(c, g); else launch_spmv<SP_CG_E, PM, false>(c, g, nullptr, nullptr);
-          break;
-        }
-      }
-      if (s == 0) launch_ew<EW_CG, PM, false>(c, g); else launch_spmv<SP_CG, PM, false>(c, g, nullptr, nullptr);
-      break;
-    case CGX_GV:
-      if constexpr (PM != 1) {
-        if (c->cg_elide) {
-          if (s == 0) launch_ew<EW_GV_E, PM, false>(c, g); else launch_spmv<SP_GV_E, PM, false>(c, g, nullptr, nullptr);
-          break;
-        }
-      }
-      if (s == 0) launch_ew<EW_GV, PM, false>(c, g); else launch_spmv<SP_GV, PM, false>(c, g, nullptr, nullptr);
-      break;
-    case CGX_PR:
-      if (s == 0) launch_ew<EW_PR, PM, false>(c, g); else launch_spmv<SP_PR, PM, false>(c, g, nullptr, nullptr);
-      break;
-    case CGX_M:
-      if (s == 0) launch_ew<EW_PR, PM, true>(c, g); else launch_spmv<SP_PR, PM, true>(c, g, nullptr, nullptr);
-      break;
-    case CGX_PIPE_PR:
-      if (s == 0) launch_ew<EW_PIPE_R, PM, false>(c, g); else launch_spmv<SP_PIPE_R, PM, false>(c, g, nullptr, nullptr);
-      break;
-    case CGX_PIPE_PR_M:
-      if (s == 0) launch_ew<EW_PIPE_R, PM, true>(c, g); else launch_spmv<SP_PIPE_R, PM, true>(c, g, nullptr, nullptr);
-      break;
-    case CGX_PIPE_P:
-      if (s == 0) launch_ew<EW_PIPE_N, PM, false>(c, g); else launch_spmv<SP_PIPE_N, PM, false>(c, g, nullptr, nullptr);
-      break;
-    case CGX_PIPE_P_M:
-      if (s == 0) launch_ew<EW_PIPE_N, PM, true>(c, g); else launch_spmv<SP_PIPE_N, PM, true>(c, g, nullptr, nullptr);
-      break;
-  }
-}
 static void iter_stage(cgx_ctx* c, int s, const Args& g) {
-  if (c->pm == 2) iter_stage_pm<2>(c, s, g);
-  else if (c->pm == 1) iter_stage_pm<1>(c, s, g);
-  else iter_stage_pm<0>(c, s, g);
+  if (c->pr_fused && s == 0) { cgx_launch_pr_fused(c, g); return; }
+  if (c->pm == 2) cgx_iter_stage_pm2(c, s, g);
+  else if (c->pm == 1) cgx_iter_stage_pm1(c, s, g);
+  else cgx_iter_stage_pm0(c, s, g);
 }
 
 // multi-GPU: fold what is still pending into the persisted scalars (end of an advance)
@@ -960,7 +659,6 @@ extern "C" int cgx_load_problem_dev(cgx_ctx* c, const double* b, const double* x
 // ---------------------------------------------------------------------------------------
 // persistent path (cgx_persistent.cuh): one cooperative launch runs every iteration
 // ---------------------------------------------------------------------------------------
-struct PersGeom { int T, nb, R, nslot, slab_cap; unsigned vmask; size_t smem; bool ok; };
 
 // CTA shape for n rows per rank with `ranks_in_launch` ranks sharing one GPU's SMs
 static PersGeom pers_geometry_T(const cgx_ctx* c, int variant, int ranks_in_launch, int T) {
@@ -1002,61 +700,16 @@ static PersGeom pers_geometry(const cgx_ctx* c, int variant, int ranks_in_launch
   return G;
 }
 
-template <class Op, int PM>
-static int pers_launch_pm(cgx_ctx** cs, int count, const PersGeom& G, int k0, int k1) {
-  cgx_ctx* c0 = cs[0];
-  std::vector<PersRank<Op>> h(count);
-  for (int i = 0; i < count; ++i) {
-    cgx_ctx* c = cs[i];
-    PersRank<Op>& r = h[i];
-    if constexpr (std::is_same<Op, CsrOp>::value) r.A = c->csr; else r.A = c->sten;
-    Args g = make_args(c);
-    Plan p;                                         // fills scpar / x_true epochs
-    plan_apply(c, g, p);
-    r.g = g;
-    for (int v = 0; v < V_COUNT; ++v) r.vecs[v] = c->vec[v];
-    r.vecs[10] = c->d_dinv; r.vecs[11] = nullptr;
-    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) r.exp_[a][b] = c->d_exp[a][b];
-    r.bar = c->d_pbar; r.part = c->d_ppart; r.out = c->d_pout;
-    r.epoch0 = c->epoch;
-    for (int ch = 0; ch < kChan; ++ch) r.hepoch0[ch] = c->hepoch[ch];
-    CU(cudaMemsetAsync(c->d_pbar, 0, sizeof(u64) * 2, c0->stream));
-    CU(cudaMemsetAsync(c->d_pout, 0, sizeof(PersOut), c0->stream));
-  }
-  CU(cudaMemcpyAsync(c0->d_prank, h.data(), sizeof(PersRank<Op>) * count, cudaMemcpyHostToDevice, c0->stream));
-  CU(cudaStreamSynchronize(c0->stream));           // h is a host temporary
-  PersLaunch L{};
-  L.k0 = k0; L.k1 = k1; L.nb = G.nb; L.R = G.R; L.vmask = G.vmask; L.nslot = G.nslot; L.slab_cap = G.slab_cap;
-  const PersRank<Op>* dr = static_cast<const PersRank<Op>*>(c0->d_prank);
-  void* params[] = {(void*)&dr, (void*)&L};
-  const void* fn = nullptr;
-#define CGX_PV(V) case V: fn = (const void*)persistent_kernel<Op, V, PM>; break;
-  switch (c0->variant) {
-    CGX_PV(CGX_HS) CGX_PV(CGX_CG) CGX_PV(CGX_GV) CGX_PV(CGX_PR) CGX_PV(CGX_M) CGX_PV(CGX_PIPE_PR)
-    CGX_PV(CGX_PIPE_P) CGX_PV(CGX_PIPE_PR_M) CGX_PV(CGX_PIPE_P_M)
-  }
-#undef CGX_PV
-  if (!fn) return fail(CGX_ERR_ARG, "persistent path: unknown variant");
-  CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
-  int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, G.T, G.smem));
-  if ((i64)per_sm * c0->sm_count < (i64)G.nb * count)
-    return fail(CGX_ERR_UNSUPPORTED, "persistent path: %d CTAs of %d threads / %zu B shared memory are not co-resident",
-                G.nb * count, G.T, G.smem);
-  CU(cudaLaunchCooperativeKernel(fn, dim3(G.nb * count), dim3(G.T), params, G.smem, c0->stream));
-  c0->launches++;
-  return CGX_OK;
-}
 static int pers_launch(cgx_ctx** cs, int count, const PersGeom& G, int k0, int k1) {
-  cgx_ctx* c = cs[0];
+  const cgx_ctx* c = cs[0];
   if (c->op_kind == 1) {
-    if (c->pm == 2) return pers_launch_pm<CsrOp, 2>(cs, count, G, k0, k1);
-    if (c->pm == 1) return pers_launch_pm<CsrOp, 1>(cs, count, G, k0, k1);
-    return pers_launch_pm<CsrOp, 0>(cs, count, G, k0, k1);
+    if (c->pm == 2) return cgx_pers_launch_csr_pm2(cs, count, G, k0, k1);
+    if (c->pm == 1) return cgx_pers_launch_csr_pm1(cs, count, G, k0, k1);
+    return cgx_pers_launch_csr_pm0(cs, count, G, k0, k1);
   }
-  if (c->pm == 2) return pers_launch_pm<StencilOp, 2>(cs, count, G, k0, k1);
-  if (c->pm == 1) return pers_launch_pm<StencilOp, 1>(cs, count, G, k0, k1);
-  return pers_launch_pm<StencilOp, 0>(cs, count, G, k0, k1);
+  if (c->pm == 2) return cgx_pers_launch_sten_pm2(cs, count, G, k0, k1);
+  if (c->pm == 1) return cgx_pers_launch_sten_pm1(cs, count, G, k0, k1);
+  return cgx_pers_launch_sten_pm0(cs, count, G, k0, k1);
 }
 // after the launch has drained: adopt the epoch counters the kernel advanced
 static int pers_collect(cgx_ctx* c) {
@@ -1123,6 +776,11 @@ static int begin_prepare(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
                 c->pm != 1 && !c->no_elide;
   c->launches_run = 0; c->loop_ms = 0.0;
   c->pend.clear();
+  c->pr_fused = false; c->fpar = 0;
+  if ((variant == CGX_PR || variant == CGX_M) && path == CGX_PATH_STREAM && !c->no_fused) {
+    int frc = cgx_fused_prepare(c);
+    if (frc) return frc;
+  }
   return CGX_OK;
 }
 
@@ -1142,7 +800,7 @@ static int begin_finish(cgx_ctx* c, i64 launches0) {
 static int check_device_flags(cgx_ctx* c, const char* who) {
   if (c->use_tma) {
     int flag = 0;
-    CU(cudaMemcpyFromSymbol(&flag, g_tma_timeout, sizeof(int)));
+    CU(cudaMemcpy(&flag, c->d_tma_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flag) return fail(CGX_ERR_CUDA, "%s: a TMA plane copy did not complete within 1 s", who);
   }
   if (c->dist.world > 1 && c->d_win) {
@@ -1180,7 +838,7 @@ static int group_begin(cgx_ctx** cs, int count, int variant, int max_iter, unsig
   // k = 0 entry of the histories (the reference's callbacks fire on the initial state)
   for (int i = 0; i < count; ++i) cs[i]->cur_k = 0;
   if (cs[0]->hist_mask) {
-    const int core = (variant == CGX_HS) ? 3 : 2;
+    const int core = core_stages(cs[0]);
     for (int s = core; s < iter_stage_count(cs[0]); ++s)
       for (int i = 0; i < count; ++i) {
         if (count > 1) cudaSetDevice(cs[i]->device);
@@ -1341,6 +999,8 @@ extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
   if (!strcmp(name, "csr_stream")) { c->no_csr_stream = (value == 0); return CGX_OK; }
   if (!strcmp(name, "csr_slab")) { c->no_slab = (value == 0); return CGX_OK; }
   if (!strcmp(name, "cg_elide")) { c->no_elide = (value == 0); return CGX_OK; }
+  if (!strcmp(name, "pr_fused")) { c->no_fused = (value == 0); return CGX_OK; }
+  if (!strcmp(name, "fused_min_planes")) { c->fused_min_planes = std::max(1, value); return CGX_OK; }
   if (!strcmp(name, "persistent_threshold")) { c->pers_threshold = value; return CGX_OK; }
   if (!strcmp(name, "pers_threads")) { c->pers_threads = value; return CGX_OK; }
   if (!strcmp(name, "pers_ctas")) { c->pers_ctas = value; return CGX_OK; }
@@ -1431,7 +1091,7 @@ extern "C" int cgx_fetch_vector_host(cgx_ctx* c, const char* name, double* out) 
         launch_scale(c, c->d_dinv, c->vec[i == V_RT ? V_R : V_W], c->vec[i]);
         CU(cudaStreamSynchronize(c->stream));
       }
-      CU(cudaMemcpy(out, c->vec[i], sizeof(double) * c->n, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(out, cgx_cur_vec(c, i), sizeof(double) * c->n, cudaMemcpyDeviceToHost));
       return CGX_OK;
     }
   return fail(CGX_ERR_ARG, "cgx_fetch_vector_host: unknown vector '%s'", name);
@@ -1587,8 +1247,7 @@ extern "C" int cgx_spmv_host(cgx_ctx* c, const double* v, double* y, int64_t n) 
   if (c->op_kind == 2 && tma_prepare_geom(c) && tma_encode_dims(dv, c->sten.nx, c->sten.ny, c->sten.nz, &tm)) {
     // the TMA-staged stencil kernel in its plainest mode (SP_PIPE_N: u = A v, no epilogue)
     g.u = dy;
-    CU(cudaFuncSetAttribute(stencil_tma_kernel<SP_PIPE_N, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)tma_smem_bytes(1)));
+    ctx_occupancy(c, (const void*)stencil_tma_kernel<SP_PIPE_N, 0, false>, kTmaThreads, tma_smem_bytes(1));
     stencil_tma_kernel<SP_PIPE_N, 0, false><<<c->tma_grid[0], kTmaThreads, tma_smem_bytes(1), c->stream>>>(
         tm, tm, c->geom, g);
     c->launches++;

@@ -100,7 +100,7 @@ template <int NR, class Fin>
 __device__ __forceinline__ void grid_sum_finalize(double (&v)[NR], double* __restrict__ partials,
                                                   unsigned* __restrict__ ticket, Fin fin,
                                                   bool sys = false) {
-  __shared__ double sh[NR * (kBlock / 32)];
+  __shared__ double sh[NR * 32];          // any CTA width up to 1024 threads
   __shared__ bool is_last;
   block_sum<NR>(v, sh);
   if (threadIdx.x == 0) {
@@ -297,7 +297,7 @@ __device__ __forceinline__ double ll_finish(LLReq& r, u64 epoch, int* err) {
   return __longlong_as_double((long long)((r.lo & 0xffffffffull) | (r.hi << 32)));
 }
 // Out-of-line variant for rarely taken paths (keeps the polling loop out of hot code).
-__device__ __noinline__ double ll_load16_cold(const u64* rec, int j, u64 epoch, int* err) {
+static __device__ __noinline__ double ll_load16_cold(const u64* rec, int j, u64 epoch, int* err) {
   return ll_load16(rec, j, epoch, err);
 }
 // Warp-collective: all-rank totals of the record of `epoch` (NQ = 4 or 8 sums, the first `nr`

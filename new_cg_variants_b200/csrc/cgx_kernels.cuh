@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(kBlock) instrument_kernel(const Op A, const Ar
 }
 
 // multi-GPU: fold all ranks' instrumentation records of epoch pend_e[0] into history entry k
-__global__ void hist_consume_kernel(const Args g) {
+static __global__ void hist_consume_kernel(const Args g) {
   double acc[kNRed];
   dist_totals(g, g.pend_e[0], 4, acc);
   if (threadIdx.x == 0) {
@@ -816,14 +816,14 @@ __global__ void hist_consume_kernel(const Args g) {
 }
 
 // multi-GPU: fold the pending reductions into the persisted scalars (end of cgx_advance)
-__global__ void flush_scalars_kernel(const Args g) {
+static __global__ void flush_scalars_kernel(const Args g) {
   double a, b;
   dist_scalars(g, g.meur != 0, a, b);
 }
 
 // multi-GPU: copy the first / last plane of v into the neighbours' ghost planes of channel
 // hout_ch (initialisation SpMVs, instrumentation x, x_true) and publish the halo epoch.
-__global__ void __launch_bounds__(kBlock) halo_push_kernel(const Args g, const double* __restrict__ v) {
+static __global__ void __launch_bounds__(kBlock) halo_push_kernel(const Args g, const double* __restrict__ v) {
   const i64 pl = g.d.plane;
   const i64 stride = (i64)gridDim.x * kBlock;
   for (i64 i = (i64)blockIdx.x * kBlock + threadIdx.x; i < pl; i += stride) {
@@ -836,7 +836,7 @@ __global__ void __launch_bounds__(kBlock) halo_push_kernel(const Args g, const d
 // -------------------------------------------------------------------------------------
 // Small helpers used only by the (non-timed) initialisation.
 // -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) scale_kernel(const double* __restrict__ dinv,
+static __global__ void __launch_bounds__(kBlock) scale_kernel(const double* __restrict__ dinv,
                                                       const double* __restrict__ v,
                                                       double* __restrict__ out, i64 n) {
   const i64 stride = (i64)gridDim.x * kBlock;
@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(kBlock) scale_kernel(const double* __restrict_
 }
 
 // sc->tmp[slot] = u . (dinv ? dinv*v : v)   (multi-GPU: the rank's partial)
-__global__ void __launch_bounds__(kBlock) dot_kernel(const double* __restrict__ u,
+static __global__ void __launch_bounds__(kBlock) dot_kernel(const double* __restrict__ u,
                                                     const double* __restrict__ v,
                                                     const double* __restrict__ dinv, i64 n,
                                                     Scal* sc, int slot, double* partials,
@@ -860,7 +860,7 @@ __global__ void __launch_bounds__(kBlock) dot_kernel(const double* __restrict__ 
 }
 
 // multi-GPU: publish the rank's eight initialisation partials (tmp[0..7]) as epoch sepoch
-__global__ void push_tmp_kernel(const Args g) {
+static __global__ void push_tmp_kernel(const Args g) {
   if (threadIdx.x != 0) return;
   const Scal* sc = g.sc + g.scpar;
   const int slot = (int)(g.sepoch % kSlots);
@@ -879,7 +879,7 @@ __global__ void push_tmp_kernel(const Args g) {
 // Initial scalars from the initialisation dots.  tmp: 0 nu, 1 mu, 2 eta, 3 delta, 4 gamma.
 // variant_class: 0 HS, 1 CG/GV (mu := p.s), 2 PR/M/pipe (predict first beta).
 // Multi-GPU (g.d.world > 1): tmp[] first becomes the all-rank total of epoch pend_e[0].
-__global__ void init_scalars_kernel(const Args g, int variant_class, int meurant) {
+static __global__ void init_scalars_kernel(const Args g, int variant_class, int meurant) {
   if (threadIdx.x != 0) return;
   Scal* sc = g.sc + g.scpar;
   if (g.d.world > 1) {

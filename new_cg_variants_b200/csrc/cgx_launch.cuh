@@ -1,0 +1,85 @@
+// cgx_launch.cuh -- launchers of the fused vector passes and fused SpMV passes (templates;
+// instantiated per preconditioner mode in cgx_iter.cu, and for the plain modes in cgx.cu).
+#pragma once
+#include "cgx_host.h"
+
+// which state vector a fused SpMV pass reads (second one for the 2-RHS pass)
+template <int MODE> struct SpInput { static constexpr int v0 = -1, v1 = -1; };
+template <> struct SpInput<SP_HS> { static constexpr int v0 = V_P, v1 = -1; };
+template <> struct SpInput<SP_PR> { static constexpr int v0 = V_P, v1 = -1; };
+template <> struct SpInput<SP_CG> { static constexpr int v0 = V_RT, v1 = -1; };
+template <> struct SpInput<SP_CG_E> { static constexpr int v0 = V_R, v1 = -1; };
+template <> struct SpInput<SP_GV_E> { static constexpr int v0 = V_W, v1 = -1; };
+template <> struct SpInput<SP_GV> { static constexpr int v0 = V_WT, v1 = -1; };
+template <> struct SpInput<SP_PIPE_R> { static constexpr int v0 = V_ST, v1 = V_RT; };
+template <> struct SpInput<SP_PIPE_N> { static constexpr int v0 = V_ST, v1 = -1; };
+
+
+// Fused SpMV pass of stage MODE (vin/vout only for SP_PLAIN / SP_RESID).
+template <int MODE, int PM, bool MEUR>
+static void launch_spmv(cgx_ctx* c, Args g, const double* vin, double* vout) {
+  constexpr int v0 = SpInput<MODE>::v0, v1 = SpInput<MODE>::v1;
+  constexpr int nv = (v1 >= 0) ? 2 : 1;
+  Plan p;
+  p.produce = SpTraits<MODE>::FK;
+  p.hin_n = nv; p.hin_ch = 0;
+  plan_apply(c, g, p);
+  {
+    ProfScope ps(c, PC_SP0 + (MODE == SP_CG_E ? (int)SP_CG : MODE == SP_GV_E ? (int)SP_GV : MODE));
+    bool done = false;
+    if constexpr (v0 >= 0) {
+      if (c->op_kind == 2 && c->use_tma && c->tmap_ok[v0] && (v1 < 0 || c->tmap_ok[v1 < 0 ? 0 : v1])) {
+        // grid = the CTAs that are actually co-resident (one wave): the kernel splits the work
+        // evenly over gridDim.x, so a partial second wave would cost a full extra pass
+        const int per_sm = ctx_occupancy(c, (const void*)stencil_tma_kernel<MODE, PM, MEUR>, kTmaThreads,
+                                         tma_smem_bytes(nv));
+        const int tgrid = std::min(c->tma_grid[nv - 1], per_sm * c->sm_count);
+        stencil_tma_kernel<MODE, PM, MEUR><<<tgrid, kTmaThreads, tma_smem_bytes(nv), c->stream>>>(
+            c->tmap[v0], c->tmap[v1 < 0 ? v0 : v1], c->geom, g);
+        done = true;
+      }
+    }
+    if (!done) {
+      const double* a0 = v0 >= 0 ? c->vec[v0 < 0 ? 0 : v0] : vin;
+      const double* a1 = v1 >= 0 ? c->vec[v1 < 0 ? 0 : v1] : nullptr;
+      const VecIn in0 = vec_in(c, a0, 0, g), in1 = vec_in(c, a1, 1, g);
+      if (c->op_kind == 1) {
+        if (!c->no_csr_stream) {
+          const int grid = std::max(1, std::min(c->n_rowblk, c->sm_count * 8));
+          csr_stream_kernel<MODE, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(c->csr, c->d_rowblk, c->n_rowblk, g,
+                                                                           in0, in1, vout);
+        } else {
+          spmv_kernel<CsrOp, MODE, PM, MEUR><<<grid_for(c, c->n), kBlock, 0, c->stream>>>(c->csr, g, in0, in1, vout);
+        }
+      } else {
+        spmv_kernel<StencilOp, MODE, PM, MEUR><<<grid_for(c, c->n), kBlock, 0, c->stream>>>(c->sten, g, in0, in1, vout);
+      }
+    }
+    c->launches++;
+  }
+  plan_commit(c, g, p);
+}
+
+template <int KID, int PM, bool MEUR>
+static void launch_ew(cgx_ctx* c, Args g) {
+  Plan p;
+  p.consume = true;
+  p.produce = EwKind<KID>::FK;
+  p.hout_ch = 0;
+  p.hout_n = (KID == EW_HS1) ? 0 : (KID == EW_PIPE_R ? 2 : 1);
+  plan_apply(c, g, p);
+  {
+    // One resident wave: on a partition every CTA folds the all-rank records before it streams
+    // (2-4 us); with 1184 CTAs at 3 resident per SM that prologue was paid by three successive
+    // waves (+10 us per launch, found with the in-kernel clock stamps).  Grid-stride covers the rows.
+    const int per_sm = ctx_occupancy(c, (const void*)ew_kernel<KID, PM, MEUR>, kBlock, 0);
+    int grid = grid_for(c, (c->n + 1) / 2);
+    // (one GPU: measured neutral to slightly negative for the long passes, -4 % per iteration
+    // for HS-CG's two short ones -- tools/onewave_probe.py)
+    if (c->dist.world > 1 || c->one_wave || KID == EW_HS1 || KID == EW_HS2) grid = std::min(grid, per_sm * c->sm_count);
+    ProfScope ps(c, PC_EW0 + (KID == EW_CG_E ? (int)EW_CG : KID == EW_GV_E ? (int)EW_GV : KID));
+    ew_kernel<KID, PM, MEUR><<<grid, kBlock, 0, c->stream>>>(g);
+    c->launches++;
+  }
+  plan_commit(c, g, p);
+}

@@ -1,0 +1,256 @@
+// cgx_stencil_fused.cuh -- PR-CG / M-CG: ONE launch per iteration on the matrix-free stencil.
+//
+// The two dependency stages of pr_cg.py:146-158 (vector updates, then s = A p with its dots)
+// are separated only by the halo of p: s_i needs the NEW p at the six neighbours of i.  This
+// kernel recomputes p on that halo instead of going through HBM:
+//
+//   plane step zz (a CTA owns a kTX x kTY column and marches in z, as cgx_stencil_tma.cuh):
+//     stage 1   p_old, s_old, rt_old of plane zz -- tile + one-point xy halo -- arrive by three
+//               bulk-tensor copies (TMA, one mbarrier); on the tile:   x += a p ; r -= a s ;
+//               rt -= a M s ; p = rt + b p  (+ nu = rt.r), on the halo only rt and p; the new p
+//               plane stays in shared memory (ring of 4 planes);
+//     stage 2   s = A p for plane zz-1 from the ring planes zz-2, zz-1, zz  (+ mu, delta, gamma)
+//
+//   HBM words per row: read x, r, p, s, rt; write x, r, p, s, rt = 10 (two-kernel path: 12),
+//   one launch, one fused reduction {mu, delta, gamma, nu} per iteration.
+//
+// p, s and rt are read on the halo while other CTAs write them, so they are ping-pong buffered
+// (read `cur`, write `nxt`); x and r are touched by their owner only and stay in place.
+//
+// Warp-specialised: warp 8 is the TMA producer (one elected lane, per-stage full/empty
+// mbarriers, runs up to kFStages planes ahead and across column changes); warps 0-7 compute.
+// The only CTA-level synchronisation is one 256-thread named barrier per plane (the new p
+// plane is exchanged between threads through shared memory).
+//
+// Arithmetic: every elementwise product/sum and every row sum is the same separately rounded
+// operation, in the same order, as ew_kernel<EW_PR> followed by stencil_tma_kernel<SP_PR>, so the
+// state vectors after an iteration are bit-identical to the two-kernel path given the same
+// (a, b); only the summation order of the four dots differs (deterministic).
+#pragma once
+#include "cgx_stencil_tma.cuh"
+
+namespace cgx {
+
+constexpr int kFStages = 2;                       // TMA input stages (3 planes each)
+constexpr int kFRing = 4;                         // planes of new p kept in shared memory
+constexpr int kFConsumers = 256;                  // 8 compute warps: warp w <-> row w of the tile
+constexpr int kFThreads = kFConsumers + 32;       // + 1 producer warp
+constexpr int kFPairs = kTX / 64;                 // a lane owns the point pairs (2 lx, 2 lx + 1) + 64 j
+
+__host__ __device__ constexpr size_t fused_smem_bytes() {
+  return (size_t)(kFStages * 3 + kFRing) * kPlaneStride * sizeof(double) + 128;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void sts2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
+// PM: 0 identity, 2 Jacobi with a constant diagonal (a Jacobi VECTOR would need dinv on the halo:
+// those runs keep the two-kernel path).
+template <int PM, bool MEUR>
+__global__ void __launch_bounds__(kFThreads, 2)
+pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_s,
+                const __grid_constant__ CUtensorMap tm_rt, const TmaGeom G, const Args g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* smem = reinterpret_cast<double*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+  double* stage = smem;                                            // [kFStages][3][kPlaneStride]
+  double* ring = smem + (size_t)kFStages * 3 * kPlaneStride;       // [kFRing][kPlaneStride]
+  __shared__ __align__(8) uint64_t full_bar[kFStages], empty_bar[kFStages];
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kFStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kFConsumers / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const double a = g.sc->a, b = g.sc->b;
+  const double ds = g.dinv_s;
+  auto M = [&](double v) { return PM == 2 ? mul_(ds, v) : v; };
+
+  const int zmin = G.has_zlo ? -1 : 0, zmax = G.has_zhi ? G.nz : G.nz - 1;
+  const i64 plane_pts = (i64)G.nx * G.ny;
+  const i64 total = (i64)G.ntx * G.nty * G.nz;
+  const i64 pos_begin = (i64)blockIdx.x * total / gridDim.x;
+  const i64 range_end = ((i64)blockIdx.x + 1) * total / gridDim.x;
+  constexpr uint32_t kBytes = (uint32_t)(3 * kPlane * 8);
+
+  double red[kNRed] = {0.0, 0.0, 0.0, 0.0};     // mu, delta, gamma, nu
+
+  if (tid >= kFConsumers) {
+    // ------------------------------------------------------------------ producer warp
+    if (tid == kFConsumers) {
+      uint32_t li = 0;
+      for (i64 pos = pos_begin; pos < range_end;) {
+        const int col = (int)(pos / G.nz);
+        const int z0 = (int)(pos - (i64)col * G.nz);
+        const int z1 = (int)min((i64)G.nz, (i64)z0 + (range_end - pos));
+        pos += z1 - z0;
+        const int x0 = (col % G.ntx) * kTX, y0 = (col / G.ntx) * kTY;
+        const int lo = G.march_y ? z0 : max(z0 - 1, zmin), hi = G.march_y ? z1 - 1 : min(z1, zmax);
+        for (int zz = lo; zz <= hi; ++zz, ++li) {
+          const int slot = li % kFStages;
+          if (li >= kFStages) mbar_wait(&empty_bar[slot], ((li / kFStages) - 1) & 1u, G.err);
+          double* dst = stage + (size_t)slot * 3 * kPlaneStride;
+          mbar_arrive_expect_tx(&full_bar[slot], kBytes);
+          const int ty0 = G.march_y ? zz * kTY : y0, tz = G.march_y ? 0 : zz;
+          tma_load_3d(dst, &tm_p, x0 - 2, ty0 - 1, tz, &full_bar[slot]);
+          tma_load_3d(dst + kPlaneStride, &tm_s, x0 - 2, ty0 - 1, tz, &full_bar[slot]);
+          tma_load_3d(dst + 2 * kPlaneStride, &tm_rt, x0 - 2, ty0 - 1, tz, &full_bar[slot]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ compute warps
+    const int ly = tid >> 5, lx = tid & 31;
+    uint32_t li = 0;
+    bool first_seg = true;
+    for (i64 pos = pos_begin; pos < range_end;) {
+      const int col = (int)(pos / G.nz);
+      const int z0 = (int)(pos - (i64)col * G.nz);
+      const int z1 = (int)min((i64)G.nz, (i64)z0 + (range_end - pos));
+      pos += z1 - z0;
+      const int x0 = (col % G.ntx) * kTX, y0 = (col / G.ntx) * kTY;
+      const int lo = G.march_y ? z0 : max(z0 - 1, zmin), hi = G.march_y ? z1 - 1 : min(z1, zmax);
+      // the previous column's last stencil stage may still be reading the ring
+      if (!first_seg) named_bar_sync(1, kFConsumers);
+      first_seg = false;
+
+      // x and r do not go through shared memory: fetched one plane ahead into registers
+      double xn[kFPairs][2], rn[kFPairs][2];
+      auto fetch_xr = [&](int z) {
+        const int gy = G.march_y ? z * kTY + ly : y0 + ly;
+        const i64 ib = (G.march_y ? 0 : (i64)z * plane_pts) + (i64)gy * G.nx + x0 + 2 * lx;
+#pragma unroll
+        for (int j = 0; j < kFPairs; ++j) {
+          const bool ok = gy < G.ny && (x0 + 2 * lx + 64 * j) < G.nx;
+          double2 xv = make_double2(0.0, 0.0), rv = make_double2(0.0, 0.0);
+          if (ok) {
+            xv = *reinterpret_cast<const double2*>(g.x + ib + 64 * j);
+            rv = *reinterpret_cast<const double2*>(g.r + ib + 64 * j);
+          }
+          xn[j][0] = xv.x; xn[j][1] = xv.y; rn[j][0] = rv.x; rn[j][1] = rv.y;
+        }
+      };
+      if (lo >= z0) fetch_xr(lo);
+      double r_cur[kFPairs][2] = {}, r_prev[kFPairs][2] = {};
+
+      for (int zz = lo; zz <= hi + 1; ++zz) {
+#pragma unroll
+        for (int j = 0; j < kFPairs; ++j) { r_prev[j][0] = r_cur[j][0]; r_prev[j][1] = r_cur[j][1]; }
+        if (zz <= hi) {
+          const bool fullp = zz >= z0 && zz < z1;          // a plane this CTA owns (else: only its new p)
+          double xc[kFPairs][2], rc[kFPairs][2];
+#pragma unroll
+          for (int j = 0; j < kFPairs; ++j) { xc[j][0] = xn[j][0]; xc[j][1] = xn[j][1]; rc[j][0] = rn[j][0]; rc[j][1] = rn[j][1]; }
+          if (zz + 1 >= z0 && zz + 1 < z1) fetch_xr(zz + 1);
+          const int slot = li % kFStages;
+          mbar_wait(&full_bar[slot], (li / kFStages) & 1u, G.err);
+          const double* sp = stage + (size_t)slot * 3 * kPlaneStride;
+          const double* ss = sp + kPlaneStride;
+          const double* srt = sp + 2 * kPlaneStride;
+          double* pn = ring + (size_t)(zz & (kFRing - 1)) * kPlaneStride;
+          const int gy = G.march_y ? zz * kTY + ly : y0 + ly;
+          const i64 ib = (G.march_y ? 0 : (i64)zz * plane_pts) + (i64)gy * G.nx + x0 + 2 * lx;
+#pragma unroll
+          for (int j = 0; j < kFPairs; ++j) {
+            const int c = (ly + 1) * kPX + 2 * lx + 64 * j + 2;
+            const double2 po = lds2(sp + c), so = lds2(ss + c), rto = lds2(srt + c);
+            const double pov[2] = {po.x, po.y}, sov[2] = {so.x, so.y}, rtov[2] = {rto.x, rto.y};
+            double xo[2], ro[2], rtn[2], pnw[2];
+            const bool ok = fullp && gy < G.ny && (x0 + 2 * lx + 64 * j) < G.nx;
+#pragma unroll
+            for (int l = 0; l < 2; ++l) {                   // pr_cg.py:146-148,151,157
+              xo[l] = axpy_(xc[j][l], a, pov[l]);
+              ro[l] = axmy_(rc[j][l], a, sov[l]);
+              rtn[l] = axmy_(rtov[l], a, M(sov[l]));
+              pnw[l] = axpy_(rtn[l], b, pov[l]);
+              if (ok) red[3] = fma(rtn[l], ro[l], red[3]);
+              r_cur[j][l] = ro[l];
+            }
+            sts2(pn + c, pnw[0], pnw[1]);
+            if (ok) {
+              const i64 i = ib + 64 * j;
+              *reinterpret_cast<double2*>(g.x + i) = make_double2(xo[0], xo[1]);
+              *reinterpret_cast<double2*>(g.r + i) = make_double2(ro[0], ro[1]);
+              *reinterpret_cast<double2*>(g.rt + i) = make_double2(rtn[0], rtn[1]);
+              *reinterpret_cast<double2*>(g.p + i) = make_double2(pnw[0], pnw[1]);
+            }
+          }
+          if (fullp) {
+            // the new p on the one-point xy halo of the tile (recomputed, never stored to HBM)
+            if (tid < 2 * (kTX / 2)) {
+              const int py = (tid >= kTX / 2) ? kPY - 1 : 0;
+              const int c = py * kPX + 2 * (tid & (kTX / 2 - 1)) + 2;
+              const double2 po = lds2(sp + c), so = lds2(ss + c), rto = lds2(srt + c);
+              const double r0 = axmy_(rto.x, a, M(so.x)), r1 = axmy_(rto.y, a, M(so.y));
+              sts2(pn + c, axpy_(r0, b, po.x), axpy_(r1, b, po.y));
+            } else if (tid < kTX + 2 * kTY) {
+              const int u = tid - kTX;
+              const int c = ((u % kTY) + 1) * kPX + ((u >= kTY) ? kTX + 2 : 1);
+              const double r0 = axmy_(srt[c], a, M(ss[c]));
+              pn[c] = axpy_(r0, b, sp[c]);
+            }
+          }
+          __syncwarp();
+          if (lx == 0) mbar_arrive(&empty_bar[slot]);       // this warp is done with the input stage
+          ++li;
+        }
+        named_bar_sync(1, kFConsumers);                     // the new p plane zz is complete
+
+        const int q = zz - 1;                               // stencil + dots for plane q
+        if (q >= z0 && q < z1) {
+          const double* pm = ring + (size_t)((q - 1) & (kFRing - 1)) * kPlaneStride;
+          const double* pc = ring + (size_t)(q & (kFRing - 1)) * kPlaneStride;
+          const double* pp = ring + (size_t)((q + 1) & (kFRing - 1)) * kPlaneStride;
+          const bool has_zm = !G.march_y && ((q > 0) || G.has_zlo);
+          const bool has_zp = !G.march_y && ((q < G.nz - 1) || G.has_zhi);
+          const int gy = G.march_y ? q * kTY + ly : y0 + ly;
+          const i64 ib = (G.march_y ? 0 : (i64)q * plane_pts) + (i64)gy * G.nx + x0 + 2 * lx;
+#pragma unroll
+          for (int j = 0; j < kFPairs; ++j) {
+            if (gy < G.ny && (x0 + 2 * lx + 64 * j) < G.nx) {
+              const int c = (ly + 1) * kPX + 2 * lx + 64 * j + 2;
+              const double2 zm = lds2(pm + c), zp = lds2(pp + c), ym = lds2(pc + c - kPX), yp = lds2(pc + c + kPX),
+                            ct = lds2(pc + c);
+              const double xm = pc[c - 1], xp = pc[c + 2];
+              const double zmv[2] = {zm.x, zm.y}, zpv[2] = {zp.x, zp.y}, ymv[2] = {ym.x, ym.y}, ypv[2] = {yp.x, yp.y},
+                           ctv[2] = {ct.x, ct.y}, xmv[2] = {xm, ct.x}, xpv[2] = {ct.y, xp};
+              double y[2];
+#pragma unroll
+              for (int l = 0; l < 2; ++l) {
+                // canonical CSR order z-1, y-1, x-1, centre, x+1, y+1, z+1; xy neighbours outside
+                // the domain are +0.0 (TMA fill -> p = 0): adding off * 0 never changes the sum;
+                // absent z planes are stale shared memory and keep their select (cgx_stencil_tma.cuh)
+                double acc = 0.0, t;
+                t = add_(acc, mul_(G.off, zmv[l]));          acc = has_zm ? t : acc;
+                acc = add_(acc, mul_(G.off, ymv[l]));
+                acc = add_(acc, mul_(G.off, xmv[l]));
+                acc = add_(acc, mul_(G.diag, ctv[l]));
+                acc = add_(acc, mul_(G.off, xpv[l]));
+                acc = add_(acc, mul_(G.off, ypv[l]));
+                t = add_(acc, mul_(G.off, zpv[l]));          acc = has_zp ? t : acc;
+                y[l] = acc;
+                const double sti = M(acc);                   // pr_cg.py:152-156
+                red[0] = fma(ctv[l], acc, red[0]);
+                red[1] = fma(r_prev[j][l], sti, red[1]);
+                red[2] = fma(sti, acc, red[2]);
+              }
+              *reinterpret_cast<double2*>(g.s + ib + 64 * j) = make_double2(y[0], y[1]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // {mu, delta, gamma, nu} -> a, b of the next iteration (pr_cg.py:154-158 then :149-150)
+  grid_sum_finalize<4>(red, g.partials, g.ticket, [&](const double* acc) {
+    apply_finalize(FK_PIPE, MEUR, g.sc, acc, g.k);
+  }, false);
+}
+
+}  // namespace cgx

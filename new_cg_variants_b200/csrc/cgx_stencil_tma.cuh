@@ -61,12 +61,11 @@ __device__ __forceinline__ uint64_t global_ns() {
 }
 // Bounded wait: a copy that never lands (bad descriptor) must fail loudly, not hang the GPU.
 // The flag is checked by the host after every synchronisation (CGX_ERR_CUDA).
-__device__ int g_tma_timeout = 0;
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = global_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (global_ns() - t0 > 1000000000ull) { atomicExch(&g_tma_timeout, 1); return; }
+    if (global_ns() - t0 > 1000000000ull) { atomicExch(err, 1); return; }
   }
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2,
@@ -90,6 +89,7 @@ struct TmaGeom {
                                  // column of x-tiles, so consecutive tiles pipeline through the ring like
                                  // z-planes do (nz = number of y-tiles, nty = 1; no z neighbours)
   double diag, off;
+  int* err;                      // device word set when a plane copy did not land within 1 s
 };
 
 #define NV_OF(MODE) ((MODE) == SP_PIPE_R ? 2 : 1)
@@ -153,7 +153,7 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
       tma_load_3d(dst, &tm0, x0 - 2, ty0 - 1, tz, &bar[slot]);
       if constexpr (NV == 2) tma_load_3d(dst + kPlaneStride, &tm1, x0 - 2, ty0 - 1, tz, &bar[slot]);
     };
-    auto wait_load = [&](uint32_t li) { mbar_wait(&bar[li % kRing], (li / kRing) & 1u); };
+    auto wait_load = [&](uint32_t li) { mbar_wait(&bar[li % kRing], (li / kRing) & 1u, G.err); };
     // Ghost plane of a slab (multi-GPU): the neighbour rank's vector pass stored it into this
     // rank's window as LL words (each 8-byte word = half a double + the halo epoch).  All
     // threads poll their elements and write the tile -- zero outside the domain, like the TMA
@@ -164,7 +164,6 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
       const int side = z < 0 ? 0 : 1;
       WinHdr* w = g.d.win[g.d.rank];
       double* dst = smem + (size_t)slot * NV * kPlaneStride;
-#pragma unroll
       constexpr int kPer = (kPlane + kTmaThreads - 1) / kTmaThreads;      // elements per thread
       const u64 tag = g.hin_epoch & 0xffffffffull;
 #pragma unroll

@@ -458,3 +458,39 @@ def test_cg_cg_with_elided_rt_is_bitwise_identical(shape):
         x, hist, info = s.solve("cg", b, x0, 12, x_true=x_true, path="stream")
         ref = orc.solve("cg", S.tocsr(), b, x0, 12, dinv=1 / (S.diagonal() + np.arange(n) % 3), x_true=x_true)
         np.testing.assert_allclose(hist["updated_residual_2_norm"][:8], ref["updated_residual_2_norm"][:8], rtol=1e-10)
+
+
+@pytest.mark.parametrize("shape", [(256, 16, 1), (130, 9, 1), (64, 24, 20), (258, 10, 7), (12, 12, 12), (2, 3, 40),
+                                   (128, 8, 33), (256, 40, 1)])
+def test_pr_fused_single_launch_equals_two_kernel_path(shape):
+    """PR-CG / M-CG on the TMA stencil path run ONE kernel per iteration (cgx_stencil_fused.cuh: the
+    vector updates and s = A p fused by recomputing p on the tile halo).  Every elementwise and
+    row-sum operation is the two-kernel path's, so after one loop trip (same alpha, beta) the state
+    vectors are BITWISE those of ew_kernel<EW_PR> + stencil_tma_kernel<SP_PR>; afterwards only the
+    summation order of the four fused dots differs -> equal to rounding.  Chunk sizes of 1, 3 and
+    8 planes per CTA exercise column changes, outer planes and partial tiles."""
+    nx, ny, nz = shape
+    S = PoissonStencil(nx, ny, nz, dim=2 if nz == 1 else 3)
+    n = S.shape[0]
+    x_true = np.ones(n) / np.sqrt(n)
+    b, x0 = S @ x_true, np.zeros(n)
+    for dinv in (1 / S.diagonal(), None):
+        for tag in ("pr", "m"):
+            res = {}
+            for key, fused, planes in (("two", 0, 8), ("f8", 1, 8), ("f3", 1, 3), ("f1", 1, 1)):
+                with Session(S, dinv=dinv) as s:
+                    s.set_option("pr_fused", fused)
+                    s.set_option("fused_min_planes", planes)
+                    s.load_problem(b, x0, x_true)
+                    info = s.run(tag, 2, path="stream")
+                    one = {v: s.vector(v) for v in ("x", "r", "rt", "p", "s")}
+                    x, hist, info = s.solve(tag, b, x0, 14, x_true=x_true, path="stream")
+                    res[key] = (one, x, hist, info["kernel_launches"])
+            if nx % 2 == 0 and (ny >= 4 or nz == 1):                 # (else: no TMA path, the generic kernels run)
+                assert res["f8"][3] < res["two"][3]                  # fewer launches: the fused kernel ran
+            for key in ("f8", "f3", "f1"):
+                for v in ("x", "r", "rt", "p", "s"):
+                    assert np.array_equal(res[key][0][v], res["two"][0][v]), (shape, tag, key, v)
+                np.testing.assert_allclose(res[key][1], res["two"][1], rtol=1e-10, atol=1e-13, err_msg=f"{shape}/{tag}/{key}")
+                for h in orc.HISTORIES:
+                    np.testing.assert_allclose(res[key][2][h], res["two"][2][h], rtol=1e-10, err_msg=f"{shape}/{tag}/{key}/{h}")
