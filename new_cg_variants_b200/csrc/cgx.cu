@@ -394,6 +394,7 @@ static bool tma_prepare_geom(cgx_ctx* c) {
   G.has_zlo = S.has_zlo; G.has_zhi = S.has_zhi;
   G.diag = S.diag; G.off = S.off;
   G.err = c->d_tma_err;
+  G.nchunk = 1;
   G.march_y = 0;
   if (S.nz == 1 && !S.has_zlo && !S.has_zhi && G.nty > 1) {   // 2-D: march down the y-tiles of a column
     G.march_y = 1;
@@ -1001,6 +1002,7 @@ extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
   if (!strcmp(name, "cg_elide")) { c->no_elide = (value == 0); return CGX_OK; }
   if (!strcmp(name, "pr_fused")) { c->no_fused = (value == 0); return CGX_OK; }
   if (!strcmp(name, "fused_min_planes")) { c->fused_min_planes = std::max(1, value); return CGX_OK; }
+  if (!strcmp(name, "fused_chunks")) { c->fused_chunks = std::max(0, value); return CGX_OK; }
   if (!strcmp(name, "persistent_threshold")) { c->pers_threshold = value; return CGX_OK; }
   if (!strcmp(name, "pers_threads")) { c->pers_threads = value; return CGX_OK; }
   if (!strcmp(name, "pers_ctas")) { c->pers_ctas = value; return CGX_OK; }

@@ -32,12 +32,15 @@ template <int PM, bool MEUR>
 static void launch_fused_t(cgx_ctx* c, const Args& g, int cur) {
   const size_t smem = fused_smem_bytes();
   const int per_sm = ctx_occupancy(c, (const void*)pr_fused_kernel<PM, MEUR>, kFThreads, smem);
-  const TmaGeom& G = c->geom;
-  const i64 total = (i64)G.ntx * G.nty * G.nz;
-  const i64 want = std::max<i64>(1, (total + c->fused_min_planes - 1) / c->fused_min_planes);
-  const int grid = (int)std::min<i64>(want, (i64)per_sm * c->sm_count);
+  // (column, z-chunk) work units, all co-resident when the columns fit: every chunk then marches
+  // in lockstep over its planes (L2 serves the halos neighbouring columns share)
+  TmaGeom G = c->geom;
+  const int cap = per_sm * c->sm_count, ncols = G.ntx * G.nty;
+  G.nchunk = std::max(1, std::min(cap / std::max(1, ncols), G.nz / std::max(1, c->fused_min_planes)));
+  if (c->fused_chunks > 0) G.nchunk = std::min(c->fused_chunks, G.nz);
+  const int grid = (int)std::min<i64>((i64)ncols * G.nchunk, cap);
   pr_fused_kernel<PM, MEUR><<<grid, kFThreads, smem, c->stream>>>(c->ftmap[cur][0], c->ftmap[cur][1], c->ftmap[cur][2],
-                                                                  c->geom, g);
+                                                                  G, g);
 }
 
 void cgx_launch_pr_fused(cgx_ctx* c, Args g) {

@@ -144,7 +144,7 @@ struct cgx_ctx {
   int fpar = 0;
   double* alt[3] = {};                     // second buffers of p, s, rt
   CUtensorMap ftmap[2][3];
-  int fused_min_planes = 8;
+  int fused_min_planes = 8, fused_chunks = 0;   // options: planes per CTA at least / force the chunk count
   std::map<std::pair<const void*, size_t>, int> occ;   // ctx_occupancy cache (per device)
   int* d_tma_err = nullptr;                // set by a TMA wait that expired (mbar_wait)
   int variant = 0, max_iter = 0, cur_k = 0, path = CGX_PATH_STREAM;

@@ -73,9 +73,12 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
 
   const int zmin = G.has_zlo ? -1 : 0, zmax = G.has_zhi ? G.nz : G.nz - 1;
   const i64 plane_pts = (i64)G.nx * G.ny;
-  const i64 total = (i64)G.ntx * G.nty * G.nz;
-  const i64 pos_begin = (i64)blockIdx.x * total / gridDim.x;
-  const i64 range_end = ((i64)blockIdx.x + 1) * total / gridDim.x;
+  // Work units = (column, z-chunk), chunk-major: unit u is column u % ncols of chunk u / ncols, so the
+  // CTAs of one chunk march through the same planes at the same time and the tile halos that
+  // neighbouring columns share are served by L2 instead of HBM.  The host launches one CTA per
+  // unit when they are all co-resident.
+  const int ncols = G.ntx * G.nty;
+  const int nunits = ncols * G.nchunk;
   constexpr uint32_t kBytes = (uint32_t)(3 * kPlane * 8);
 
   double red[kNRed] = {0.0, 0.0, 0.0, 0.0};     // mu, delta, gamma, nu
@@ -84,11 +87,9 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
     // ------------------------------------------------------------------ producer warp
     if (tid == kFConsumers) {
       uint32_t li = 0;
-      for (i64 pos = pos_begin; pos < range_end;) {
-        const int col = (int)(pos / G.nz);
-        const int z0 = (int)(pos - (i64)col * G.nz);
-        const int z1 = (int)min((i64)G.nz, (i64)z0 + (range_end - pos));
-        pos += z1 - z0;
+      for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const int col = unit % ncols, chunk = unit / ncols;
+        const int z0 = (int)((i64)chunk * G.nz / G.nchunk), z1 = (int)((i64)(chunk + 1) * G.nz / G.nchunk);
         const int x0 = (col % G.ntx) * kTX, y0 = (col / G.ntx) * kTY;
         const int lo = G.march_y ? z0 : max(z0 - 1, zmin), hi = G.march_y ? z1 - 1 : min(z1, zmax);
         for (int zz = lo; zz <= hi; ++zz, ++li) {
@@ -108,20 +109,21 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
     const int ly = tid >> 5, lx = tid & 31;
     uint32_t li = 0;
     bool first_seg = true;
-    for (i64 pos = pos_begin; pos < range_end;) {
-      const int col = (int)(pos / G.nz);
-      const int z0 = (int)(pos - (i64)col * G.nz);
-      const int z1 = (int)min((i64)G.nz, (i64)z0 + (range_end - pos));
-      pos += z1 - z0;
+    for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+      const int col = unit % ncols, chunk = unit / ncols;
+      const int z0 = (int)((i64)chunk * G.nz / G.nchunk), z1 = (int)((i64)(chunk + 1) * G.nz / G.nchunk);
       const int x0 = (col % G.ntx) * kTX, y0 = (col / G.ntx) * kTY;
       const int lo = G.march_y ? z0 : max(z0 - 1, zmin), hi = G.march_y ? z1 - 1 : min(z1, zmax);
-      // the previous column's last stencil stage may still be reading the ring
+      // the previous unit's last stencil stage may still be reading the ring
       if (!first_seg) named_bar_sync(1, kFConsumers);
       first_seg = false;
 
-      // x and r do not go through shared memory: fetched one plane ahead into registers
-      double xn[kFPairs][2], rn[kFPairs][2];
-      auto fetch_xr = [&](int z) {
+      // x and r do not go through shared memory: they are fetched ONE PLANE AHEAD into registers.
+      // Two register sets alternate (the plane loop is unrolled by two), so that no register copy
+      // of a value still in flight is ever needed -- such a copy, scheduled before the plane
+      // barrier, exposed the whole load latency in every step (ncu: 28 % of the stall samples).
+      typedef double Set[kFPairs][2];
+      auto fetch_xr = [&](int z, Set& xs, Set& rs) {
         const int gy = G.march_y ? z * kTY + ly : y0 + ly;
         const i64 ib = (G.march_y ? 0 : (i64)z * plane_pts) + (i64)gy * G.nx + x0 + 2 * lx;
 #pragma unroll
@@ -132,21 +134,17 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
             xv = *reinterpret_cast<const double2*>(g.x + ib + 64 * j);
             rv = *reinterpret_cast<const double2*>(g.r + ib + 64 * j);
           }
-          xn[j][0] = xv.x; xn[j][1] = xv.y; rn[j][0] = rv.x; rn[j][1] = rv.y;
+          xs[j][0] = xv.x; xs[j][1] = xv.y; rs[j][0] = rv.x; rs[j][1] = rv.y;
         }
       };
-      if (lo >= z0) fetch_xr(lo);
-      double r_cur[kFPairs][2] = {}, r_prev[kFPairs][2] = {};
 
-      for (int zz = lo; zz <= hi + 1; ++zz) {
-#pragma unroll
-        for (int j = 0; j < kFPairs; ++j) { r_prev[j][0] = r_cur[j][0]; r_prev[j][1] = r_cur[j][1]; }
+      // One plane step.  (xc, rc): x and r of plane zz, fetched during the previous step;
+      // (xn, rn): receive plane zz+1; rnew: receives the new r of plane zz; rold: the new r of
+      // plane zz-1 (written by the previous step), for the dots of the stencil stage.
+      auto plane_step = [&](const int zz, Set& xc, Set& rc, Set& xn, Set& rn, Set& rnew, Set& rold) {
         if (zz <= hi) {
           const bool fullp = zz >= z0 && zz < z1;          // a plane this CTA owns (else: only its new p)
-          double xc[kFPairs][2], rc[kFPairs][2];
-#pragma unroll
-          for (int j = 0; j < kFPairs; ++j) { xc[j][0] = xn[j][0]; xc[j][1] = xn[j][1]; rc[j][0] = rn[j][0]; rc[j][1] = rn[j][1]; }
-          if (zz + 1 >= z0 && zz + 1 < z1) fetch_xr(zz + 1);
+          if (zz + 1 >= z0 && zz + 1 < z1) fetch_xr(zz + 1, xn, rn);
           const int slot = li % kFStages;
           mbar_wait(&full_bar[slot], (li / kFStages) & 1u, G.err);
           const double* sp = stage + (size_t)slot * 3 * kPlaneStride;
@@ -160,22 +158,24 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
             const int c = (ly + 1) * kPX + 2 * lx + 64 * j + 2;
             const double2 po = lds2(sp + c), so = lds2(ss + c), rto = lds2(srt + c);
             const double pov[2] = {po.x, po.y}, sov[2] = {so.x, so.y}, rtov[2] = {rto.x, rto.y};
-            double xo[2], ro[2], rtn[2], pnw[2];
+            double xo[2], rtn[2], pnw[2];
             const bool ok = fullp && gy < G.ny && (x0 + 2 * lx + 64 * j) < G.nx;
 #pragma unroll
             for (int l = 0; l < 2; ++l) {                   // pr_cg.py:146-148,151,157
-              xo[l] = axpy_(xc[j][l], a, pov[l]);
-              ro[l] = axmy_(rc[j][l], a, sov[l]);
               rtn[l] = axmy_(rtov[l], a, M(sov[l]));
               pnw[l] = axpy_(rtn[l], b, pov[l]);
-              if (ok) red[3] = fma(rtn[l], ro[l], red[3]);
-              r_cur[j][l] = ro[l];
             }
             sts2(pn + c, pnw[0], pnw[1]);
             if (ok) {
+#pragma unroll
+              for (int l = 0; l < 2; ++l) {
+                xo[l] = axpy_(xc[j][l], a, pov[l]);
+                rnew[j][l] = axmy_(rc[j][l], a, sov[l]);
+                red[3] = fma(rtn[l], rnew[j][l], red[3]);
+              }
               const i64 i = ib + 64 * j;
               *reinterpret_cast<double2*>(g.x + i) = make_double2(xo[0], xo[1]);
-              *reinterpret_cast<double2*>(g.r + i) = make_double2(ro[0], ro[1]);
+              *reinterpret_cast<double2*>(g.r + i) = make_double2(rnew[j][0], rnew[j][1]);
               *reinterpret_cast<double2*>(g.rt + i) = make_double2(rtn[0], rtn[1]);
               *reinterpret_cast<double2*>(g.p + i) = make_double2(pnw[0], pnw[1]);
             }
@@ -236,13 +236,20 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
                 y[l] = acc;
                 const double sti = M(acc);                   // pr_cg.py:152-156
                 red[0] = fma(ctv[l], acc, red[0]);
-                red[1] = fma(r_prev[j][l], sti, red[1]);
+                red[1] = fma(rold[j][l], sti, red[1]);
                 red[2] = fma(sti, acc, red[2]);
               }
               *reinterpret_cast<double2*>(g.s + ib + 64 * j) = make_double2(y[0], y[1]);
             }
           }
         }
+      };
+
+      Set xa, ra, xb, rb, rna = {}, rnb = {};
+      if (lo >= z0) fetch_xr(lo, xa, ra);
+      for (int zz = lo; zz <= hi + 1; zz += 2) {
+        plane_step(zz, xa, ra, xb, rb, rna, rnb);
+        if (zz + 1 <= hi + 1) plane_step(zz + 1, xb, rb, xa, ra, rnb, rna);
       }
     }
   }

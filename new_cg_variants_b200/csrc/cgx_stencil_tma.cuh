@@ -89,6 +89,7 @@ struct TmaGeom {
                                  // column of x-tiles, so consecutive tiles pipeline through the ring like
                                  // z-planes do (nz = number of y-tiles, nty = 1; no z neighbours)
   double diag, off;
+  int nchunk;                    // z-chunks per column (kernels that take (column, chunk) work units)
   int* err;                      // device word set when a plane copy did not land within 1 s
 };
 
