@@ -72,7 +72,6 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
   auto M = [&](double v) { return PM == 2 ? mul_(ds, v) : v; };
 
   const int zmin = G.has_zlo ? -1 : 0, zmax = G.has_zhi ? G.nz : G.nz - 1;
-  const i64 plane_pts = (i64)G.nx * G.ny;
   // Work units = (column, z-chunk), chunk-major: unit u is column u % ncols of chunk u / ncols, so the
   // CTAs of one chunk march through the same planes at the same time and the tile halos that
   // neighbouring columns share are served by L2 instead of HBM.  The host launches one CTA per
@@ -123,17 +122,23 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
       // of a value still in flight is ever needed -- such a copy, scheduled before the plane
       // barrier, exposed the whole load latency in every step (ncu: 28 % of the stall samples).
       typedef double Set[kFPairs][2];
+      // element index of this lane's first pair in plane z (int: n + 2 planes < 2^31, cgx_set_stencil)
+      const int step_stride = G.march_y ? kTY * G.nx : G.nx * G.ny;
+      const int idx0 = (G.march_y ? ly : y0 + ly) * G.nx + x0 + 2 * lx;
+      const int ybase = G.march_y ? ly : y0 + ly, ystep = G.march_y ? kTY : 0;
+      bool okx[kFPairs];
+#pragma unroll
+      for (int j = 0; j < kFPairs; ++j) okx[j] = (x0 + 2 * lx + 64 * j) < G.nx;
       auto fetch_xr = [&](int z, Set& xs, Set& rs) {
-        const int gy = G.march_y ? z * kTY + ly : y0 + ly;
-        const i64 ib = (G.march_y ? 0 : (i64)z * plane_pts) + (i64)gy * G.nx + x0 + 2 * lx;
+        const bool oky = ybase + z * ystep < G.ny;
+        const int ib = idx0 + z * step_stride;
 #pragma unroll
         for (int j = 0; j < kFPairs; ++j) {
-          const bool ok = gy < G.ny && (x0 + 2 * lx + 64 * j) < G.nx;
-          double2 xv = make_double2(0.0, 0.0), rv = make_double2(0.0, 0.0);
-          if (ok) {
-            xv = *reinterpret_cast<const double2*>(g.x + ib + 64 * j);
-            rv = *reinterpret_cast<const double2*>(g.r + ib + 64 * j);
-          }
+          // unconditional loads (a pair outside the grid reads element 0 and is never used): a
+          // select on the loaded value would wait for the load right here
+          const int i = (oky && okx[j]) ? ib + 64 * j : 0;
+          const double2 xv = *reinterpret_cast<const double2*>(g.x + i);
+          const double2 rv = *reinterpret_cast<const double2*>(g.r + i);
           xs[j][0] = xv.x; xs[j][1] = xv.y; rs[j][0] = rv.x; rs[j][1] = rv.y;
         }
       };
@@ -151,15 +156,15 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
           const double* ss = sp + kPlaneStride;
           const double* srt = sp + 2 * kPlaneStride;
           double* pn = ring + (size_t)(zz & (kFRing - 1)) * kPlaneStride;
-          const int gy = G.march_y ? zz * kTY + ly : y0 + ly;
-          const i64 ib = (G.march_y ? 0 : (i64)zz * plane_pts) + (i64)gy * G.nx + x0 + 2 * lx;
+          const bool oky = ybase + zz * ystep < G.ny;
+          const int ib = idx0 + zz * step_stride;
 #pragma unroll
           for (int j = 0; j < kFPairs; ++j) {
             const int c = (ly + 1) * kPX + 2 * lx + 64 * j + 2;
             const double2 po = lds2(sp + c), so = lds2(ss + c), rto = lds2(srt + c);
             const double pov[2] = {po.x, po.y}, sov[2] = {so.x, so.y}, rtov[2] = {rto.x, rto.y};
             double xo[2], rtn[2], pnw[2];
-            const bool ok = fullp && gy < G.ny && (x0 + 2 * lx + 64 * j) < G.nx;
+            const bool ok = fullp && oky && okx[j];
 #pragma unroll
             for (int l = 0; l < 2; ++l) {                   // pr_cg.py:146-148,151,157
               rtn[l] = axmy_(rtov[l], a, M(sov[l]));
@@ -173,7 +178,7 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
                 rnew[j][l] = axmy_(rc[j][l], a, sov[l]);
                 red[3] = fma(rtn[l], rnew[j][l], red[3]);
               }
-              const i64 i = ib + 64 * j;
+              const int i = ib + 64 * j;
               *reinterpret_cast<double2*>(g.x + i) = make_double2(xo[0], xo[1]);
               *reinterpret_cast<double2*>(g.r + i) = make_double2(rnew[j][0], rnew[j][1]);
               *reinterpret_cast<double2*>(g.rt + i) = make_double2(rtn[0], rtn[1]);
@@ -208,11 +213,11 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
           const double* pp = ring + (size_t)((q + 1) & (kFRing - 1)) * kPlaneStride;
           const bool has_zm = !G.march_y && ((q > 0) || G.has_zlo);
           const bool has_zp = !G.march_y && ((q < G.nz - 1) || G.has_zhi);
-          const int gy = G.march_y ? q * kTY + ly : y0 + ly;
-          const i64 ib = (G.march_y ? 0 : (i64)q * plane_pts) + (i64)gy * G.nx + x0 + 2 * lx;
+          const bool oky = ybase + q * ystep < G.ny;
+          const int ib = idx0 + q * step_stride;
 #pragma unroll
           for (int j = 0; j < kFPairs; ++j) {
-            if (gy < G.ny && (x0 + 2 * lx + 64 * j) < G.nx) {
+            if (oky && okx[j]) {
               const int c = (ly + 1) * kPX + 2 * lx + 64 * j + 2;
               const double2 zm = lds2(pm + c), zp = lds2(pp + c), ym = lds2(pc + c - kPX), yp = lds2(pc + c + kPX),
                             ct = lds2(pc + c);
