@@ -119,15 +119,44 @@ def pinned(a):
 
 
 # ------------------------------------------------------------------------------ reference arm
+def _cpu_threads():
+    """Use every host core for the BLAS part whatever the launcher exported (torchrun sets
+    OMP_NUM_THREADS=1): returns (context manager, threads actually in use)."""
+    from threadpoolctl import threadpool_info, threadpool_limits
+    want = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    ctl = threadpool_limits(limits=want)
+    blas = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    return ctl, blas
+
+
+def _timed_oracle(orc, variant, A, b, x0, dinv, its, repeats):
+    """Seconds per `its` loop iterations of the oracle, initialisation excluded: each repeat times
+    solve(max_iter = its + 1) minus the initialisation alone (solve(max_iter = 1), best of 2)."""
+    t_init = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        orc.solve(variant, A, b, x0, 1, dinv=dinv, history=False)
+        dt = time.perf_counter() - t0
+        t_init = dt if t_init is None else min(t_init, dt)
+    out = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.solve(variant, A, b, x0, its + 1, dinv=dinv, history=False)
+        out.append(max(1e-9, time.perf_counter() - t0 - t_init))
+    return out, t_init
+
+
 def run_reference(args, rank, world):
     """The reference's CPU path: its algorithm restated in numpy/scipy (oracle/cg_oracle.py,
     bit-identical to the reference's *_pcg on the same machine) on the same workload.  The
     reference is pure Python and /root/reference does not travel to the GPU box, so this is
-    the "port" kind.  Each step is a bounded sample: `ref_iters` iterations from x0."""
+    the "port" kind.  Each step is a bounded sample: `ref_iters` loop iterations from x0
+    (6 iterations, callbacks=[], precomputed dinv), initialisation
+    excluded, all host cores."""
     if rank != 0:
         return
     from oracle import cg_oracle as orc
-    from threadpoolctl import threadpool_info
+    ctl, blas = _cpu_threads()
     t0 = time.time()
     A = orc.poisson3d(args.grid) if args.dim == 3 else orc.poisson2d(args.grid)
     x_true, b, x0 = orc.setup_problem(A)
@@ -136,12 +165,9 @@ def run_reference(args, rank, world):
     its = args.ref_iters
     for _ in range(min(args.warmup, 1)):       # one warm-up solve
         orc.solve(args.variant, A, b, x0, its + 1, dinv=dinv, history=False)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc.solve(args.variant, A, b, x0, its + 1, dinv=dinv, history=False)
-    dt = time.perf_counter() - t0
+    times, t_init = _timed_oracle(orc, args.variant, A, b, x0, dinv, its, args.steps)
+    dt = sum(times)
     value = its * args.steps / dt
-    blas = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     n = A.shape[0]
     line = {
         "impl": "reference", "metric": f"CG iterations/s ({REF_FUN.get(args.variant, args.variant)}, Jacobi, {args.dim}-D Poisson {args.grid}^{args.dim})",
@@ -151,9 +177,10 @@ def run_reference(args, rank, world):
         "config": {"workload": f"poisson{args.dim}d_{args.grid} {REF_FUN.get(args.variant, args.variant)} jacobi (scipy CSR, nnz={A.nnz})",
                    "iters_per_step": its, "n": n},
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": blas, "kind": "port",
-                         "sample": f"{args.steps} x {its} iterations of the numpy/scipy restatement on the full {args.grid}^{args.dim} CSR matrix "
-                                   f"(scipy SpMV single-threaded, OpenBLAS dots {blas} threads, host has {os.cpu_count()} cpus; "
-                                   f"matrix build {build_s:.1f}s untimed)"},
+                         "best_step_value": its / min(times),
+                         "sample": f"{args.steps} x {its} loop iterations of the numpy/scipy restatement on the full {args.grid}^{args.dim} CSR matrix, "
+                                   f"initialisation ({t_init:.2f}s) excluded (scipy SpMV single-threaded, OpenBLAS dots {blas} threads set explicitly, "
+                                   f"host has {os.cpu_count()} cpus; matrix build {build_s:.1f}s untimed)"},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "hbm_gbs_model": value * (8 * n * W_V[args.variant] + 12 * A.nnz + 4 * (n + 1)) / 1e9,
     }
@@ -161,25 +188,102 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------ our arm
-def cpu_baseline_sample(args):
+def cpu_baseline_sample(args, dev_hist=None):
+    """Bounded CPU sample of the same workload (min of 3 runs of `cpu_iters` loop iterations,
+    initialisation excluded) and -- the oracle being the checker -- the agreement of the device's
+    first iterations with it (`parity`)."""
     from oracle import cg_oracle as orc
-    from threadpoolctl import threadpool_info
+    ctl, blas = _cpu_threads()
     A = orc.poisson3d(args.grid) if args.dim == 3 else orc.poisson2d(args.grid)
     x_true, b, x0 = orc.setup_problem(A)
     dinv = orc.jacobi_dinv(A)
     its = args.cpu_iters
     orc.solve(args.variant, A, b, x0, 2, dinv=dinv, history=False)      # warm-up
-    best = None
-    for _ in range(2):
-        t0 = time.perf_counter()
-        orc.solve(args.variant, A, b, x0, its + 1, dinv=dinv, history=False)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    blas = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    return {"value": its / best, "unit": "iterations/s", "cores": blas, "kind": "port",
-            "sample": f"min of 2 runs of {its} iterations of oracle/cg_oracle.py ({REF_FUN.get(args.variant, args.variant)}, callbacks=[], "
-                      f"precomputed dinv) on the full {args.grid}^{args.dim} scipy CSR matrix; scipy SpMV single-threaded, "
-                      f"OpenBLAS {blas} threads, host {os.cpu_count()} cpus"}
+    times, t_init = _timed_oracle(orc, args.variant, A, b, x0, dinv, its, 3)
+    best = min(times)
+    out = {"value": its / best, "unit": "iterations/s", "cores": blas, "kind": "port",
+           "sample": f"min of 3 runs of {its} loop iterations of oracle/cg_oracle.py ({REF_FUN.get(args.variant, args.variant)}, callbacks=[], "
+                     f"precomputed dinv, initialisation excluded) on the full {args.grid}^{args.dim} scipy CSR matrix; scipy SpMV single-threaded, "
+                     f"OpenBLAS {blas} threads, host {os.cpu_count()} cpus"}
+    parity = None
+    if dev_hist is not None:
+        k = args.parity_iters
+        ref = orc.solve(args.variant, A, b, x0, k, dinv=dinv, x_true=x_true)
+        worst = 0.0
+        for h in ("updated_residual_2_norm", "residual_2_norm", "error_A_norm"):
+            rel = np.abs(dev_hist[h][:k] - ref[h][:k]) / np.abs(ref[h][:k])
+            worst = max(worst, float(rel.max()))
+        parity = {"iterations": k, "max_rel": worst, "tolerance": 1e-10, "ok": bool(worst <= 1e-10),
+                  "what": "device histories (updated/true residual norm, A-norm error) vs the oracle on the same problem, k < %d" % k}
+    return out, parity
+
+
+def read_traffic(kernel_class):
+    """ncu-measured DRAM bytes per launch of `kernel_class` from profiles/traffic.json -- only when
+    the file was recorded for the library that is loaded now (kernel-source fingerprint), so a
+    stale capture is never echoed."""
+    try:
+        from new_cg_variants_b200 import build as _b
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = t.get(kernel_class)
+        if not isinstance(ent, dict):
+            return None, "no ncu capture recorded for this kernel"
+        if ent.get("kernel_sources_sha") != _b.kernel_fingerprint():
+            return None, "stale: profiles/traffic.json was captured for other kernel sources"
+        return ent["dram_bytes_per_launch"], ent.get("source", "profiles/traffic.json")
+    except Exception as e:                                    # noqa: BLE001
+        return None, f"unavailable ({type(e).__name__})"
+
+
+def check_partitioned_answer(args, sess, S, b, x0, x_true, dinv, rank, world, local_rank):
+    """N > 1: verify the answer of the path that was timed.
+      (1) side problem 64^3, 25 iterations: the N-process run (x and all four histories) is
+          BIT-IDENTICAL to the same partition emulated as N contexts on rank 0's GPU;
+      (2) the full problem, 40 iterations with instrumentation: the partitioned histories agree
+          with the single-GPU run on rank 0 to 1e-10 (another summation order of the dots)."""
+    import torch.distributed as dist
+    from new_cg_variants_b200 import PoissonStencil, Session
+    from new_cg_variants_b200.dist import DistSession, GroupSession
+    out = {"ok": True}
+    hn = ("error_A_norm", "residual_2_norm", "error_2_norm", "updated_residual_2_norm")
+    # (1)
+    g = 64
+    S2 = PoissonStencil(g, g, g, dim=3)
+    n2 = S2.shape[0]
+    xt2 = np.ones(n2) / np.sqrt(n2)
+    b2, x02, d2 = S2 @ xt2, np.zeros(n2), 1 / S2.diagonal()
+    ds = DistSession(S2, dinv=d2, device=local_rank, rank=rank, world=world)
+    xl, hl, _ = ds.solve(args.variant, b2, x02, 26, x_true=xt2, histories=hn, path="stream")
+    xg = ds.gather_x(xl)
+    ds.close()
+    if rank == 0:
+        gs = GroupSession(S2, world, dinv=d2, devices=[local_rank] * world)
+        xe, he, _ = gs.solve(args.variant, b2, x02, 26, x_true=xt2, histories=hn, path="stream")
+        gs.close()
+        same = bool(np.array_equal(xg, xe)) and all(np.array_equal(hl[h], he[h]) for h in hn)
+        out["side_problem_bitwise_equal_to_emulation"] = same
+        out["ok"] &= same
+    # (2)
+    k = 41
+    sess.load_problem(b, x0, x_true)
+    sess.run(args.variant, k, histories=hn, path=args.path)
+    _, hist = sess.fetch_local(want_x=False, want_hist=True)
+    sess.load_problem(b, x0, None)
+    if rank == 0:
+        one = Session(S, dinv=dinv, device=local_rank)
+        _, h1, _ = one.solve(args.variant, b, x0, k, x_true=x_true, path="stream")
+        one.close()
+        worst = 0.0
+        for i, h in enumerate(hn):
+            rel = np.abs(hist[i] - h1[h]) / np.abs(h1[h])
+            worst = max(worst, float(rel.max()))
+        out["full_problem_vs_1gpu_max_rel"] = worst
+        out["full_problem_iterations"] = k - 1
+        out["ok"] &= bool(worst <= 1e-10)
+    flag = __import__("torch").tensor([1 if out["ok"] else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    out["ok"] = bool(flag.item())
+    return out
 
 
 def run_ours(args, rank, world, local_rank):
@@ -279,18 +383,17 @@ def run_ours(args, rank, world, local_rank):
     words = cw(top)
     bytes_per_launch = 8.0 * n_loc * words
     achieved = bytes_per_launch / (ms / cnt * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
-    except Exception:
-        pass
+    traffic, traffic_note = read_traffic(top)
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic if world == 1 else None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic if world == 1 else None, "traffic_source": traffic_note,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": ms / cnt,
                 "rows_per_launch": n_loc,
                 "share_of_loop": ms / sum(v[0] for v in prof.values()),
                 "kernels": {c: {"avg_ms": v[0] / v[1], "launches": v[1],
                                 "words_per_row": cw(c),
+                                "actual_us": 1e3 * v[0] / v[1],
+                                "ideal_us": 8.0 * n_loc * cw(c) / (peak * 1e9) * 1e6,
                                 "GBps": 8.0 * n_loc * cw(c) / (v[0] / v[1] * 1e-3) / 1e9}
                             for c, v in prof.items() if c in CLASS_WORDS}}
     # ---- the other variants on the same problem (2 solves each, resident inputs)
@@ -308,9 +411,14 @@ def run_ours(args, rank, world, local_rank):
                        "hbm_gbs_model": ips * 8 * n * W_V[v] / 1e9,
                        "pct_of_8TBs_per_gpu": 100 * ips * 8 * n * W_V[v] / 8e12 / world}
 
-    cpu = None
+    # ---- correctness of what was timed
+    dist_check = None
+    if world > 1:
+        dist_check = check_partitioned_answer(args, sess, S, b, x0, x_true, dinv, rank, world, local_rank)
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_sample(args)
+        _, dev_hist, _ = sess.solve(variant, b, x0, args.parity_iters, x_true=x_true, path=args.path)
+        cpu, parity = cpu_baseline_sample(args, dev_hist)
 
     if rank == 0:
         b_iter = 8.0 * n * W_V[variant]
@@ -328,6 +436,12 @@ def run_ours(args, rank, world, local_rank):
             "pct_of_measured_peak": 100 * value * b_iter / 1e9 / measured_peak()[0] / world,
             "roofline": roofline, "cpu_baseline": cpu, "variants": variants,
         }
+        if parity is not None:
+            line["parity"] = parity
+            line["parity_max_rel"] = parity["max_rel"]
+        if dist_check is not None:
+            line["dist_check"] = "ok" if dist_check["ok"] else "FAILED"
+            line["dist_check_detail"] = dist_check
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -362,7 +476,8 @@ def main():
     ap.add_argument("--dim", type=int, default=3, choices=[2, 3],
                     help="3: BASELINE configs[3] (default, the headline); 2 with --grid 4096: configs[2]")
     ap.add_argument("--iters", type=int, default=200, help="CG iterations per step (our arm)")
-    ap.add_argument("--ref-iters", type=int, default=3, help="CG iterations per step (reference arm)")
+    ap.add_argument("--ref-iters", type=int, default=6, help="CG iterations per step (reference arm; BASELINE.md section 2)")
+    ap.add_argument("--parity-iters", type=int, default=8, help="history entries compared with the oracle (cpu_baseline leg)")
     ap.add_argument("--cpu-iters", type=int, default=10, help="iterations of the cpu_baseline sample")
     ap.add_argument("--path", default="auto", choices=["auto", "stream", "persistent"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

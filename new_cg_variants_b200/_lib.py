@@ -97,10 +97,18 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not os.path.exists(path):
-        if not build_if_missing:
-            raise CgxError(ERR_CUDA, f"{path} is missing; run `python -m new_cg_variants_b200.build`")
+    if not os.path.exists(path) and not build_if_missing:
+        raise CgxError(ERR_CUDA, f"{path} is missing; run `python -m new_cg_variants_b200.build`")
+    # never load a binary older than its sources: rebuild when a compiler is here (a no-op when the
+    # source stamp matches), otherwise refuse a stale library
+    try:
         _build.build()
+    except RuntimeError as e:
+        if "nvcc not found" not in str(e):
+            raise
+        stamp = open(_build.STAMP).read().strip() if os.path.exists(_build.STAMP) else ""
+        if not os.path.exists(path) or stamp != _build._fingerprint():
+            raise CgxError(ERR_CUDA, f"{path} is missing or older than csrc/ and nvcc is not available to rebuild it")
     lib = C.CDLL(path)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)   # AttributeError here = ABI mismatch: fail loudly

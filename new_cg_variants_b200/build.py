@@ -64,6 +64,17 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
+def kernel_fingerprint() -> str:
+    """sha256 over the device-code sources only (profiles/traffic.json is stamped with it)."""
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith(".cuh"):
+            with open(os.path.join(CSRC, f), "rb") as fh:
+                h.update(f.encode())
+                h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     fp = _fingerprint()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP):

@@ -24,6 +24,7 @@ import numpy as np
 import scipy.sparse as sps
 
 from .. import _lib
+from .. import callbacks as _cbk
 from ..callbacks import DEVICE_HISTORIES
 from ..operators import PoissonStencil, canonical_csr
 from ..session import Session
@@ -65,6 +66,8 @@ def _fingerprint(A):
     if isinstance(A, PoissonStencil):
         return ("stencil", A.dim, A.nx, A.ny, A.nz, A.diag, A.off)
     if sps.issparse(A):
+        if A.format not in ("csr", "csc", "coo", "bsr", "dia"):
+            A = A.tocsr()                      # e.g. LIL keeps object-dtype rows
         d = A.data
         step = max(1, d.shape[0] // 4096)
         return ("sparse", A.shape, A.nnz, A.format, float(d.sum()), float(d[::step].sum()))
@@ -109,7 +112,13 @@ def _split_callbacks(callbacks):
     device, ticks, generic = [], [], []
     for cb in callbacks:
         name = getattr(cb, "__name__", "")
-        if name in DEVICE_HISTORIES:
+        # the four standard callbacks: this package's objects, or the reference's own (module
+        # `callbacks.<name>` of numerical_experiments) -- a user callable that merely shares the name
+        # is called like any other
+        mod = getattr(cb, "__module__", "") or ""
+        std = name in DEVICE_HISTORIES and (cb is getattr(_cbk, name, None) or mod.split(".")[0] == "callbacks"
+                                            or mod.endswith("callbacks." + name))
+        if std:
             device.append(name)
         elif hasattr(cb, "_cgx_print_every") or name == "pk":
             ticks.append(cb)          # print_k(K): progress only
@@ -141,9 +150,11 @@ def _solve(name, tag, A, b, x0, max_iter, preconditioner, callbacks, kwargs):
     x_true = kwargs.get("x_true")
 
     sess = own.get("session")
+    dinv = probe_preconditioner(preconditioner, n)
     if sess is None:
-        dinv = probe_preconditioner(preconditioner, n)
         sess = _session_for(A, dinv, device)
+    else:
+        sess.set_jacobi(dinv)                  # an explicit session still honours `preconditioner`
 
     if not generic:
         _, hist, info = sess.solve(tag, b, x0, max_iter, x_true=x_true, histories=tuple(dev_hist),

@@ -50,16 +50,20 @@ class GpuComm:
             self._dist.barrier(self.group)
 
 
-_SESSIONS = {}
+_SESSIONS = {}          # (id(A), size, rank) -> (A, session); holding A keeps its id from being reused
+_MAX_SESSIONS = 4
 
 
 def _operator_session(comm, A, m):
     """One resident operator per (operator, partition) -- the reference builds A once and runs
-    five variants on it (scaling_tests.py:60-66)."""
+    five variants on it (scaling_tests.py:60-66).  The cache entry keeps a strong reference to A
+    (so `id(A)` cannot be recycled by another matrix while the entry lives) and is bounded."""
     size, rank = comm.Get_size(), comm.Get_rank()
     key = (id(A), size, rank)
-    if key in _SESSIONS:
-        return _SESSIONS[key]
+    if key in _SESSIONS and _SESSIONS[key][0] is A:
+        return _SESSIONS[key][1]
+    while len(_SESSIONS) >= _MAX_SESSIONS:
+        _SESSIONS.pop(next(iter(_SESSIONS)))[1].close()
     if isinstance(A, PoissonStencil):
         if size == 1:
             sess = Session(A)
@@ -72,7 +76,7 @@ def _operator_session(comm, A, m):
         raise NotImplementedError("on several GPUs the operator must be a PoissonStencil (row-partitioned into "
                                   "slabs); general matrices -- including the reference's dense column blocks -- "
                                   "run on one rank")
-    _SESSIONS[key] = sess
+    _SESSIONS[key] = (A, sess)
     return sess
 
 
@@ -124,6 +128,6 @@ def model_problem(n, kappa=1e6, rho=0.9):
 
 
 def clear_sessions():
-    for s in _SESSIONS.values():
+    for _, s in _SESSIONS.values():
         s.close()
     _SESSIONS.clear()

@@ -778,6 +778,7 @@ static int begin_prepare(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
   c->launches_run = 0; c->loop_ms = 0.0;
   c->pend.clear();
   c->pr_fused = false; c->fpar = 0;
+  for (int ch = 0; ch < 3; ++ch) c->hepoch[ch] = std::max(c->hepoch[ch], c->fepoch);   // (LL tags stay unique)
   if ((variant == CGX_PR || variant == CGX_M) && path == CGX_PATH_STREAM && !c->no_fused) {
     int frc = cgx_fused_prepare(c);
     if (frc) return frc;
@@ -836,6 +837,10 @@ static int group_begin(cgx_ctx** cs, int count, int variant, int max_iter, unsig
       if (count > 1) cudaSetDevice(cs[i]->device);
       steps[i][s]();
     }
+  for (int i = 0; i < count; ++i) {
+    if (count > 1) cudaSetDevice(cs[i]->device);
+    cgx_fused_push_initial_halo(cs[i]);
+  }
   // k = 0 entry of the histories (the reference's callbacks fire on the initial state)
   for (int i = 0; i < count; ++i) cs[i]->cur_k = 0;
   if (cs[0]->hist_mask) {
@@ -1141,6 +1146,7 @@ extern "C" int cgx_set_stencil_slab(cgx_ctx* c, int64_t nx, int64_t ny, int64_t 
   c->peer_base[rank] = c->d_win;
   c->epoch = 0; c->scpar = 0; c->pend.clear();
   for (auto& h : c->hepoch) h = 0;
+  c->fepoch = 0;
   return CGX_OK;
 }
 

@@ -17,21 +17,26 @@ double* cgx_cur_vec(cgx_ctx* c, int v) {
 int cgx_fused_prepare(cgx_ctx* c) {
   c->pr_fused = false;
   c->fpar = 0;
-  if (c->op_kind != 2 || !c->use_tma || c->pm == 1 || c->dist.world > 1) return CGX_OK;
+  if (c->op_kind != 2 || !c->use_tma || c->pm == 1) return CGX_OK;
+  // partitioned: the records travel peer to peer (the NCCL mode keeps the two-kernel path)
+  if (c->dist.world > 1 && (c->dist.mode == 2 || !c->halo_ll)) return CGX_OK;
   const StencilOp& S = c->sten;
   for (int j = 0; j < 3; ++j) {
     if (!c->alt[j]) CU(cudaMalloc(&c->alt[j], sizeof(double) * c->n));
     if (!tma_encode_dims(c->vec[kFusedVec[j]], S.nx, S.ny, S.nz, &c->ftmap[0][j])) return CGX_OK;
     if (!tma_encode_dims(c->alt[j], S.nx, S.ny, S.nz, &c->ftmap[1][j])) return CGX_OK;
   }
+  // the LL ghost planes are shared with the other partitioned kernels (tags = epochs): keep the
+  // tags unique by starting above every epoch any of them has used
+  for (int ch = 0; ch < 3; ++ch) c->fepoch = std::max(c->fepoch, c->hepoch[ch]);
   c->pr_fused = true;
   return CGX_OK;
 }
 
-template <int PM, bool MEUR>
+template <int PM, bool MEUR, bool DIST>
 static void launch_fused_t(cgx_ctx* c, const Args& g, int cur) {
   const size_t smem = fused_smem_bytes();
-  const int per_sm = ctx_occupancy(c, (const void*)pr_fused_kernel<PM, MEUR>, kFThreads, smem);
+  const int per_sm = ctx_occupancy(c, (const void*)pr_fused_kernel<PM, MEUR, DIST>, kFThreads, smem);
   // (column, z-chunk) work units, all co-resident when the columns fit: every chunk then marches
   // in lockstep over its planes (L2 serves the halos neighbouring columns share)
   TmaGeom G = c->geom;
@@ -39,7 +44,7 @@ static void launch_fused_t(cgx_ctx* c, const Args& g, int cur) {
   G.nchunk = std::max(1, std::min(cap / std::max(1, ncols), G.nz / std::max(1, c->fused_min_planes)));
   if (c->fused_chunks > 0) G.nchunk = std::min(c->fused_chunks, G.nz);
   const int grid = (int)std::min<i64>((i64)ncols * G.nchunk, cap);
-  pr_fused_kernel<PM, MEUR><<<grid, kFThreads, smem, c->stream>>>(c->ftmap[cur][0], c->ftmap[cur][1], c->ftmap[cur][2],
+  pr_fused_kernel<PM, MEUR, DIST><<<grid, kFThreads, smem, c->stream>>>(c->ftmap[cur][0], c->ftmap[cur][1], c->ftmap[cur][2],
                                                                   G, g);
 }
 
@@ -48,12 +53,36 @@ void cgx_launch_pr_fused(cgx_ctx* c, Args g) {
   g.p = nxt ? c->alt[0] : c->vec[V_P];
   g.s = nxt ? c->alt[1] : c->vec[V_S];
   g.rt = nxt ? c->alt[2] : c->vec[V_RT];
+  const bool dist = c->dist.world > 1;
+  Plan p;
+  p.consume = true;
+  p.produce = FK_PIPE;
+  plan_apply(c, g, p);
+  if (dist) {       // LL ghost planes of p, s, rt: one epoch counter for the three channels
+    g.hin_epoch = c->fepoch; g.hin_par = (int)(g.hin_epoch & 1);
+    g.hout_epoch = c->fepoch + 1; g.hout_par = (int)(g.hout_epoch & 1);
+  }
   {
     ProfScope ps(c, PC_FUSED);
     const bool meur = c->variant == CGX_M;
-    if (c->pm == 2) { if (meur) launch_fused_t<2, true>(c, g, cur); else launch_fused_t<2, false>(c, g, cur); }
-    else { if (meur) launch_fused_t<0, true>(c, g, cur); else launch_fused_t<0, false>(c, g, cur); }
+#define CGX_FUSED_GO(PM, D) do { if (meur) launch_fused_t<PM, true, D>(c, g, cur); else launch_fused_t<PM, false, D>(c, g, cur); } while (0)
+    if (c->pm == 2) { if (dist) CGX_FUSED_GO(2, true); else CGX_FUSED_GO(2, false); }
+    else { if (dist) CGX_FUSED_GO(0, true); else CGX_FUSED_GO(0, false); }
+#undef CGX_FUSED_GO
     c->launches++;
   }
+  plan_commit(c, g, p);
+  if (dist) c->fepoch++;
   c->fpar = nxt;
+}
+
+// partitioned runs: after the initialisation, hand the boundary planes of p, s, rt to the neighbours
+void cgx_fused_push_initial_halo(cgx_ctx* c) {
+  if (!c->pr_fused || c->dist.world <= 1) return;
+  Args g = make_args(c);
+  g.d = c->dist;
+  g.hout_epoch = c->fepoch + 1; g.hout_par = (int)(g.hout_epoch & 1);
+  fused_halo_init_kernel<<<grid_for(c, c->dist.plane), kBlock, 0, c->stream>>>(g);
+  c->launches++;
+  c->fepoch++;
 }

@@ -121,6 +121,7 @@ struct cgx_ctx {
   cudaStream_t own_stream = nullptr;      // c->stream may be a group's shared stream
   u64 epoch = 0;                           // last scalar-exchange epoch produced
   u64 hepoch[kChan] = {};                  // last halo epoch produced per channel
+  u64 fepoch = 0;                          // fused PR kernel: epoch of the LL ghost planes of p, s, rt
   int scpar = 0;
   struct Pend { u64 e; int kind; int k; };
   std::vector<Pend> pend;
@@ -209,6 +210,7 @@ bool tma_encode_dims(double* ptr, i64 nx, i64 ny, i64 nz, CUtensorMap* out);
 // cgx_fused.cu
 int cgx_fused_prepare(cgx_ctx* c);              // second buffers + tensor maps; sets c->pr_fused
 void cgx_launch_pr_fused(cgx_ctx* c, Args g);   // one whole PR-CG / M-CG iteration
+void cgx_fused_push_initial_halo(cgx_ctx* c);   // partitioned runs: boundary planes of the initial p, s, rt
 double* cgx_cur_vec(cgx_ctx* c, int v);         // the buffer that currently holds state vector v
 
 void launch_halo_push(cgx_ctx* c, Args g, const double* v, int ch);

@@ -244,10 +244,11 @@ __device__ __forceinline__ void dist_totals(const Args& g, u64 e, int nr, double
 
 // Every CTA of a kernel that needs alpha/beta: fold the pending reductions into the scalars
 // (redundantly, identical bits everywhere); CTA 0 persists the result in the other parity.
-__device__ __forceinline__ void dist_scalars(const Args& g, bool meurant, double& a, double& b) {
-  __shared__ double sh_ab[2];
+// dist_fold: the warp-0 part (call with threadIdx.x < 32); the caller synchronises the CTA (or
+// its compute warps) before reading sh_ab.
+__device__ __forceinline__ void dist_fold(const Args& g, bool meurant, double* sh_ab) {
   const bool stamp = (g.dbg & 2) && blockIdx.x == 0 && threadIdx.x == 0;
-  if (threadIdx.x < 32) {
+  {
     // Peer-to-peer records: every word of every pending record is requested FIRST (lane l: value
     // l & 3 of rank l >> 2), then the persisted scalars are loaded, then the records are
     // validated, summed in rank order and folded -- one memory round trip for the whole fold
@@ -293,6 +294,10 @@ __device__ __forceinline__ void dist_scalars(const Args& g, bool meurant, double
     }
   }
   if (stamp) g.dbg_t[9] = (u64)clock64();
+}
+__device__ __forceinline__ void dist_scalars(const Args& g, bool meurant, double& a, double& b) {
+  __shared__ double sh_ab[2];
+  if (threadIdx.x < 32) dist_fold(g, meurant, sh_ab);
   __syncthreads();
   a = sh_ab[0]; b = sh_ab[1];
 }

@@ -49,7 +49,13 @@ __device__ __forceinline__ void sts2(double* p, double a, double b) { *reinterpr
 
 // PM: 0 identity, 2 Jacobi with a constant diagonal (a Jacobi VECTOR would need dinv on the halo:
 // those runs keep the two-kernel path).
-template <int PM, bool MEUR>
+// DIST: this launch is one rank of a z-slab partition (cgx_common.cuh "Row-partitioned ..."): alpha and
+// beta come from folding all ranks' records of the previous launch; the three input vectors of
+// the ghost planes z = -1 / z = nz were stored by the neighbours' previous launch into this
+// rank's window as LL words (channels 0 p, 1 s, 2 rt) and are polled by the compute warps; this
+// launch stores its own first / last plane of the new p, rt (stage 1) and s (stage 2) into the
+// neighbours' windows the moment they are computed, and ends by publishing its record.
+template <int PM, bool MEUR, bool DIST>
 __global__ void __launch_bounds__(kFThreads, 2)
 pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_s,
                 const __grid_constant__ CUtensorMap tm_rt, const TmaGeom G, const Args g) {
@@ -67,7 +73,16 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
   }
   __syncthreads();
 
-  const double a = g.sc->a, b = g.sc->b;
+  double a, b;
+  if constexpr (DIST) {
+    // only the compute warps need the scalars: the producer warp starts its copies at once
+    __shared__ double sh_ab[2];
+    if (tid < kFConsumers) {
+      if (tid < 32) dist_fold(g, MEUR, sh_ab);
+      named_bar_sync(1, kFConsumers);
+      a = sh_ab[0]; b = sh_ab[1];
+    } else { a = b = 0.0; }
+  } else { a = g.sc->a; b = g.sc->b; }
   const double ds = g.dinv_s;
   auto M = [&](double v) { return PM == 2 ? mul_(ds, v) : v; };
 
@@ -91,7 +106,8 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
         const int z0 = (int)((i64)chunk * G.nz / G.nchunk), z1 = (int)((i64)(chunk + 1) * G.nz / G.nchunk);
         const int x0 = (col % G.ntx) * kTX, y0 = (col / G.ntx) * kTY;
         const int lo = G.march_y ? z0 : max(z0 - 1, zmin), hi = G.march_y ? z1 - 1 : min(z1, zmax);
-        for (int zz = lo; zz <= hi; ++zz, ++li) {
+        for (int zz = lo; zz <= hi; ++zz) {
+          if (zz < 0 || zz >= G.nz) continue;               // ghost plane of a slab: LL words, no copy
           const int slot = li % kFStages;
           if (li >= kFStages) mbar_wait(&empty_bar[slot], ((li / kFStages) - 1) & 1u, G.err);
           double* dst = stage + (size_t)slot * 3 * kPlaneStride;
@@ -100,6 +116,7 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
           tma_load_3d(dst, &tm_p, x0 - 2, ty0 - 1, tz, &full_bar[slot]);
           tma_load_3d(dst + kPlaneStride, &tm_s, x0 - 2, ty0 - 1, tz, &full_bar[slot]);
           tma_load_3d(dst + 2 * kPlaneStride, &tm_rt, x0 - 2, ty0 - 1, tz, &full_bar[slot]);
+          ++li;
         }
       }
     }
@@ -147,7 +164,37 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
       // (xn, rn): receive plane zz+1; rnew: receives the new r of plane zz; rold: the new r of
       // plane zz-1 (written by the previous step), for the dots of the stencil stage.
       auto plane_step = [&](const int zz, Set& xc, Set& rc, Set& xn, Set& rn, Set& rnew, Set& rold) {
-        if (zz <= hi) {
+        if (DIST && zz <= hi && (zz < 0 || zz >= G.nz)) {
+          // ghost plane: p, s, rt of the tile from the LL words the neighbour stored (no xy halo needed)
+          if (zz + 1 >= z0 && zz + 1 < z1) fetch_xr(zz + 1, xn, rn);
+          double* pn = ring + (size_t)(zz & (kFRing - 1)) * kPlaneStride;
+          const int side = zz < 0 ? 0 : 1;
+          int* err = &g.d.win[g.d.rank]->error;
+          const bool oky = ybase < G.ny;
+#pragma unroll
+          for (int j = 0; j < kFPairs; ++j) {
+            const int c = (ly + 1) * kPX + 2 * lx + 64 * j + 2;
+            double pnw[2] = {0.0, 0.0};
+            if (oky && okx[j] && !(g.dbg & 1)) {
+              const int e = idx0 + 64 * j;                  // element of the plane (march_y is never a slab)
+              LLReq rq[3][2];
+#pragma unroll
+              for (int v = 0; v < 3; ++v)
+#pragma unroll
+                for (int l = 0; l < 2; ++l) {
+                  rq[v][l].src = g.d.ghl + ghl_off(g.d, v, g.hin_par, side) + 2 * (size_t)(e + l);
+                  ll_issue(rq[v][l]);
+                }
+#pragma unroll
+              for (int l = 0; l < 2; ++l) {
+                const double po = ll_finish(rq[0][l], g.hin_epoch, err), so = ll_finish(rq[1][l], g.hin_epoch, err),
+                             rto = ll_finish(rq[2][l], g.hin_epoch, err);
+                pnw[l] = axpy_(axmy_(rto, a, M(so)), b, po);
+              }
+            }
+            sts2(pn + c, pnw[0], pnw[1]);
+          }
+        } else if (zz <= hi) {
           const bool fullp = zz >= z0 && zz < z1;          // a plane this CTA owns (else: only its new p)
           if (zz + 1 >= z0 && zz + 1 < z1) fetch_xr(zz + 1, xn, rn);
           const int slot = li % kFStages;
@@ -183,6 +230,25 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
               *reinterpret_cast<double2*>(g.r + i) = make_double2(rnew[j][0], rnew[j][1]);
               *reinterpret_cast<double2*>(g.rt + i) = make_double2(rtn[0], rtn[1]);
               *reinterpret_cast<double2*>(g.p + i) = make_double2(pnw[0], pnw[1]);
+              if constexpr (DIST) {
+                if (!(g.dbg & 1)) {
+                  const int e = idx0 + 64 * j;
+                  if (zz == 0 && g.d.has_lo) {
+#pragma unroll
+                    for (int l = 0; l < 2; ++l) {
+                      ll_store(g.d.ghl_lo + ghl_off(g.d, 0, g.hout_par, 1) + 2 * (size_t)(e + l), pnw[l], g.hout_epoch);
+                      ll_store(g.d.ghl_lo + ghl_off(g.d, 2, g.hout_par, 1) + 2 * (size_t)(e + l), rtn[l], g.hout_epoch);
+                    }
+                  }
+                  if (zz == G.nz - 1 && g.d.has_hi) {
+#pragma unroll
+                    for (int l = 0; l < 2; ++l) {
+                      ll_store(g.d.ghl_hi + ghl_off(g.d, 0, g.hout_par, 0) + 2 * (size_t)(e + l), pnw[l], g.hout_epoch);
+                      ll_store(g.d.ghl_hi + ghl_off(g.d, 2, g.hout_par, 0) + 2 * (size_t)(e + l), rtn[l], g.hout_epoch);
+                    }
+                  }
+                }
+              }
             }
           }
           if (fullp) {
@@ -245,6 +311,21 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
                 red[2] = fma(sti, acc, red[2]);
               }
               *reinterpret_cast<double2*>(g.s + ib + 64 * j) = make_double2(y[0], y[1]);
+              if constexpr (DIST) {
+                if (!(g.dbg & 1)) {
+                  const int e = idx0 + 64 * j;
+                  if (q == 0 && g.d.has_lo) {
+#pragma unroll
+                    for (int l = 0; l < 2; ++l)
+                      ll_store(g.d.ghl_lo + ghl_off(g.d, 1, g.hout_par, 1) + 2 * (size_t)(e + l), y[l], g.hout_epoch);
+                  }
+                  if (q == G.nz - 1 && g.d.has_hi) {
+#pragma unroll
+                    for (int l = 0; l < 2; ++l)
+                      ll_store(g.d.ghl_hi + ghl_off(g.d, 1, g.hout_par, 0) + 2 * (size_t)(e + l), y[l], g.hout_epoch);
+                  }
+                }
+              }
             }
           }
         }
@@ -261,8 +342,24 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
 
   // {mu, delta, gamma, nu} -> a, b of the next iteration (pr_cg.py:154-158 then :149-150)
   grid_sum_finalize<4>(red, g.partials, g.ticket, [&](const double* acc) {
-    apply_finalize(FK_PIPE, MEUR, g.sc, acc, g.k);
+    if constexpr (DIST) dist_publish<4>(g, acc);
+    else apply_finalize(FK_PIPE, MEUR, g.sc, acc, g.k);
   }, false);
+}
+
+// Partitioned runs, once per solve after the initialisation: the boundary planes of p, s, rt as LL
+// words into the neighbours' windows (what every later launch does for the planes it computes).
+static __global__ void __launch_bounds__(kBlock) fused_halo_init_kernel(const Args g) {
+  const i64 pl = g.d.plane;
+  const double* src[3] = {g.p, g.s, g.rt};
+  const i64 stride = (i64)gridDim.x * kBlock;
+  for (i64 i = (i64)blockIdx.x * kBlock + threadIdx.x; i < pl; i += stride) {
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      if (g.d.has_lo) ll_store(g.d.ghl_lo + ghl_off(g.d, v, g.hout_par, 1) + 2 * i, src[v][i], g.hout_epoch);
+      if (g.d.has_hi) ll_store(g.d.ghl_hi + ghl_off(g.d, v, g.hout_par, 0) + 2 * i, src[v][g.n - pl + i], g.hout_epoch);
+    }
+  }
 }
 
 }  // namespace cgx

@@ -128,13 +128,19 @@ def _lanes8_dot(u, v):
     return (t[:m].reshape(-1, 8).sum(axis=0).sum() + t[m:].sum()) if m else t.sum()
 
 
+def _strided_dot(u, v):
+    t = u * v                                # 1024 strided sequential partials, then a tree: the shape of a
+    m = (t.shape[0] // 1024) * 1024          # grid-stride GPU reduction
+    return (t[:m].reshape(-1, 1024).sum(axis=0).sum() + t[m:].sum()) if m else t.sum()
+
+
 def _extended_dot(u, v):
     return float(u.astype(np.longdouble) @ v.astype(np.longdouble))   # nearly exact
 
 
 # alternative summation orders for the rounding-sensitivity ensemble
 DOT_ORDERS = {"blas": _blas_dot, "pairwise": _pairwise_dot, "reversed": _reversed_dot,
-              "lanes8": _lanes8_dot, "extended": _extended_dot}
+              "lanes8": _lanes8_dot, "strided1024": _strided_dot, "extended": _extended_dot}
 
 
 def solve(variant, A, b, x0, max_iter, dinv=None, x_true=None, history=True, return_state=False,

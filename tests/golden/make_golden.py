@@ -48,24 +48,69 @@ from oracle import cg_oracle as orc          # noqa: E402
 
 REF_FUN = {tag: getattr(ref_solvers, name) for tag, name in orc.VARIANTS.items()}
 
-# (case name, matrix source, max_iter, preconditioner) -- max_iter from figure_gen.py:247-315
+# (case name, matrix source, max_iter, preconditioner, tier) -- max_iter from figure_gen.py:247-315;
+# every (matrix, preconditioner) of that list whose matrix is in matrices/ is here.
+#   tier "full"    : all four histories of all nine variants + exact_pcg are stored
+#   tier "prefix"  : same reference runs; stored are the windows/bands and the first entries of the
+#                    two residual histories (enough for P1) -- keeps the fixture file small
+#   tier "metrics" : long runs (>= 5000 iterations): no exact_pcg (its re-orthogonalisation is
+#                    O(k^2 n)); stored are the reference's summary metrics (figure_gen.py:80-89),
+#                    live and from its stored data/<case>/*.npy, and the ensemble bands
 CASES = [
-    ("bcsstk03_jacobi", "bcsstk03", 250, "jacobi"),
-    ("bcsstk03_None", "bcsstk03", 1250, None),
-    ("nos4_jacobi", "nos4", 120, "jacobi"),
-    ("nos4_None", "nos4", 150, None),
-    ("model_48_8_3_None", "model_48_8_3", 110, None),
-    ("model_48_8_3_jacobi", "model_48_8_3", 200, "jacobi"),
-    ("494_bus_jacobi", "494_bus", 500, "jacobi"),
-    ("bcsstm22_None", "bcsstm22", 85, None),
-    ("nos6_jacobi", "nos6", 130, "jacobi"),
-    ("bcsstk15_jacobi", "bcsstk15", 830, "jacobi"),
-    ("poisson_ca_jacobi", "poisson_ca", 60, "jacobi"),
-    ("poisson2d_32_jacobi", ("poisson2d", 32), 120, "jacobi"),
-    ("poisson2d_128_jacobi", ("poisson2d", 128), 420, "jacobi"),
-    ("poisson3d_12_jacobi", ("poisson3d", 12), 60, "jacobi"),
-    ("poisson3d_32_None", ("poisson3d", 32), 130, None),
+    ("bcsstk03_jacobi", "bcsstk03", 250, "jacobi", "full"),
+    ("bcsstk03_None", "bcsstk03", 1250, None, "full"),
+    ("nos4_jacobi", "nos4", 120, "jacobi", "full"),
+    ("nos4_None", "nos4", 150, None, "full"),
+    ("model_48_8_3_None", "model_48_8_3", 110, None, "full"),
+    ("model_48_8_3_jacobi", "model_48_8_3", 200, "jacobi", "full"),
+    ("494_bus_jacobi", "494_bus", 500, "jacobi", "full"),
+    ("bcsstm22_None", "bcsstm22", 85, None, "full"),
+    ("nos6_jacobi", "nos6", 130, "jacobi", "full"),
+    ("bcsstk15_jacobi", "bcsstk15", 830, "jacobi", "full"),
+    ("poisson_ca_jacobi", "poisson_ca", 60, "jacobi", "full"),
+    ("poisson2d_32_jacobi", ("poisson2d", 32), 120, "jacobi", "full"),
+    ("poisson2d_128_jacobi", ("poisson2d", 128), 420, "jacobi", "full"),
+    ("poisson3d_12_jacobi", ("poisson3d", 12), 60, "jacobi", "full"),
+    ("poisson3d_32_None", ("poisson3d", 32), 130, None, "full"),
+    # ---- the rest of figure_gen.py:247-315
+    ("bcsstk14_jacobi", "bcsstk14", 800, "jacobi", "prefix"),
+    ("bcsstk16_jacobi", "bcsstk16", 320, "jacobi", "prefix"),
+    ("bcsstk18_jacobi", "bcsstk18", 2700, "jacobi", "prefix"),
+    ("bcsstk27_jacobi", "bcsstk27", 380, "jacobi", "prefix"),
+    ("bcsstk16_None", "bcsstk16", 900, None, "prefix"),
+    ("bcsstk27_None", "bcsstk27", 2300, None, "prefix"),
+    ("nos1_jacobi", "nos1", 900, "jacobi", "prefix"),
+    ("nos3_jacobi", "nos3", 350, "jacobi", "prefix"),
+    ("nos5_jacobi", "nos5", 350, "jacobi", "prefix"),
+    ("nos7_jacobi", "nos7", 200, "jacobi", "prefix"),
+    ("nos1_None", "nos1", 4500, None, "prefix"),
+    ("nos3_None", "nos3", 400, None, "prefix"),
+    ("nos5_None", "nos5", 600, None, "prefix"),
+    ("nos6_None", "nos6", 2400, None, "prefix"),
+    ("bcsstm19_None", "bcsstm19", 1100, None, "prefix"),
+    ("bcsstm20_None", "bcsstm20", 700, None, "prefix"),
+    ("bcsstm21_None", "bcsstm21", 10, None, "prefix"),
+    ("494_bus_None", "494_bus", 2500, None, "prefix"),
+    ("662_bus_None", "662_bus", 1200, None, "prefix"),
+    ("685_bus_None", "685_bus", 950, None, "prefix"),
+    ("662_bus_jacobi", "662_bus", 350, "jacobi", "prefix"),
+    ("685_bus_jacobi", "685_bus", 350, "jacobi", "prefix"),
+    ("1138_bus_jacobi", "1138_bus", 1300, "jacobi", "prefix"),
+    ("bcsstk14_None", "bcsstk14", 25000, None, "metrics"),
+    ("bcsstk15_None", "bcsstk15", 35000, None, "metrics"),
+    ("bcsstk18_None", "bcsstk18", 1750000, None, "metrics"),
+    ("nos2_jacobi", "nos2", 11000, "jacobi", "metrics"),
+    ("nos2_None", "nos2", 45000, None, "metrics"),
+    ("nos7_None", "nos7", 7000, None, "metrics"),
+    ("bcsstm23_None", "bcsstm23", 10000, None, "metrics"),
+    ("bcsstm24_None", "bcsstm24", 45000, None, "metrics"),
+    ("bcsstm25_None", "bcsstm25", 130000, None, "metrics"),
+    ("1138_bus_None", "1138_bus", 5000, None, "metrics"),
 ]
+# cases too long for a live reference run here (hours of interpreter time): only the reference's own
+# stored results (data/<case>/*.npy where present, convergence_table_data.tex) pin them
+STORED_ONLY = {"bcsstk18_None", "bcsstm25_None"}
+PREFIX_EXTRA = 16
 
 
 def load_mtx(name):
@@ -109,7 +154,7 @@ def load_npz_matrix(path):
     return A
 
 
-def run_reference(A, max_iter, prec_name):
+def run_reference(A, max_iter, prec_name, with_exact=True):
     """figure_gen.py:31-60 without the file I/O."""
     n = A.shape[0]
     x_true = np.ones(n) / np.sqrt(n)
@@ -125,6 +170,8 @@ def run_reference(A, max_iter, prec_name):
     res = {}
     for tag, fun in REF_FUN.items():
         res[tag] = fun(A, b, x0, max_iter, callbacks=cbs, x_true=x_true, preconditioner=prec)
+    if not with_exact:
+        return res
     with contextlib.redirect_stdout(io.StringIO()):
         res["exact"] = ref_solvers.exact_pcg(
             A.astype(np.longdouble), b.astype(np.longdouble), x0.astype(np.longdouble),
@@ -145,29 +192,48 @@ def rounding_band(tag, A, b, x0, max_iter, dinv, x_true, ref, exact):
     products changes?  (CG amplifies O(eps) differences.)  Returns
 
       kstar10 / kstar12 : first k where the reference leaves exact_pcg by 1e-10 / 1e-12
-      window            : iterations over which every summation order still agrees with the
-                          reference to 1e-10 on both residual histories, capped by kstar12 --
-                          the range where "agree to 1e-10" is a property of the algorithm and
-                          not of one BLAS build
+                          (the contract's k*, north_star: "until the reference curve departs from
+                          exact arithmetic"); None when exact_pcg was not run (tier "metrics")
+      ensemble          : iterations over which every other summation order (oracle.DOT_ORDERS)
+                          still agrees with the reference to 1e-10 on both residual histories
+      window            : min(kstar10, ensemble) -- the range over which "agree to 1e-10" is a
+                          property of the algorithm and not of one BLAS build (P1 of tests/helpers.py)
       iters_band/acc_band : [min, max] over the ensemble of the two figure_gen.py:80-89
                           summary metrics (iterations to 1e-5, log10 attainable accuracy)
     """
     hists = ("updated_residual_2_norm", "residual_2_norm")
-    k10 = min(orc.departure_index(ref[h], exact[h], 1e-10) for h in hists)
-    k12 = min(orc.departure_index(ref[h], exact[h], 1e-12) for h in hists)
-    window = k12
+    k10 = k12 = None
+    if exact is not None:
+        k10 = int(min(orc.departure_index(ref[h], exact[h], 1e-10) for h in hists))
+        k12 = int(min(orc.departure_index(ref[h], exact[h], 1e-12) for h in hists))
+    ens = max_iter
     iters, accs = [], []
     for name, dot in orc.DOT_ORDERS.items():
         o = orc.solve(tag, A, b, x0, max_iter, dinv=dinv, x_true=x_true, dot=dot)
         if name != "blas":
-            window = min(window, min(first_deviation(o[h], np.asarray(ref[h], dtype=np.float64))
-                                     for h in hists))
+            ens = min(ens, min(first_deviation(o[h], np.asarray(ref[h], dtype=np.float64)) for h in hists))
         it, acc = orc.convergence_metrics(o["error_A_norm"])
         iters.append(it)
         accs.append(acc)
-    return {"kstar10": int(k10), "kstar12": int(k12), "window": int(window),
+    window = ens if k10 is None else min(k10, ens)
+    return {"kstar10": k10, "kstar12": k12, "ensemble": int(ens), "window": int(window),
             "iters_band": [int(min(iters)), int(max(iters))],
             "acc_band": [float(min(accs)), float(max(accs))]}
+
+
+def stored_metrics(case):
+    """figure_gen.py:80-89 metrics of the reference's own stored runs data/<case>/<method>.npy
+    (2019, numpy/MKL) -- None where the blob is missing (.MISSING_LARGE_BLOBS)."""
+    out = {}
+    for tag, name in orc.VARIANTS.items():
+        path = os.path.join(REF, "numerical_experiments/data", case, name + ".npy")
+        try:
+            d = np.load(path, allow_pickle=True).item()
+            it, acc = orc.convergence_metrics(np.asarray(d["error_A_norm"], dtype=np.float64))
+            out[tag] = [int(it), float(acc)]
+        except Exception:
+            out[tag] = None
+    return out
 
 
 def parse_table():
@@ -223,35 +289,73 @@ def mpi_kats():
     return out
 
 
+def do_case(spec):
+    case, src, max_iter, prec, tier = spec
+    import time
+    t0 = time.time()
+    A = get_matrix(src)
+    meta = {"matrix": src if isinstance(src, str) else list(src), "max_iter": max_iter,
+            "preconditioner": prec, "n": int(A.shape[0]), "nnz": int(A.nnz), "tier": tier,
+            "stored_metrics": stored_metrics(case)}
+    hist = {}
+    if case in STORED_ONLY:
+        meta["kstar"] = None
+        return case, meta, hist, time.time() - t0
+    res = run_reference(A, max_iter, prec, with_exact=(tier != "metrics"))
+    x_true, b, x0 = orc.setup_problem(A)
+    dinv = orc.jacobi_dinv(A) if prec == "jacobi" else None
+    kstar, refm = {}, {}
+    for tag in orc.VARIANTS:
+        o = orc.solve(tag, A, b, x0, max_iter, dinv=dinv, x_true=x_true)
+        assert o["name"] == res[tag]["name"]
+        for h in orc.HISTORIES:
+            ref_h = np.asarray(res[tag][h], dtype=np.float64)
+            if not np.array_equal(o[h], ref_h, equal_nan=True):
+                bad = np.nonzero(o[h] != ref_h)[0]
+                raise AssertionError(f"oracle != reference: {case} {tag} {h} first at k={bad[0]}")
+        kstar[tag] = rounding_band(tag, A, b, x0, max_iter, dinv, x_true, res[tag], res.get("exact"))
+        refm[tag] = [int(v) if i == 0 else float(v)
+                     for i, v in enumerate(orc.convergence_metrics(np.asarray(res[tag]["error_A_norm"], dtype=np.float64)))]
+        if tier == "full":
+            for h in orc.HISTORIES:
+                hist[f"{case}/{tag}/{h}"] = np.asarray(res[tag][h], dtype=np.float64)
+        elif tier == "prefix":
+            m = min(max_iter, kstar[tag]["window"] + PREFIX_EXTRA)
+            for h in ("updated_residual_2_norm", "residual_2_norm"):
+                hist[f"{case}/{tag}/{h}"] = np.asarray(res[tag][h], dtype=np.float64)[:m]
+    if tier == "full":
+        for h in orc.HISTORIES:
+            hist[f"{case}/exact/{h}"] = np.asarray(res["exact"][h], dtype=np.float64)
+    meta["kstar"] = kstar
+    meta["ref_metrics"] = refm
+    return case, meta, hist, time.time() - t0
+
+
 def main():
+    import multiprocessing as mp
+    only = set(sys.argv[1:])
     convert_matrices()
     hist = {}
     meta = {}
-    for case, src, max_iter, prec in CASES:
-        A = get_matrix(src)
-        res = run_reference(A, max_iter, prec)
-        x_true, b, x0 = orc.setup_problem(A)
-        dinv = orc.jacobi_dinv(A) if prec == "jacobi" else None
-        kstar = {}
-        for tag in orc.VARIANTS:
-            o = orc.solve(tag, A, b, x0, max_iter, dinv=dinv, x_true=x_true)
-            assert o["name"] == res[tag]["name"]
-            for h in orc.HISTORIES:
-                ref_h = np.asarray(res[tag][h], dtype=np.float64)
-                if not np.array_equal(o[h], ref_h, equal_nan=True):
-                    bad = np.nonzero(o[h] != ref_h)[0]
-                    raise AssertionError(f"oracle != reference: {case} {tag} {h} first at k={bad[0]}")
-                hist[f"{case}/{tag}/{h}"] = ref_h
-            kstar[tag] = rounding_band(tag, A, b, x0, max_iter, dinv, x_true, res[tag], res["exact"])
-        for h in orc.HISTORIES:
-            hist[f"{case}/exact/{h}"] = np.asarray(res["exact"][h], dtype=np.float64)
-        meta[case] = {"matrix": src if isinstance(src, str) else list(src), "max_iter": max_iter,
-                      "preconditioner": prec, "n": int(A.shape[0]), "nnz": int(A.nnz), "kstar": kstar}
-        print(f"case {case:22s} oracle == reference bit-for-bit; window = { {t: v['window'] for t, v in kstar.items()} }")
+    todo = [c for c in CASES if not only or c[0] in only]
+    if only:                                   # partial regeneration: keep the other cases
+        meta = json.load(open(os.path.join(HERE, "cases.json")))
+        old = np.load(os.path.join(HERE, "histories.npz"))
+        hist = {k: old[k] for k in old.files if k.split("/")[0] not in only}
+    # longest first, one process per case
+    todo.sort(key=lambda c: -c[2] * (1 if c[4] == "metrics" else 3))
+    with mp.Pool(min(8, len(todo))) as pool:
+        for case, m, h, dt in pool.imap_unordered(do_case, todo):
+            meta[case] = m
+            hist.update(h)
+            w = {t: v["window"] for t, v in m["kstar"].items()} if m["kstar"] else "stored results only"
+            print(f"case {case:22s} [{m['tier']:7s}] {dt:7.1f}s oracle == reference bit-for-bit; window = {w}", flush=True)
+    meta = {c[0]: meta[c[0]] for c in CASES if c[0] in meta}
     np.savez_compressed(os.path.join(HERE, "histories.npz"), **hist)
     json.dump(meta, open(os.path.join(HERE, "cases.json"), "w"), indent=1)
     json.dump(parse_table(), open(os.path.join(HERE, "table.json"), "w"), indent=1)
-    json.dump(mpi_kats(), open(os.path.join(HERE, "mpi_kat.json"), "w"), indent=1)
+    if not only:
+        json.dump(mpi_kats(), open(os.path.join(HERE, "mpi_kat.json"), "w"), indent=1)
     print("golden fixtures written to", HERE)
 
 

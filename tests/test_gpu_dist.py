@@ -144,3 +144,37 @@ def test_partitioned_persistent_kernel(shape, world):
             assert all(s == sc[0] for s in sc)
         finally:
             grp.close()
+
+
+@pytest.mark.parametrize("shape,world", [((16, 12, 8), 2), ((130, 10, 9), 3), ((258, 9, 12), 4), ((20, 18, 16), 8),
+                                         ((32, 6, 3), 3), ((128, 8, 5), 4), ((256, 16, 24), 2)])
+def test_partitioned_pr_fused_equals_two_kernel_path(shape, world):
+    """PR-CG / M-CG on a partition run the single-launch kernel too (ghost planes of p, s, r~ as LL
+    words, polled by the compute warps; boundary planes pushed the moment they are computed).
+    After one loop trip x equals the partitioned two-kernel path BIT FOR BIT; afterwards only the
+    summation order of the dots differs."""
+    nx, ny, nz = shape
+    S = PoissonStencil(nx, ny, nz, dim=3)
+    x_true, b, x0 = _problem(S)
+    for dinv in (1 / S.diagonal(), None):
+        res = {}
+        for fused in (1, 0):
+            grp = GroupSession(S, world, dinv=dinv)
+            try:
+                for m in grp.members:
+                    m.set_option("pr_fused", fused)
+                for tag in ("pr", "m"):
+                    x1, _, infos = grp.solve(tag, b, x0, 2, x_true=x_true)
+                    xk, hk, infos = grp.solve(tag, b, x0, 16, x_true=x_true)
+                    xk2, hk2, _ = grp.solve(tag, b, x0, 16, x_true=x_true)
+                    assert np.array_equal(xk, xk2)
+                    res[(fused, tag)] = (x1, xk, hk, sum(i["kernel_launches"] for i in infos))
+            finally:
+                grp.close()
+        for tag in ("pr", "m"):
+            f, t = res[(1, tag)], res[(0, tag)]
+            assert f[3] < t[3], "the fused kernel did not run"
+            assert np.array_equal(f[0], t[0]), (shape, world, tag)
+            np.testing.assert_allclose(f[1], t[1], rtol=1e-9, atol=1e-13)
+            for h in orc.HISTORIES:
+                np.testing.assert_allclose(f[2][h][:12], t[2][h][:12], rtol=1e-10, err_msg=f"{shape}x{world}/{tag}/{h}")

@@ -1,6 +1,9 @@
 """GPU (-m gpu): parity of the CUDA path, called through the reference-shaped Python
 functions and the C ABI, against the oracle run live on the same inputs and against the
 golden fixtures.  Nothing here reads /root/reference."""
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -61,12 +64,16 @@ def _device_solve(tag, A, b, x0, max_iter, dinv, x_true, **kw):
 
 
 @pytest.mark.parametrize("path", ["stream", "persistent"])
-@pytest.mark.parametrize("case", list(helpers.cases()))
+@pytest.mark.parametrize("case", helpers.cases_of("full", "prefix"))
 def test_variants_match_oracle_and_goldens(case, path):
-    """Every variant on every fixture, through both execution paths: `stream` (2-3 fused
-    kernels per iteration) and `persistent` (one cooperative launch for the whole solve)."""
+    """Every variant on every figure_gen.py case short enough for a live oracle run, through both
+    execution paths: `stream` (1-3 fused kernels per iteration) and `persistent` (one cooperative
+    launch for the whole solve).  P1-P3 against the oracle run live and against the stored
+    reference histories (whole histories for tier "full", their first entries for tier "prefix")."""
     A, b, x0, x_true, dinv, max_iter = helpers.case_problem(case)
-    bands = helpers.cases()[case]["kstar"]
+    meta = helpers.cases()[case]
+    bands = meta["kstar"]
+    full = helpers.tier(case) == "full"
     report = []
     for tag in ALL_TAGS:
         dev = _device_solve(tag, A, b, x0, max_iter, dinv, x_true, path=path, return_info=True)
@@ -74,16 +81,54 @@ def test_variants_match_oracle_and_goldens(case, path):
         assert dev["_info"]["kernel_launches"] > 0
         assert dev["name"] == orc.VARIANTS[tag] and dev["max_iter"] == max_iter
         live = orc.solve(tag, A, b, x0, max_iter, dinv=dinv, x_true=x_true)
-        gold = {h: helpers.golden_history(case, tag, h) for h in orc.HISTORIES}
         for h in orc.HISTORIES:
             assert dev[h].shape == (max_iter,)
             # k = 0: one reduction, no recurrence yet -> agreement at rounding level
             np.testing.assert_allclose(dev[h][:1], live[h][:1], rtol=1e-13, err_msg=f"{case}/{tag}/{h}")
-        it, acc = helpers.check_parity(dev, live, bands[tag], f"{case}/{tag} vs live oracle")
-        helpers.check_parity(dev, gold, bands[tag], f"{case}/{tag} vs golden")
         kd = min(helpers.first_deviation(dev[h], live[h]) for h in helpers.RESIDUAL_HISTS)
+        it, acc = orc.convergence_metrics(dev["error_A_norm"])
+        helpers.log_kd(case=case, variant=tag, path=path, kd=kd, window=bands[tag]["window"],
+                       kstar10=bands[tag]["kstar10"], ensemble=bands[tag].get("ensemble"), max_iter=max_iter,
+                       iters=it, acc=acc, iters_band=bands[tag]["iters_band"], acc_band=bands[tag]["acc_band"])
+        helpers.check_parity(dev, live, bands[tag], f"{case}/{tag} vs live oracle")
+        gold = {h: helpers.golden_history(case, tag, h) for h in (orc.HISTORIES if full else helpers.RESIDUAL_HISTS)}
+        helpers.check_window(dev, gold, bands[tag], f"{case}/{tag} vs golden")
         report.append(f"{tag}: agree<1e-10 to k={kd} (window {bands[tag]['window']}, k*10 {bands[tag]['kstar10']}) it={it} acc={acc:.2f}")
     print(f"\n[{case}/{path}] " + " | ".join(report))
+
+
+@pytest.mark.parametrize("case", helpers.cases_of("metrics"))
+def test_long_runs_match_reference_metrics(case):
+    """The long figure_gen.py cases (5 000 ... 1 750 000 iterations; the persistent kernel runs each
+    solve in one launch).  No oracle run here (minutes of interpreter time each): P2 / P3 against
+    the band the reference itself spans under re-ordered inner products (make_golden.py ran it),
+    P1 against the stored window prefix is not applicable (tier "metrics" stores no histories);
+    bcsstk18_None / bcsstm25_None are pinned only by the reference's own stored results."""
+    A, b, x0, x_true, dinv, max_iter = helpers.case_problem(case)
+    meta = helpers.cases()[case]
+    tags = ALL_TAGS if max_iter <= 200_000 else ["hs", "pr", "pipe_pr"]
+    table = json.load(open(os.path.join(helpers.GOLDEN, "table.json"))).get(case)
+    cols = ["hs", "cg", "m", "pr", "gv", "pipe_pr_m", "pipe_pr"]          # figure_gen.py:360
+    for tag in tags:
+        dev = _device_solve(tag, A, b, x0, max_iter, dinv, x_true, return_info=True)
+        assert dev["_info"]["path"] == 2                                   # latency-bound: persistent kernel
+        it, acc = orc.convergence_metrics(dev["error_A_norm"])
+        band = meta["kstar"][tag] if meta["kstar"] else None
+        stored = (meta.get("stored_metrics") or {}).get(tag)
+        pub = (table["iters"][cols.index(tag)], table["acc"][cols.index(tag)]) if table and tag in cols else None
+        helpers.log_kd(case=case, variant=tag, path="persistent", kd=None, window=None, kstar10=None, ensemble=None,
+                       max_iter=max_iter, iters=it, acc=acc, iters_band=band and band["iters_band"],
+                       acc_band=band and band["acc_band"], stored=stored, published=pub)
+        if band:
+            helpers.check_metrics(dev, band, f"{case}/{tag}")
+        for src, ref in (("stored .npy", stored), ("published table", pub)):
+            if ref is None:
+                continue
+            # coarse regression against the reference's 2019 runs (SURVEY.md section 8c): attainable
+            # accuracy within one decade, iterations-to-1e-5 within 5 % when both reached it
+            assert abs(acc - ref[1]) <= 1.0, (case, tag, src, acc, ref)
+            if ref[0] and it:
+                assert abs(it - ref[0]) <= max(3, 0.05 * ref[0]), (case, tag, src, it, ref)
 
 
 def test_unpreconditioned_twins_and_names():

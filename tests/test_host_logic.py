@@ -43,10 +43,16 @@ def test_callback_classification():
     assert dev == ["error_A_norm", "residual_2_norm", "error_2_norm", "updated_residual_2_norm"]
     assert len(ticks) == 1 and generic == [save_x]
 
-    def error_A_norm_like(**kw):      # a foreign callable with a reference name also maps
-        pass
+    def error_A_norm_like(**kw):      # a user callable that merely shares a reference name is CALLED,
+        pass                          # not replaced by the device history
     error_A_norm_like.__name__ = "error_A_norm"
-    assert _split_callbacks([error_A_norm_like])[0] == ["error_A_norm"]
+    dev, ticks, generic = _split_callbacks([error_A_norm_like])
+    assert dev == [] and generic == [error_A_norm_like]
+    # the reference's own callback objects (module `callbacks.error_A_norm`) do map
+    import types
+    ref_cb = types.FunctionType(error_A_norm_like.__code__, {}, "error_A_norm")
+    ref_cb.__module__ = "callbacks.error_A_norm"
+    assert _split_callbacks([ref_cb])[0] == ["error_A_norm"]
 
 
 def test_host_callbacks_follow_reference_protocol():

@@ -9,7 +9,8 @@ import pytest
 import helpers
 from helpers import orc
 
-FAST_CASES = [c for c, m in helpers.cases().items() if m["n"] * m["max_iter"] <= 1_000_000]
+FAST_CASES = [c for c, m in helpers.cases().items() if m["n"] * m["max_iter"] <= 1_000_000 and helpers.tier(c) == "full"]
+PREFIX_FAST = [c for c, m in helpers.cases().items() if helpers.tier(c) == "prefix" and m["n"] * m["max_iter"] <= 400_000]
 
 
 @pytest.mark.parametrize("case", FAST_CASES)
@@ -26,6 +27,31 @@ def test_oracle_matches_reference_goldens(case):
         helpers.check_parity(out, ref, helpers.cases()[case]["kstar"][tag], f"{case}/{tag}")
         exact_bits += all(np.array_equal(out[h], ref[h], equal_nan=True) for h in orc.HISTORIES)
     print(f"{case}: {exact_bits}/9 variants bit-identical to the stored reference run")
+
+
+@pytest.mark.parametrize("case", PREFIX_FAST)
+def test_oracle_matches_reference_prefixes(case):
+    """The figure_gen.py cases stored as prefixes: the oracle reproduces the stored start of both
+    residual histories (P1) and the reference's summary metrics of the same run."""
+    A, b, x0, x_true, dinv, max_iter = helpers.case_problem(case)
+    meta = helpers.cases()[case]
+    for tag in ("hs", "pr", "pipe_pr", "gv"):
+        out = orc.solve(tag, A, b, x0, max_iter, dinv=dinv, x_true=x_true)
+        ref = {h: helpers.golden_history(case, tag, h) for h in helpers.RESIDUAL_HISTS}
+        helpers.check_window(out, ref, meta["kstar"][tag], f"{case}/{tag}")
+        helpers.check_metrics(out, meta["kstar"][tag], f"{case}/{tag}")
+
+
+def test_every_figure_gen_case_has_a_fixture():
+    """figure_gen.py:247-315 restricted to the matrices present: 43 (matrix, preconditioner) pairs."""
+    c = helpers.cases()
+    listed = [k for k in c if not k.startswith("poisson")]
+    assert len(listed) == 43
+    assert sum(helpers.tier(k) == "metrics" for k in c) == 10
+    for k, m in c.items():
+        if m["kstar"] is not None:
+            for tag, band in m["kstar"].items():
+                assert band["window"] == (band["ensemble"] if band["kstar10"] is None else min(band["kstar10"], band["ensemble"]))
 
 
 def test_goldens_match_reference_first_values():
