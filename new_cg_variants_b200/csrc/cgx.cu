@@ -75,6 +75,7 @@ static void free_problem(cgx_ctx* c) {
 static void free_state(cgx_ctx* c) {
   for (int i = 0; i < V_COUNT; ++i) { cudaFree(c->vec[i]); c->vec[i] = nullptr; }
   for (auto& q : c->alt) { cudaFree(q); q = nullptr; }
+  cudaFree(c->d_gscr); c->d_gscr = nullptr;
   for (auto& pp : c->d_exp) for (auto& q : pp) { cudaFree(q); q = nullptr; }
   cudaFree(c->d_hist); c->d_hist = nullptr; c->hist_len = 0;
   c->ran = false;

@@ -29,6 +29,7 @@ int cgx_fused_prepare(cgx_ctx* c) {
   // the LL ghost planes are shared with the other partitioned kernels (tags = epochs): keep the
   // tags unique by starting above every epoch any of them has used
   for (int ch = 0; ch < 3; ++ch) c->fepoch = std::max(c->fepoch, c->hepoch[ch]);
+  if (c->dist.world > 1 && !c->d_gscr) CU(cudaMalloc(&c->d_gscr, sizeof(double) * 2 * (size_t)c->dist.plane));
   c->pr_fused = true;
   return CGX_OK;
 }
@@ -54,6 +55,7 @@ void cgx_launch_pr_fused(cgx_ctx* c, Args g) {
   g.s = nxt ? c->alt[1] : c->vec[V_S];
   g.rt = nxt ? c->alt[2] : c->vec[V_RT];
   const bool dist = c->dist.world > 1;
+  g.gscr = c->d_gscr;
   Plan p;
   p.consume = true;
   p.produce = FK_PIPE;

@@ -144,6 +144,7 @@ struct cgx_ctx {
   bool pr_fused = false, no_fused = false;
   int fpar = 0;
   double* alt[3] = {};                     // second buffers of p, s, rt
+  double* d_gscr = nullptr;                // partitioned: [2][plane] scratch (new p of the ghost planes)
   CUtensorMap ftmap[2][3];
   int fused_min_planes = 8, fused_chunks = 0;   // options: planes per CTA at least / force the chunk count
   std::map<std::pair<const void*, size_t>, int> occ;   // ctx_occupancy cache (per device)

@@ -98,6 +98,7 @@ struct Args {
   u64 xt_epoch;
   int meur;                        // Meurant predictor (kernels that are not templated on it)
   int halo_ll;                     // the consumer is the TMA stencil kernel: boundary planes travel as LL words
+  double* gscr;                    // fused PR kernel on a partition: [plane] new p of the ghost plane above the slab
   int dbg;                         // timing experiments (cgx_set_option "debug_skip"): 1 = no halo traffic, 2 = time stamps
   u64* dbg_t;                      // dbg & 2: CTA 0 writes %globaltimer at kernel start / after the scalar fold / at its end
 };

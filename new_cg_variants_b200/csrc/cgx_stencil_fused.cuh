@@ -53,8 +53,8 @@ __device__ __forceinline__ void sts2(double* p, double a, double b) { *reinterpr
 // beta come from folding all ranks' records of the previous launch; the three input vectors of
 // the ghost planes z = -1 / z = nz were stored by the neighbours' previous launch into this
 // rank's window as LL words (channels 0 p, 1 s, 2 rt) and are polled by the compute warps; this
-// launch stores its own first / last plane of the new p, rt (stage 1) and s (stage 2) into the
-// neighbours' windows the moment they are computed, and ends by publishing its record.
+// launch stores its own first / last plane of the new p, s, rt into the neighbours' windows when
+// the unit that owns them has finished its march, and ends by publishing its record.
 template <int PM, bool MEUR, bool DIST>
 __global__ void __launch_bounds__(kFThreads, 2)
 pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_s,
@@ -146,6 +146,8 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
       bool okx[kFPairs];
 #pragma unroll
       for (int j = 0; j < kFPairs; ++j) okx[j] = (x0 + 2 * lx + 64 * j) < G.nx;
+      // real planes of the march (a slab's ghost planes are handled outside the plane loop)
+      const int rlo = DIST ? max(lo, 0) : lo, rhi = DIST ? min(hi, G.nz - 1) : hi;
       auto fetch_xr = [&](int z, Set& xs, Set& rs) {
         const bool oky = ybase + z * ystep < G.ny;
         const int ib = idx0 + z * step_stride;
@@ -164,37 +166,7 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
       // (xn, rn): receive plane zz+1; rnew: receives the new r of plane zz; rold: the new r of
       // plane zz-1 (written by the previous step), for the dots of the stencil stage.
       auto plane_step = [&](const int zz, Set& xc, Set& rc, Set& xn, Set& rn, Set& rnew, Set& rold) {
-        if (DIST && zz <= hi && (zz < 0 || zz >= G.nz)) {
-          // ghost plane: p, s, rt of the tile from the LL words the neighbour stored (no xy halo needed)
-          if (zz + 1 >= z0 && zz + 1 < z1) fetch_xr(zz + 1, xn, rn);
-          double* pn = ring + (size_t)(zz & (kFRing - 1)) * kPlaneStride;
-          const int side = zz < 0 ? 0 : 1;
-          int* err = &g.d.win[g.d.rank]->error;
-          const bool oky = ybase < G.ny;
-#pragma unroll
-          for (int j = 0; j < kFPairs; ++j) {
-            const int c = (ly + 1) * kPX + 2 * lx + 64 * j + 2;
-            double pnw[2] = {0.0, 0.0};
-            if (oky && okx[j] && !(g.dbg & 1)) {
-              const int e = idx0 + 64 * j;                  // element of the plane (march_y is never a slab)
-              LLReq rq[3][2];
-#pragma unroll
-              for (int v = 0; v < 3; ++v)
-#pragma unroll
-                for (int l = 0; l < 2; ++l) {
-                  rq[v][l].src = g.d.ghl + ghl_off(g.d, v, g.hin_par, side) + 2 * (size_t)(e + l);
-                  ll_issue(rq[v][l]);
-                }
-#pragma unroll
-              for (int l = 0; l < 2; ++l) {
-                const double po = ll_finish(rq[0][l], g.hin_epoch, err), so = ll_finish(rq[1][l], g.hin_epoch, err),
-                             rto = ll_finish(rq[2][l], g.hin_epoch, err);
-                pnw[l] = axpy_(axmy_(rto, a, M(so)), b, po);
-              }
-            }
-            sts2(pn + c, pnw[0], pnw[1]);
-          }
-        } else if (zz <= hi) {
+        if (zz <= rhi) {
           const bool fullp = zz >= z0 && zz < z1;          // a plane this CTA owns (else: only its new p)
           if (zz + 1 >= z0 && zz + 1 < z1) fetch_xr(zz + 1, xn, rn);
           const int slot = li % kFStages;
@@ -230,25 +202,6 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
               *reinterpret_cast<double2*>(g.r + i) = make_double2(rnew[j][0], rnew[j][1]);
               *reinterpret_cast<double2*>(g.rt + i) = make_double2(rtn[0], rtn[1]);
               *reinterpret_cast<double2*>(g.p + i) = make_double2(pnw[0], pnw[1]);
-              if constexpr (DIST) {
-                if (!(g.dbg & 1)) {
-                  const int e = idx0 + 64 * j;
-                  if (zz == 0 && g.d.has_lo) {
-#pragma unroll
-                    for (int l = 0; l < 2; ++l) {
-                      ll_store(g.d.ghl_lo + ghl_off(g.d, 0, g.hout_par, 1) + 2 * (size_t)(e + l), pnw[l], g.hout_epoch);
-                      ll_store(g.d.ghl_lo + ghl_off(g.d, 2, g.hout_par, 1) + 2 * (size_t)(e + l), rtn[l], g.hout_epoch);
-                    }
-                  }
-                  if (zz == G.nz - 1 && g.d.has_hi) {
-#pragma unroll
-                    for (int l = 0; l < 2; ++l) {
-                      ll_store(g.d.ghl_hi + ghl_off(g.d, 0, g.hout_par, 0) + 2 * (size_t)(e + l), pnw[l], g.hout_epoch);
-                      ll_store(g.d.ghl_hi + ghl_off(g.d, 2, g.hout_par, 0) + 2 * (size_t)(e + l), rtn[l], g.hout_epoch);
-                    }
-                  }
-                }
-              }
             }
           }
           if (fullp) {
@@ -269,6 +222,16 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
           __syncwarp();
           if (lx == 0) mbar_arrive(&empty_bar[slot]);       // this warp is done with the input stage
           ++li;
+        } else if constexpr (DIST) {
+          if (hi >= G.nz) {                                 // drain step of the top unit: plane nz from the scratch
+            double* pn = ring + (size_t)(G.nz & (kFRing - 1)) * kPlaneStride + (ly + 1) * kPX + 2 * lx + 2;
+#pragma unroll
+            for (int j = 0; j < kFPairs; ++j) {
+              const int e = (ybase < G.ny && okx[j]) ? idx0 + 64 * j : 0;
+              const double2 t = *reinterpret_cast<const double2*>(g.gscr + e);
+              sts2(pn + 64 * j, t.x, t.y);
+            }
+          }
         }
         named_bar_sync(1, kFConsumers);                     // the new p plane zz is complete
 
@@ -285,8 +248,8 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
           for (int j = 0; j < kFPairs; ++j) {
             if (oky && okx[j]) {
               const int c = (ly + 1) * kPX + 2 * lx + 64 * j + 2;
-              const double2 zm = lds2(pm + c), zp = lds2(pp + c), ym = lds2(pc + c - kPX), yp = lds2(pc + c + kPX),
-                            ct = lds2(pc + c);
+              const double2 zm = lds2(pm + c), zp = lds2(pp + c);
+              const double2 ym = lds2(pc + c - kPX), yp = lds2(pc + c + kPX), ct = lds2(pc + c);
               const double xm = pc[c - 1], xp = pc[c + 2];
               const double zmv[2] = {zm.x, zm.y}, zpv[2] = {zp.x, zp.y}, ymv[2] = {ym.x, ym.y}, ypv[2] = {yp.x, yp.y},
                            ctv[2] = {ct.x, ct.y}, xmv[2] = {xm, ct.x}, xpv[2] = {ct.y, xp};
@@ -311,31 +274,76 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
                 red[2] = fma(sti, acc, red[2]);
               }
               *reinterpret_cast<double2*>(g.s + ib + 64 * j) = make_double2(y[0], y[1]);
-              if constexpr (DIST) {
-                if (!(g.dbg & 1)) {
-                  const int e = idx0 + 64 * j;
-                  if (q == 0 && g.d.has_lo) {
-#pragma unroll
-                    for (int l = 0; l < 2; ++l)
-                      ll_store(g.d.ghl_lo + ghl_off(g.d, 1, g.hout_par, 1) + 2 * (size_t)(e + l), y[l], g.hout_epoch);
-                  }
-                  if (q == G.nz - 1 && g.d.has_hi) {
-#pragma unroll
-                    for (int l = 0; l < 2; ++l)
-                      ll_store(g.d.ghl_hi + ghl_off(g.d, 1, g.hout_par, 0) + 2 * (size_t)(e + l), y[l], g.hout_epoch);
-                  }
-                }
-              }
             }
           }
         }
       };
 
       Set xa, ra, xb, rb, rna = {}, rnb = {};
-      if (lo >= z0) fetch_xr(lo, xa, ra);
-      for (int zz = lo; zz <= hi + 1; zz += 2) {
+      if (rlo >= z0) fetch_xr(rlo, xa, ra);
+      if constexpr (DIST) {
+        // Ghost planes of the slab, BEFORE the march: the new p at this lane's own points of plane
+        // z = -1 / nz, from the LL words (p, s, rt = channels 0, 1, 2) the neighbour's previous launch
+        // stored, into the scratch planes.  Nothing of this lives in the plane loop.
+        int* err = &g.d.win[g.d.rank]->error;
+        const size_t chs = ghl_off(g.d, 1, 0, 0);              // channel stride of the LL ghost planes
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+          if (side == 0 ? lo >= 0 : hi < G.nz) continue;
+          const u64* gh = g.d.ghl + ghl_off(g.d, 0, g.hin_par, side);
+#pragma unroll 1
+          for (int j = 0; j < kFPairs; ++j) {
+            if (!(ybase < G.ny && okx[j])) continue;
+            const int e = idx0 + 64 * j;
+            double pnw[2] = {0.0, 0.0};
+            if (!(g.dbg & 1)) {
+              LLReq rq[3][2];
+#pragma unroll
+              for (int v = 0; v < 3; ++v)
+#pragma unroll
+                for (int l = 0; l < 2; ++l) { rq[v][l].src = gh + v * chs + 2 * (size_t)(e + l); ll_issue(rq[v][l]); }
+#pragma unroll
+              for (int l = 0; l < 2; ++l) {
+                const double po = ll_finish(rq[0][l], g.hin_epoch, err), so = ll_finish(rq[1][l], g.hin_epoch, err),
+                             rto = ll_finish(rq[2][l], g.hin_epoch, err);
+                pnw[l] = axpy_(axmy_(rto, a, M(so)), b, po);
+              }
+            }
+            // below: straight into the ring slot of plane -1 (this thread reads it back itself in the
+            // stencil stage of plane 0, before plane 3 reuses the slot); above: parked in the scratch
+            // plane until the drain step (the ring slot of plane nz is in use until then)
+            if (side == 0) sts2(ring + (size_t)((-1) & (kFRing - 1)) * kPlaneStride + (ly + 1) * kPX + 2 * lx + 64 * j + 2, pnw[0], pnw[1]);
+            else *reinterpret_cast<double2*>(g.gscr + e) = make_double2(pnw[0], pnw[1]);
+          }
+        }
+      }
+      for (int zz = rlo; zz <= rhi + 1; zz += 2) {
         plane_step(zz, xa, ra, xb, rb, rna, rnb);
-        if (zz + 1 <= hi + 1) plane_step(zz + 1, xb, rb, xa, ra, rnb, rna);
+        if (zz + 1 <= rhi + 1) plane_step(zz + 1, xb, rb, xa, ra, rnb, rna);
+      }
+      if constexpr (DIST) {
+        // Boundary planes of the slab this unit computed, AFTER the march: the new p, s, rt go to the
+        // neighbour's window as LL words; every thread re-reads what it stored itself.
+        if (!(g.dbg & 1)) {
+          const size_t chs = ghl_off(g.d, 1, 0, 0);
+          const double* src[3] = {g.p, g.s, g.rt};
+#pragma unroll 1
+          for (int side = 0; side < 2; ++side) {
+            if (side == 0 ? !(z0 == 0 && g.d.has_lo) : !(z1 == G.nz && g.d.has_hi)) continue;
+            u64* dst = (side == 0 ? g.d.ghl_lo : g.d.ghl_hi) + ghl_off(g.d, 0, g.hout_par, side ^ 1);
+            const int i0 = idx0 + (side == 0 ? 0 : (G.nz - 1) * step_stride);
+#pragma unroll 1
+            for (int j = 0; j < kFPairs; ++j) {
+              if (!(ybase < G.ny && okx[j])) continue;
+#pragma unroll
+              for (int v = 0; v < 3; ++v) {
+                const double2 t = *reinterpret_cast<const double2*>(src[v] + i0 + 64 * j);
+                ll_store(dst + v * chs + 2 * (size_t)(idx0 + 64 * j), t.x, g.hout_epoch);
+                ll_store(dst + v * chs + 2 * (size_t)(idx0 + 64 * j + 1), t.y, g.hout_epoch);
+              }
+            }
+          }
+        }
       }
     }
   }
