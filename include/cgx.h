@@ -170,6 +170,31 @@ int cgx_fetch_dev(cgx_ctx* ctx, double* x_dev, double* hist_dev);
 /* one named state vector ("x","r","rt","p","s","st","w","wt","u","ut","t") for tests */
 int cgx_fetch_vector_host(cgx_ctx* ctx, const char* name, double* out_host);
 
+/* ---- on-device support for the remaining reference callbacks and for GV residual replacement
+ *      (single-GPU contexts, stream path).
+ *   cgx_set_capture: what to record after every iteration k = 0 .. max_iter-1, in device memory
+ *      (one device-to-host copy at the end instead of one per iteration):
+ *        CGX_CAPTURE_X / _R   x_k / r_k   -> callbacks/save_x.py, save_r.py, and the inputs of
+ *                                            lanczos_recurrence.py:43-61 (r_k, r_k1) and
+ *                                            updated_error_A_norm.py:43-45 (r_k)
+ *        CGX_CAPTURE_SCALARS  (a, b) as the recurrences hold them after iteration k
+ *                                            -> a_k1, a_k2, b_k1 of lanczos_recurrence.py:51-53
+ *      Takes effect at the next cgx_begin / cgx_run (mask 0 switches it off).
+ *   cgx_fetch_capture_host: which = 0 x [max_iter][n], 1 r [max_iter][n], 2 scalars [2][max_iter].
+ *   cgx_set_gv_replace: gv_cg.py:156-158 -- flags[k] != 0 makes iteration k of GV-CG replace
+ *      w_k by A r_k after the vector updates (then wt, t, eta follow from the new w as in the
+ *      reference); flags == NULL clears the schedule.
+ *   cgx_advance_stages / cgx_gv_replace_now: for a host-evaluated `w_replace` predicate that
+ *      looks at vectors: run `nstages` kernel stages of the current iteration (GV: stage 0 = the
+ *      vector pass that forms x_k, r_k, w_k; stage 1 = t = A wt; then the instrumentation), and
+ *      replace w between them. */
+enum { CGX_CAPTURE_X = 1u, CGX_CAPTURE_R = 2u, CGX_CAPTURE_SCALARS = 4u };
+int cgx_set_capture(cgx_ctx* ctx, unsigned mask);
+int cgx_fetch_capture_host(cgx_ctx* ctx, int which, double* out_host);
+int cgx_set_gv_replace(cgx_ctx* ctx, const uint8_t* flags, int n);
+int cgx_advance_stages(cgx_ctx* ctx, int nstages);
+int cgx_gv_replace_now(cgx_ctx* ctx);
+
 /* ---- the whole reference call in one: load + run + fetch with HOST buffers
  *      (this is what `trial = method(A,b,x0,max_iter,callbacks=...,x_true=...,
  *      preconditioner=...)`, figure_gen.py:59, maps to once A and dinv are set). */

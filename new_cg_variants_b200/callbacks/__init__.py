@@ -7,9 +7,12 @@ Passed in ``callbacks=[...]`` to the solvers of ``new_cg_variants_b200.cg_varian
   and computed ON THE GPU inside the solve, one fused matrix pass per iteration; the
   functions below are never called for them on that path;
 * ``print_k(K)`` is honoured as a progress tick without forcing a device round trip;
-* anything else (``save_x``, ``save_r``, or a user callable) makes the solver step the GPU
-  one iteration at a time and call it with the reference's keyword protocol
-  (``output, A, b, x_k, r_k, k, max_iter, kwargs, a_k1, a_k2, b_k1, r_k1, ...``).
+* ``save_x``, ``save_r``, ``lanczos_recurrence`` and ``updated_error_A_norm`` are served from
+  device capture buffers: the GPU records x_k / r_k / (a, b) after every iteration and the
+  bodies below run once on the host afterwards, fed from one device-to-host copy;
+* any other callable makes the solver step the GPU one iteration at a time and call it with
+  the reference's keyword protocol (``output, A, b, x_k, r_k, k, max_iter, kwargs, a_k1, a_k2,
+  b_k1, r_k1, ...``).
 
 The bodies here are plain host-side instrumentation with the reference's semantics, so
 the same objects also work with any solver that follows the ``callback(**locals())``
@@ -81,6 +84,50 @@ def save_r(**kw):
     out["r"][k] = r
 
 
+def updated_error_A_norm(**kw):
+    """sqrt(r_k . A^{-1} r_k): the A-norm of the error the algorithm "sees" through its updated
+    residual (updated_error_A_norm.py:43-45; a direct solve per iteration, as in the reference)."""
+    A, r = kw["A"], kw["r_k"]
+    solve = spla.spsolve if sps.issparse(A) else np.linalg.solve
+    e = solve(A.astype(np.double), r.astype(np.double))
+    _slot(kw, "updated_error_A_norm")[kw["k"]] = np.sqrt(e.T @ r)
+
+
+def lanczos_recurrence(**kw):
+    """Lanczos vectors / coefficients implied by the CG iterates and the loss of the three-term
+    recurrence and of orthogonality (lanczos_recurrence.py:43-77)."""
+    out, max_iter, k, r = kw["output"], kw["max_iter"], kw["k"], kw["r_k"]
+    a_k1, b_k1 = kw["a_k1"], kw["b_k1"]
+    A = kw["A"]
+    if k == 0:
+        out["lanczos_alpha"] = np.zeros(max_iter, dtype=A.dtype)
+        out["lanczos_beta"] = np.zeros(max_iter, dtype=A.dtype)
+        out["lanczos_z"] = np.zeros((len(r), max_iter), dtype=A.dtype)
+        out["lanczos_z"][:, 0] = r / np.linalg.norm(r)
+    elif k < max_iter:
+        r_k1, a_k2 = kw["r_k1"], kw["a_k2"]
+        out["lanczos_alpha"][k - 1] = 1 / a_k1 + b_k1 / a_k2 if k > 1 else 1 / a_k1
+        out["lanczos_beta"][k - 1] = np.linalg.norm(r) / (a_k1 * np.linalg.norm(r_k1))
+        out["lanczos_z"][:, k] = (-1) ** k * r / np.linalg.norm(r)
+    if k == max_iter - 1:
+        _lanczos_finish(out, A, max_iter)
+
+
+def _lanczos_finish(out, A, max_iter):
+    """lanczos_recurrence.py:63-77: T (max_iter x max_iter-1), E = A Z[:, :-1] - Z T."""
+    T = sps.diags([out["lanczos_alpha"], out["lanczos_beta"][:max_iter - 2], out["lanczos_beta"][:max_iter - 1]],
+                  [0, 1, -1], shape=(max_iter, max_iter - 1))
+    Z = out["lanczos_z"]
+    E = A @ Z[:, :-1] - Z @ T
+    out["lanczos_3_term_error"] = np.linalg.norm(E, axis=0)
+    out["lanczos_orthogonality"] = np.abs(np.einsum("ji,ji->i", out["lanczos_beta"][:max_iter - 1] * Z[:, :-1], Z[:, 1:]))
+
+
+# Callbacks served from the DEVICE capture buffers (x_k / r_k / scalars recorded on the GPU during
+# the solve, one copy at the end) instead of a host round trip per iteration.
+CAPTURE_CALLBACKS = ("save_x", "save_r", "lanczos_recurrence", "updated_error_A_norm")
+
+
 def print_k(K):
     """Progress line every K iterations (print_k.py)."""
     def pk(**kw):
@@ -91,4 +138,5 @@ def print_k(K):
 
 
 __all__ = ["error_A_norm", "error_2_norm", "residual_2_norm", "updated_residual_2_norm",
-           "save_x", "save_r", "print_k", "DEVICE_HISTORIES"]
+           "save_x", "save_r", "lanczos_recurrence", "updated_error_A_norm", "print_k", "DEVICE_HISTORIES",
+           "CAPTURE_CALLBACKS"]

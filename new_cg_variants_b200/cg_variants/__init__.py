@@ -5,7 +5,10 @@
 
 for ``hs_pcg, cg_pcg, gv_pcg, pr_pcg, m_pcg, pipe_pr_pcg, pipe_p_pcg, pipe_pr_m_pcg,
 pipe_p_m_pcg`` and the un-preconditioned twins ``*_cg`` (no ``preconditioner`` argument).
-``gv_*`` also accept ``w_replace`` (gv_cg.py:89); only the default "never" runs on the GPU.
+``gv_*`` also accept ``w_replace`` (gv_cg.py:89,156-158): a predicate that depends only on ``k``
+becomes a replacement schedule executed on the GPU; one that reads vectors is evaluated on the
+host every iteration against the device state (the replacement ``w = A r`` itself always runs on
+the GPU).
 
 Every iteration runs in libcgx_b200 on the GPU (there is no CPU solve path).  ``A`` may be
 a scipy sparse matrix, a dense ndarray, or a ``PoissonStencil``.  ``preconditioner`` stays an
@@ -25,11 +28,11 @@ import scipy.sparse as sps
 
 from .. import _lib
 from .. import callbacks as _cbk
-from ..callbacks import DEVICE_HISTORIES
+from ..callbacks import CAPTURE_CALLBACKS, DEVICE_HISTORIES
 from ..operators import PoissonStencil, canonical_csr
 from ..session import Session
 
-_OWN_KEYS = ("device", "path", "session", "return_info")
+_OWN_KEYS = ("device", "path", "session", "return_info", "w_replace")
 
 # ---------------------------------------------------------------------------------------
 # preconditioner probe
@@ -108,6 +111,18 @@ def clear_cache():
 # ---------------------------------------------------------------------------------------
 # the driver behind every exported function
 # ---------------------------------------------------------------------------------------
+def _is_package_callback(cb, name):
+    mod = getattr(cb, "__module__", "") or ""
+    return cb is getattr(_cbk, name, None) or mod.split(".")[0] == "callbacks" or mod.endswith("callbacks." + name)
+
+
+def _split_capture(generic):
+    """(callbacks served from the device capture buffers, the rest)."""
+    cap = [cb for cb in generic if getattr(cb, "__name__", "") in CAPTURE_CALLBACKS
+           and _is_package_callback(cb, cb.__name__)]
+    return cap, [cb for cb in generic if cb not in cap]
+
+
 def _split_callbacks(callbacks):
     device, ticks, generic = [], [], []
     for cb in callbacks:
@@ -156,14 +171,28 @@ def _solve(name, tag, A, b, x0, max_iter, preconditioner, callbacks, kwargs):
     else:
         sess.set_jacobi(dinv)                  # an explicit session still honours `preconditioner`
 
-    if not generic:
-        _, hist, info = sess.solve(tag, b, x0, max_iter, x_true=x_true, histories=tuple(dev_hist),
-                                   path=path, return_x=False)
-        for h in dev_hist:
-            output[h] = hist[h]
+    w_replace = own.get("w_replace")
+    plan = _plan_w_replace(w_replace, max_iter) if tag == "gv" else None
+    capture, other = _split_capture(generic)
+    if not other and not isinstance(plan, str):
+        if capture and isinstance(A, PoissonStencil):
+            A = A.tocsr()                      # the callback bodies multiply / factor A on the host
+        sess.set_gv_replace(plan)
+        names = {cb.__name__ for cb in capture}
+        sess.set_capture(x="save_x" in names, r=bool(names - {"save_x"}), scalars="lanczos_recurrence" in names)
+        try:
+            _, hist, info = sess.solve(tag, b, x0, max_iter, x_true=x_true, histories=tuple(dev_hist),
+                                       path=path, return_x=False)
+            for h in dev_hist:
+                output[h] = hist[h]
+            if capture:
+                _replay_captured(sess, tag, A, b, x0, max_iter, capture, output, kwargs)
+        finally:
+            sess.set_capture()
+            sess.set_gv_replace(None)
     else:
         info = _solve_stepwise(sess, tag, A, b, x0, max_iter, x_true, dev_hist, generic, output,
-                               kwargs, path)
+                               kwargs, path, w_replace if isinstance(plan, str) else None, plan)
     for cb in ticks:   # leave the terminal as print_k would after the last iteration
         try:
             cb(output=output, k=max_iter - 1, max_iter=max_iter)
@@ -174,12 +203,64 @@ def _solve(name, tag, A, b, x0, max_iter, preconditioner, callbacks, kwargs):
     return output
 
 
-def _solve_stepwise(sess, tag, A, b, x0, max_iter, x_true, dev_hist, generic, output, extra, path):
-    """Arbitrary callbacks: step the GPU one iteration at a time and hand each callback the
-    reference's keyword set (hs_cg.py:97-98,128-129).  Slow (a device round trip per
-    iteration) but still no CPU arithmetic on the solve itself."""
+def _replay_captured(sess, tag, A, b, x0, max_iter, capture, output, extra):
+    """Run the capture-served callbacks once, on the host, from what the GPU recorded during the
+    solve: x_k / r_k rows and the (a, b) the recurrences held after every iteration.  Same keyword
+    protocol as the reference's `callback(**locals())`."""
+    names = {cb.__name__ for cb in capture}
+    X = sess.fetch_capture("x") if "save_x" in names else None
+    R = sess.fetch_capture("r") if names - {"save_x"} else None
+    sc = sess.fetch_capture("scalars") if "lanczos_recurrence" in names else None
+    predicted = tag in ("pr", "m") or tag.startswith("pipe")
+    b_arr = np.asarray(b, dtype=np.float64)
+    a_k1 = a_k2 = b_k = b_k1 = 0.0
+    for k in range(max_iter):
+        if k > 0 and sc is not None:
+            a_k2, a_k1 = a_k1, sc[0][k - 1]
+            b_k1, b_k = b_k, (sc[1][k - 1] if predicted else sc[1][k])
+        loc = dict(output=output, A=A, b=b_arr, x0=x0, k=k, max_iter=max_iter, n=len(b_arr), kwargs=extra,
+                   x_k=None if X is None else X[k], r_k=None if R is None else R[k],
+                   x_k1=None if X is None or k == 0 else X[k - 1], r_k1=None if R is None or k == 0 else R[k - 1],
+                   a_k=None if sc is None else sc[0][k], a_k1=a_k1, a_k2=a_k2, b_k=b_k, b_k1=b_k1)
+        for cb in capture:
+            cb(**loc)
+
+
+def _plan_w_replace(w_replace, max_iter):
+    """None: never (the reference's default); a uint8 schedule when the predicate depends only on k
+    (it is then evaluated up front, in order, with the reference's `wk_replace_flags` dict);
+    "host" when it reads vectors -> evaluated every iteration against the device state."""
+    if w_replace is None or w_replace is _never:
+        return None
+    flags = {}
+    sched = np.zeros(max_iter, dtype=np.uint8)
+    try:
+        for k in range(1, max_iter):
+            sched[k] = 1 if w_replace(k=k, A=None, b=None, x=None, w=None, r=None, r_=None, u=None, s=None, p=None,
+                                      wk_replace_flags=flags) else 0
+    except Exception:                                   # noqa: BLE001 -- it looked at a vector
+        return "host"
+    return sched if sched.any() else None
+
+
+def _solve_stepwise(sess, tag, A, b, x0, max_iter, x_true, dev_hist, generic, output, extra, path,
+                    w_replace=None, plan=None):
+    """Arbitrary callbacks (and vector-reading GV `w_replace` predicates): step the GPU one
+    iteration at a time and hand each callable the reference's keyword set (hs_cg.py:97-98,128-129;
+    gv_cg.py:156).  Slow (a device round trip per iteration) but still no CPU arithmetic on the
+    solve itself."""
     sess.load_problem(b, x0, x_true)
-    sess.begin(tag, max_iter, histories=tuple(dev_hist), path=path)
+    host_pred = w_replace is not None
+    sess.set_gv_replace(None if host_pred else plan)
+    sess.set_option("gv_manual", 1 if host_pred else 0)
+    if host_pred:
+        path = "stream"
+    try:
+        sess.begin(tag, max_iter, histories=tuple(dev_hist), path=path)
+    finally:
+        sess.set_option("gv_manual", 0)
+        sess.set_gv_replace(None)
+    wk_flags = {}
     predicted = tag in ("pr", "m") or tag.startswith("pipe")
     b_arr = np.asarray(b, dtype=np.float64)
     a_k1 = a_k2 = 0.0
@@ -189,7 +270,16 @@ def _solve_stepwise(sess, tag, A, b, x0, max_iter, x_true, dev_hist, generic, ou
     next_b = sc["b"]
     for k in range(max_iter):
         if k > 0:
-            sess.advance(1)
+            if host_pred:
+                # gv_cg.py:151-158: the vector pass forms x_k, r_k, w_k; the predicate sees them (and the
+                # previous r, u, s, p) and decides whether w_k is replaced by A r_k before t = A wt
+                sess.advance_stages(1)
+                if w_replace(k=k, A=A, b=b_arr, x=sess.vector("x"), w=sess.vector("w"), r=sess.vector("r"), r_=r_k1,
+                             u=sess.vector("u"), s=sess.vector("s"), p=sess.vector("p"), wk_replace_flags=wk_flags):
+                    sess.gv_replace_now()
+                sess.advance_stages(1 + (1 if dev_hist else 0))
+            else:
+                sess.advance(1)
             sc_new = sess.scalars()
             a_k2, a_k1 = a_k1, sc["a"]
             b_k1 = b_k
@@ -217,14 +307,14 @@ def _never(**kwargs):
 def _make(name, tag, preconditioned, gv=False):
     if preconditioned and gv:
         def f(A, b, x0, max_iter, w_replace=_never, preconditioner=lambda x: x, callbacks=[], **kwargs):
-            _check_w_replace(w_replace)
+            kwargs["w_replace"] = w_replace
             return _solve(name, tag, A, b, x0, max_iter, preconditioner, callbacks, kwargs)
     elif preconditioned:
         def f(A, b, x0, max_iter, preconditioner=lambda x: x, callbacks=[], **kwargs):
             return _solve(name, tag, A, b, x0, max_iter, preconditioner, callbacks, kwargs)
     elif gv:
         def f(A, b, x0, max_iter, w_replace=_never, callbacks=[], **kwargs):
-            _check_w_replace(w_replace)
+            kwargs["w_replace"] = w_replace
             return _solve(name, tag, A, b, x0, max_iter, None, callbacks, kwargs)
     else:
         def f(A, b, x0, max_iter, callbacks=[], **kwargs):
@@ -232,18 +322,6 @@ def _make(name, tag, preconditioned, gv=False):
     f.__name__ = f.__qualname__ = name
     f.__doc__ = f"{name}: GPU implementation of the reference's `{name}` (variant tag {tag!r})."
     return f
-
-
-def _check_w_replace(w_replace):
-    if w_replace is not _never:
-        # the reference's default is `lambda **kwargs: False` (gv_cg.py:89); accept any
-        # callable that declines at k=1 without looking at vectors, reject the rest
-        try:
-            if not w_replace(k=1, wk_replace_flags={}):
-                return
-        except Exception:
-            pass
-        raise NotImplementedError("gv residual replacement (w_replace) is not supported on the GPU path")
 
 
 _TAGS = [("hs", "hs"), ("cg", "cg"), ("gv", "gv"), ("pr", "pr"), ("m", "m"), ("pipe_pr", "pipe_pr"),

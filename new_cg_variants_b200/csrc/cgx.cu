@@ -76,6 +76,7 @@ static void free_state(cgx_ctx* c) {
   for (int i = 0; i < V_COUNT; ++i) { cudaFree(c->vec[i]); c->vec[i] = nullptr; }
   for (auto& q : c->alt) { cudaFree(q); q = nullptr; }
   cudaFree(c->d_gscr); c->d_gscr = nullptr;
+  for (int w = 0; w < 3; ++w) { cudaFree(c->d_cap[w]); c->d_cap[w] = nullptr; }
   for (auto& pp : c->d_exp) for (auto& q : pp) { cudaFree(q); q = nullptr; }
   cudaFree(c->d_hist); c->d_hist = nullptr; c->hist_len = 0;
   c->ran = false;
@@ -505,8 +506,27 @@ VariantInfo variant_info(int v, bool prec) {
 // ---------------------------------------------------------------------------------------
 static int iter_stage_count(const cgx_ctx* c) {
   int ns = core_stages(c);
-  if (c->hist_mask) ns += (c->dist.world > 1) ? 3 : 1;
+  if (c->hist_mask || c->capture) ns += (c->dist.world > 1) ? 3 : 1;
   return ns;
+}
+
+void launch_capture(cgx_ctx* c, const Args& g) {
+  const size_t bytes = sizeof(double) * c->n;
+  if (c->capture & CGX_CAPTURE_X) cudaMemcpyAsync(c->d_cap[0] + (size_t)g.k * c->n, c->vec[V_X], bytes, cudaMemcpyDeviceToDevice, c->stream);
+  if (c->capture & CGX_CAPTURE_R) cudaMemcpyAsync(c->d_cap[1] + (size_t)g.k * c->n, c->vec[V_R], bytes, cudaMemcpyDeviceToDevice, c->stream);
+  if (c->capture & CGX_CAPTURE_SCALARS) {
+    capture_scalars_kernel<<<1, 32, 0, c->stream>>>(c->d_sc, c->d_cap[2], g.k, c->hist_len);
+    c->launches++;
+  }
+}
+
+// GV residual replacement at iteration g.k, between the vector pass and t = A wt
+static void launch_gv_replace(cgx_ctx* c, Args g) {
+  launch_spmv<SP_PLAIN, 0, false>(c, g, c->vec[V_R], c->vec[V_W]);          // w = A r        gv_cg.py:158
+  launch_scale(c, c->d_dinv, c->vec[V_W], c->vec[V_WT]);                    // wt = M w       :160
+  launch_dot(c, c->vec[V_W], c->vec[V_RT], nullptr, 5);                     // eta = w . rt   :163
+  gv_refinalize_kernel<<<1, 32, 0, c->stream>>>(c->d_sc, g.k);              // mu, a          :169-170
+  c->launches++;
 }
 
 static void iter_stage(cgx_ctx* c, int s, const Args& g) {
@@ -751,6 +771,21 @@ static int begin_prepare(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
   }
   CU(cudaMemsetAsync(c->d_hist, 0, sizeof(double) * CGX_HIST_ROWS * (size_t)max_iter, c->stream));
   c->hist_mask = hist_mask;
+  c->capture = c->capture_req;
+  c->cur_stage = 0;
+  const bool gv_sched = variant == CGX_GV && std::any_of(c->gv_replace.begin(), c->gv_replace.end(), [](uint8_t f) { return f != 0; });
+  if (c->capture || gv_sched) {
+    if (c->dist.world > 1) return fail(CGX_ERR_UNSUPPORTED, "cgx_begin: capture / GV residual replacement run on single-GPU contexts");
+    if (path == CGX_PATH_PERSISTENT) return fail(CGX_ERR_UNSUPPORTED, "cgx_begin: capture / GV residual replacement need the stream path");
+    path = CGX_PATH_STREAM;
+    for (int w = 0; w < 3; ++w) { cudaFree(c->d_cap[w]); c->d_cap[w] = nullptr; }
+    const size_t vec_bytes = sizeof(double) * (size_t)c->n * (size_t)max_iter;
+    if ((c->capture & (CGX_CAPTURE_X | CGX_CAPTURE_R)) && vec_bytes > (size_t)48 << 30)
+      return fail(CGX_ERR_UNSUPPORTED, "cgx_begin: capturing %d vectors of %lld rows exceeds 48 GB per buffer", max_iter, (long long)c->n);
+    if (c->capture & CGX_CAPTURE_X) CU(cudaMalloc(&c->d_cap[0], vec_bytes));
+    if (c->capture & CGX_CAPTURE_R) CU(cudaMalloc(&c->d_cap[1], vec_bytes));
+    if (c->capture & CGX_CAPTURE_SCALARS) CU(cudaMalloc(&c->d_cap[2], sizeof(double) * 2 * (size_t)max_iter));
+  }
   { int trc = setup_tma(c, vi.need); if (trc) return trc; }
   c->variant = variant; c->max_iter = max_iter; c->cur_k = 0;
   {
@@ -775,7 +810,7 @@ static int begin_prepare(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
   c->path = path;
   c->cg_elide = (variant == CGX_CG || variant == CGX_GV) && path == CGX_PATH_STREAM && c->op_kind == 2 && c->use_tma &&
                 c->tmap_ok[variant == CGX_CG ? V_R : V_W] &&
-                c->pm != 1 && !c->no_elide;
+                c->pm != 1 && !c->no_elide && !(variant == CGX_GV && (gv_sched || c->gv_manual));
   c->launches_run = 0; c->loop_ms = 0.0;
   c->pend.clear();
   c->pr_fused = false; c->fpar = 0;
@@ -844,7 +879,7 @@ static int group_begin(cgx_ctx** cs, int count, int variant, int max_iter, unsig
   }
   // k = 0 entry of the histories (the reference's callbacks fire on the initial state)
   for (int i = 0; i < count; ++i) cs[i]->cur_k = 0;
-  if (cs[0]->hist_mask) {
+  if (cs[0]->hist_mask || cs[0]->capture) {
     const int core = core_stages(cs[0]);
     for (int s = core; s < iter_stage_count(cs[0]); ++s)
       for (int i = 0; i < count; ++i) {
@@ -894,11 +929,14 @@ static int group_advance(cgx_ctx** cs, int count, int niter) {
     }
   } else {
     const int ns = iter_stage_count(c0);
+    if (c0->cur_stage != 0) return fail(CGX_ERR_ARG, "cgx_advance: an iteration is half done (cgx_advance_stages); finish it first");
     for (int k = c0->cur_k + 1; k <= last; ++k)
       for (int s = 0; s < ns; ++s)
         for (int i = 0; i < count; ++i) {
           if (count > 1) cudaSetDevice(cs[i]->device);
           gs[i].k = k;
+          if (s == 1 && cs[i]->variant == CGX_GV && k < (int)cs[i]->gv_replace.size() && cs[i]->gv_replace[k])
+            launch_gv_replace(cs[i], gs[i]);
           iter_stage(cs[i], s, gs[i]);
         }
     for (int i = 0; i < count; ++i) {
@@ -1007,7 +1045,9 @@ extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
   if (!strcmp(name, "csr_slab")) { c->no_slab = (value == 0); return CGX_OK; }
   if (!strcmp(name, "cg_elide")) { c->no_elide = (value == 0); return CGX_OK; }
   if (!strcmp(name, "pr_fused")) { c->no_fused = (value == 0); return CGX_OK; }
+  if (!strcmp(name, "gv_manual")) { c->gv_manual = value != 0; return CGX_OK; }
   if (!strcmp(name, "fused_min_planes")) { c->fused_min_planes = std::max(1, value); return CGX_OK; }
+  if (!strcmp(name, "fused_min_slab")) { c->fused_min_slab = std::max(1, value); return CGX_OK; }
   if (!strcmp(name, "fused_chunks")) { c->fused_chunks = std::max(0, value); return CGX_OK; }
   if (!strcmp(name, "persistent_threshold")) { c->pers_threshold = value; return CGX_OK; }
   if (!strcmp(name, "pers_threads")) { c->pers_threads = value; return CGX_OK; }
@@ -1061,6 +1101,58 @@ extern "C" int cgx_get_scalars(cgx_ctx* c, double* out9) {
   CU(cudaMemcpy(&h, c->d_sc + c->scpar, sizeof(Scal), cudaMemcpyDeviceToHost));
   const double v[9] = {h.a, h.a1, h.b, h.nu, h.nu1, h.mu, h.eta, h.del, h.gam};
   memcpy(out9, v, sizeof v);
+  return CGX_OK;
+}
+
+extern "C" int cgx_set_capture(cgx_ctx* c, unsigned mask) {
+  if (!c || (mask & ~7u)) return fail(CGX_ERR_ARG, "cgx_set_capture: bad arguments");
+  c->capture_req = mask;
+  return CGX_OK;
+}
+extern "C" int cgx_fetch_capture_host(cgx_ctx* c, int which, double* out) {
+  if (!c || !c->ran || !out || which < 0 || which > 2 || !c->d_cap[which] || !(c->capture & (1u << which)))
+    return fail(CGX_ERR_ARG, "cgx_fetch_capture_host: nothing captured for selector %d", which);
+  CU(cudaSetDevice(c->device));
+  const size_t bytes = which == 2 ? sizeof(double) * 2 * (size_t)c->hist_len : sizeof(double) * (size_t)c->n * (size_t)c->hist_len;
+  CU(cudaMemcpyAsync(out, c->d_cap[which], bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return CGX_OK;
+}
+extern "C" int cgx_set_gv_replace(cgx_ctx* c, const uint8_t* flags, int n) {
+  if (!c || n < 0) return fail(CGX_ERR_ARG, "cgx_set_gv_replace: bad arguments");
+  c->gv_replace.clear();
+  if (flags && n > 0) c->gv_replace.assign(flags, flags + n);
+  return CGX_OK;
+}
+// Run `nstages` kernel stages, continuing inside iteration cur_k + 1 (single context, stream path).
+extern "C" int cgx_advance_stages(cgx_ctx* c, int nstages) {
+  if (!c || !c->ran || nstages < 0) return fail(CGX_ERR_ARG, "cgx_advance_stages: call cgx_begin first");
+  if (c->path != CGX_PATH_STREAM || c->dist.world > 1)
+    return fail(CGX_ERR_UNSUPPORTED, "cgx_advance_stages: single-GPU stream path only");
+  CU(cudaSetDevice(c->device));
+  const int ns = iter_stage_count(c);
+  Args g = make_args(c);
+  const i64 l0 = c->launches;
+  for (; nstages > 0 && c->cur_k + 1 <= c->max_iter - 1; --nstages) {
+    g.k = c->cur_k + 1;
+    iter_stage(c, c->cur_stage, g);
+    if (++c->cur_stage == ns) { c->cur_stage = 0; c->cur_k++; }
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  c->launches_run += c->launches - l0;
+  return check_device_flags(c, "cgx_advance_stages");
+}
+extern "C" int cgx_gv_replace_now(cgx_ctx* c) {
+  if (!c || !c->ran || c->variant != CGX_GV || c->cur_stage != 1 || c->cg_elide)
+    return fail(CGX_ERR_ARG, "cgx_gv_replace_now: only between the vector pass and the SpMV pass of a GV-CG iteration "
+                "begun with option gv_manual = 1");
+  CU(cudaSetDevice(c->device));
+  Args g = make_args(c);
+  g.k = c->cur_k + 1;
+  launch_gv_replace(c, g);
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
   return CGX_OK;
 }
 

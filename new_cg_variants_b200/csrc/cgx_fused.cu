@@ -20,6 +20,10 @@ int cgx_fused_prepare(cgx_ctx* c) {
   if (c->op_kind != 2 || !c->use_tma || c->pm == 1) return CGX_OK;
   // partitioned: the records travel peer to peer (the NCCL mode keeps the two-kernel path)
   if (c->dist.world > 1 && (c->dist.mode == 2 || !c->halo_ll)) return CGX_OK;
+  // thin slabs: a march of < ~16 planes per CTA no longer amortises the pipeline fill of the fused
+  // kernel (measured at 8 GPUs, 32 planes per rank: 53.4 us/iteration fused, 50.4 two kernels; at 2
+  // GPUs, 128 planes: 137 vs 151) -- option "fused_min_slab" moves the switch
+  if (c->dist.world > 1 && c->sten.nz < c->fused_min_slab) return CGX_OK;
   const StencilOp& S = c->sten;
   for (int j = 0; j < 3; ++j) {
     if (!c->alt[j]) CU(cudaMalloc(&c->alt[j], sizeof(double) * c->n));

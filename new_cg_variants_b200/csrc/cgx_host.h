@@ -146,7 +146,14 @@ struct cgx_ctx {
   double* alt[3] = {};                     // second buffers of p, s, rt
   double* d_gscr = nullptr;                // partitioned: [2][plane] scratch (new p of the ghost planes)
   CUtensorMap ftmap[2][3];
+  int fused_min_slab = 64;                 // partitioned runs: planes per rank from which the fused kernel is used
   int fused_min_planes = 8, fused_chunks = 0;   // options: planes per CTA at least / force the chunk count
+  // capture of x_k / r_k / (a, b) after every iteration, GV residual replacement (include/cgx.h)
+  unsigned capture = 0, capture_req = 0;
+  double* d_cap[3] = {};                   // x [max_iter][n], r [max_iter][n], scalars [2][max_iter]
+  std::vector<uint8_t> gv_replace;
+  bool gv_manual = false;                  // option "gv_manual": w may be replaced by hand (cgx_gv_replace_now): no w~ elision
+  int cur_stage = 0;                       // cgx_advance_stages: next stage of iteration cur_k + 1
   std::map<std::pair<const void*, size_t>, int> occ;   // ctx_occupancy cache (per device)
   int* d_tma_err = nullptr;                // set by a TMA wait that expired (mbar_wait)
   int variant = 0, max_iter = 0, cur_k = 0, path = CGX_PATH_STREAM;
@@ -217,6 +224,7 @@ double* cgx_cur_vec(cgx_ctx* c, int v);         // the buffer that currently hol
 void launch_halo_push(cgx_ctx* c, Args g, const double* v, int ch);
 void launch_instrument(cgx_ctx* c, Args g);
 void launch_hist_consume(cgx_ctx* c, Args g);
+void launch_capture(cgx_ctx* c, const Args& g);
 
 struct VariantInfo {
   bool meurant, pipe, recompute;

@@ -16,7 +16,8 @@ static void iter_stage_pm(cgx_ctx* c, int s, const Args& g) {
       else if (t == 1) launch_instrument(c, g);
       else launch_hist_consume(c, g);
     } else {
-      launch_instrument(c, g);
+      if (c->hist_mask) launch_instrument(c, g);
+      if (c->capture) launch_capture(c, g);
     }
     return;
   }

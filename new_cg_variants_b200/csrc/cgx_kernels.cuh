@@ -865,6 +865,21 @@ static __global__ void __launch_bounds__(kBlock) dot_kernel(const double* __rest
   grid_sum_finalize<1>(red, partials, ticket, [=](const double* acc) { sc->tmp[slot] = acc[0]; });
 }
 
+// capture of the scalars after iteration k: out[0][k] = a, out[1][k] = b
+static __global__ void capture_scalars_kernel(const Scal* sc, double* out, int k, int len) {
+  if (threadIdx.x == 0) { out[k] = sc->a; out[len + k] = sc->b; }
+}
+// GV residual replacement (gv_cg.py:156-158, then :162-170 with the new w): eta was re-formed from the
+// replaced w (tmp[5]); nu, nu1, b are those of the vector pass
+static __global__ void gv_refinalize_kernel(Scal* sc, int k) {
+  if (threadIdx.x != 0) return;
+  const double eta = sc->tmp[5];
+  sc->eta = eta;
+  sc->mu = sub_(eta, mul_(div_(sc->b, sc->a1), sc->nu));
+  sc->a = div_(sc->nu, sc->mu);
+  note_breakdown(sc, k, sc->a, sc->b);
+}
+
 // multi-GPU: publish the rank's eight initialisation partials (tmp[0..7]) as epoch sepoch
 static __global__ void push_tmp_kernel(const Args g) {
   if (threadIdx.x != 0) return;

@@ -137,6 +137,32 @@ class Session:
                 out[self._lib.cgx_profile_class_name(cls).decode()] = (ms.value, cnt.value)
         return out
 
+    # -- on-device support for save_x / save_r / lanczos_recurrence / GV w_replace ----------
+    def set_capture(self, x=False, r=False, scalars=False):
+        """Record x_k / r_k / (a, b) after every iteration in device memory (next begin/run)."""
+        _lib.check(self._lib.cgx_set_capture(self._ctx, (1 if x else 0) | (2 if r else 0) | (4 if scalars else 0)))
+
+    def fetch_capture(self, which):
+        """which: "x" | "r" -> (max_iter, n) array; "scalars" -> (2, max_iter): rows a, b."""
+        sel = {"x": 0, "r": 1, "scalars": 2}[which]
+        out = np.empty((2, self._max_iter)) if sel == 2 else np.empty((self._max_iter, self.n))
+        _lib.check(self._lib.cgx_fetch_capture_host(self._ctx, sel, _lib.dptr(out)))
+        return out
+
+    def set_gv_replace(self, flags=None):
+        """GV-CG residual replacement schedule (gv_cg.py:156-158): flags[k] truthy -> w_k = A r_k."""
+        if flags is None:
+            _lib.check(self._lib.cgx_set_gv_replace(self._ctx, None, 0))
+        else:
+            f = np.ascontiguousarray(np.asarray(flags, dtype=np.uint8))
+            _lib.check(self._lib.cgx_set_gv_replace(self._ctx, f.ctypes.data_as(C.POINTER(C.c_uint8)), int(f.shape[0])))
+
+    def advance_stages(self, nstages=1):
+        _lib.check(self._lib.cgx_advance_stages(self._ctx, int(nstages)))
+
+    def gv_replace_now(self):
+        _lib.check(self._lib.cgx_gv_replace_now(self._ctx))
+
     def scalars(self):
         out = np.zeros(9)
         _lib.check(self._lib.cgx_get_scalars(self._ctx, _lib.dptr(out)))

@@ -144,13 +144,16 @@ DOT_ORDERS = {"blas": _blas_dot, "pairwise": _pairwise_dot, "reversed": _reverse
 
 
 def solve(variant, A, b, x0, max_iter, dinv=None, x_true=None, history=True, return_state=False,
-          dot=None):
+          dot=None, w_replace=None):
     """Run ``max_iter-1`` iterations of ``variant`` exactly as the reference does.
 
     dinv: None for the identity preconditioner, else the vector the Jacobi lambda
     multiplies by.  Returns the reference's ``output`` dict (name, max_iter and the four
     history arrays, index 0 = initial state); with ``return_state`` also the final
     vectors/scalars (used by the single-iteration kernel tests).
+
+    w_replace: GV only -- the reference's residual-replacement predicate (gv_cg.py:89,156-158),
+    called with the same keywords; None = never (its default).
 
     dot: inner-product implementation; the default is numpy's ``u @ v`` (what the reference
     calls).  Other summation orders (``DOT_ORDERS``) are used ONLY to measure how sensitive
@@ -219,6 +222,7 @@ def solve(variant, A, b, x0, max_iter, dinv=None, x_true=None, history=True, ret
     beta = 0
     _record(hist, 0, A, b, x, r, x_true)
 
+    wk_flags = {}                  # gv_cg.py:123: scratch dict handed to the w_replace predicate
     for k in range(1, max_iter):
         a1, nu1 = a, nu
         if variant == "hs":                                   # hs_cg.py:117-125
@@ -241,11 +245,15 @@ def solve(variant, A, b, x0, max_iter, dinv=None, x_true=None, history=True, ret
             p = rt + beta * p
             s = w + beta * s
             mu = eta - (beta / a1) * nu
-        elif variant == "gv":                                 # gv_cg.py:151-170 (w_replace = never)
+        elif variant == "gv":                                 # gv_cg.py:151-170
+            r_prev = r
             x = x + a1 * p
             r = r - a1 * s
             rt = rt - a1 * st
             w = w - a1 * u
+            if w_replace is not None and w_replace(k=k, A=A, b=b, x=x, w=w, r=r, r_=r_prev, u=u, s=s, p=p,
+                                                   wk_replace_flags=wk_flags):
+                w = A @ r                                     # gv_cg.py:156-158
             wt = M(w)
             t = A @ wt
             nu = dot(r, rt)

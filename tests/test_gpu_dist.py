@@ -163,6 +163,7 @@ def test_partitioned_pr_fused_equals_two_kernel_path(shape, world):
             try:
                 for m in grp.members:
                     m.set_option("pr_fused", fused)
+                    m.set_option("fused_min_slab", 1)          # (thin test slabs: force the fused kernel)
                 for tag in ("pr", "m"):
                     x1, _, infos = grp.solve(tag, b, x0, 2, x_true=x_true)
                     xk, hk, infos = grp.solve(tag, b, x0, 16, x_true=x_true)
