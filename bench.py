@@ -447,6 +447,171 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------- latency-bound tail (configs[4])
+def run_tail(args, rank, world, local_rank):
+    """BASELINE.json configs[4] / SURVEY.md section 8d "allreduce-hiding metric": 3-D Poisson 64^3,
+    fixed 2000 iterations, HS-CG vs PR-CG vs pipe-PR-CG (+ GV, CG-CG).  Per variant, exchange mode
+    (peer-to-peer LL records | ncclAllReduce on a side stream) and path (stream kernels |
+    persistent cooperative kernel): loop time per iteration with the scalar exchange LIVE and
+    STUBBED to a local stand-in, `--tail-reps` repeats each (median, min, max; CUDA events, max
+    over ranks).   exposed = live - stub ;  hidden(v) = 1 - exposed(v) / exposed(base)."""
+    import torch
+    import torch.distributed as dist
+    from new_cg_variants_b200 import PoissonStencil, Session
+    torch.cuda.set_device(local_rank)
+    g = args.tail_grid
+    S = PoissonStencil(g, g, g, dim=3)
+    n = S.shape[0]
+    x_true = np.ones(n) / np.sqrt(n)
+    b, x0, dinv = S @ x_true, np.zeros(n), 1 / S.diagonal()
+    its, reps = args.tail_iters, max(5, args.tail_reps)
+    variants = ("hs", "cg", "pr", "gv", "pipe_pr")
+    stats = lambda v: {"median": statistics.median(v), "min": min(v), "max": max(v)}     # noqa: E731
+    out = {}
+    if world > 1:
+        from new_cg_variants_b200.dist import DistSession
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def timed(sess, v, path):
+        ts = []
+        for rep in range(reps + 1):
+            if world > 1:
+                dist.barrier()
+            info = sess.run(v, its + 1, path=path)
+            t = info["loop_ms"]
+            if world > 1:
+                tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t = tt.item()
+            if rep > 0:
+                ts.append(1e3 * t / its)
+        return ts
+
+    combos = [("p2p", "stream"), ("p2p", "persistent"), ("nccl", "stream")] if world > 1 else [("none", "stream"), ("none", "persistent")]
+    for mode, path in combos:
+        if world > 1:
+            sess = DistSession(S, dinv=dinv, device=local_rank, rank=rank, world=world, mode=mode)
+        else:
+            sess = Session(S, dinv=dinv, device=local_rank)
+        sess.load_problem(b, x0, None)
+        m = {}
+        for v in variants:
+            live = timed(sess, v, path)
+            ent = {"live": stats(live)}
+            if world > 1:
+                sess.set_option("stub_allreduce", 1)
+                stub = timed(sess, v, path)
+                sess.set_option("stub_allreduce", 0)
+                ent["stub"] = stats(stub)
+                ent["exposed"] = ent["live"]["median"] - ent["stub"]["median"]
+                ent["exposed_per_repeat"] = [a - c for a, c in zip(sorted(live), sorted(stub))]
+            m[v] = ent
+        if world > 1:
+            for v in m:
+                for base in ("hs", "pr"):
+                    if m[base]["exposed"] > 0:
+                        m[v][f"hidden_vs_{base}"] = 1 - m[v]["exposed"] / m[base]["exposed"]
+                        m[v][f"hidden_vs_{base}_per_repeat"] = [1 - e / f if f > 0 else None for e, f in
+                                                                zip(m[v]["exposed_per_repeat"], m[base]["exposed_per_repeat"])]
+        out[f"{mode}/{path}"] = m
+        sess.close()
+        if world > 1:
+            dist.barrier()
+    if rank == 0:
+        key = min(out, key=lambda k: out[k]["pipe_pr"]["live"]["median"])
+        best = out[key]
+        line = {"metric": f"latency-bound tail: us/iteration (pipe_pr_pcg, Jacobi, 3-D Poisson {g}^3, {its} iterations)",
+                "value": best["pipe_pr"]["live"]["median"], "unit": "us/iteration", "n_gpus": world, "steps": reps,
+                "warmup": 1, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": f"poisson3d_{g} tail (BASELINE.json configs[4])", "n": n,
+                                                "iters_per_step": its, "best_mode_path": key},
+                "hs_us_per_iteration": best["hs"]["live"]["median"], "pr_us_per_iteration": best["pr"]["live"]["median"],
+                "hidden_fraction": ({"pipe_pr_vs_pr": best["pipe_pr"].get("hidden_vs_pr"), "pipe_pr_vs_hs": best["pipe_pr"].get("hidden_vs_hs"),
+                                     "gv_vs_pr": best["gv"].get("hidden_vs_pr")} if world > 1 else None),
+                "tail": out}
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------- banded model problem (SURVEY 8f rank 3)
+SP_CSR_WORDS = {"sp_hs": 2, "sp_cg": 3, "sp_gv": 2, "sp_pr": 3, "sp_pipe_r": 4, "sp_pipe_n": 2}    # vector words per row
+
+
+def run_banded(args, rank, world, local_rank):
+    """The PETSc driver's model problem (ex2b.c:86-97; n = 650 000, k = 32, 65 non-zeros per row,
+    un-preconditioned, 4000 fixed iterations, strong_scaling_tests.py:49-56,121-126) on the CSR
+    kernels: us/iteration per variant, final error ||x - 1||_2 next to the reference's printed value
+    (slurm-864568.out), and the roofline of the fused CSR SpMV pass on its algorithmic bytes
+    12 nnz + 4 (n+1) + 8 n W.  N > 1: rows are block-partitioned (general-CSR halo lists)."""
+    import torch
+    from new_cg_variants_b200 import Session
+    from new_cg_variants_b200.experiments import BANDED_KAT, banded_model_problem
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        from new_cg_variants_b200.dist import CsrDistSession
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    A, b, x_true = banded_model_problem(args.banded_n, args.banded_k)
+    n, nnz = A.shape[0], A.nnz
+    x0 = np.zeros(n)
+    its = args.banded_iters
+    peak, peak_src = measured_peak()
+    sess = CsrDistSession(A, device=local_rank, rank=rank, world=world) if world > 1 else Session(A, device=local_rank)
+    n_loc, nnz_loc = (sess.n, sess.nnz) if world > 1 else (n, nnz)
+    if world > 1:
+        sess.load_problem(b, x0, None)
+    else:
+        sess.load_problem(b, x0, None)
+    rows = {}
+    for v in ("hs", "cg", "gv", "pr", "pipe_pr", "pipe_p"):
+        best = None
+        for _ in range(max(1, args.steps // 3)):
+            if world > 1:
+                dist.barrier()
+            info = sess.run(v, its + 1, histories=(), path="stream")
+            t = info["loop_ms"]
+            if world > 1:
+                tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t = tt.item()
+            best = t if best is None else min(best, t)
+        x = sess.fetch(want_hist=False)[0] if world == 1 else sess.gather_x(sess.fetch_local(want_hist=False)[0])
+        err = float(np.linalg.norm(x - x_true))
+        sess.set_profile(True)
+        sess.run(v, min(its, 300) + 1, histories=(), path="stream")
+        prof = sess.get_profile()
+        sess.set_profile(False)
+        row = {"us_per_iteration": 1e3 * best / its, "iterations_per_s": its / (best / 1e3), "error_2_norm": err,
+               "reference_error_2_norm": BANDED_KAT.get(v), "kernels": {}}
+        for kname, (ms, cnt) in prof.items():
+            us = 1e3 * ms / cnt
+            row["kernels"][kname] = {"us": us}
+            if kname in SP_CSR_WORDS:
+                by = 12.0 * nnz_loc + 4.0 * (n_loc + 1) + 8.0 * n_loc * SP_CSR_WORDS[kname]
+                row["kernels"][kname].update(GBps=by / (us * 1e-6) / 1e9, algorithmic_bytes=by, frac=by / (us * 1e-6) / 1e9 / peak)
+        rows[v] = row
+    if rank == 0:
+        v = args.variant if args.variant in rows else "pr"
+        spk = max((k for k in rows[v]["kernels"] if k in SP_CSR_WORDS), key=lambda k: rows[v]["kernels"][k]["us"])
+        kk = rows[v]["kernels"][spk]
+        traffic, traffic_note = read_traffic("csr_" + spk)
+        line = {"metric": f"CG iterations/s ({REF_FUN.get(v, v)}, un-preconditioned, banded model problem n={n} k={args.banded_k})",
+                "value": rows[v]["iterations_per_s"], "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": rows[v]["us_per_iteration"] * its / 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"banded model problem (ex2b.c:86-97) n={n} k={args.banded_k} nnz={nnz}, {its} iterations",
+                           "l2": "matrix + vectors = %.2f GB per iteration >> 126 MB L2" % ((12.0 * nnz + 8.0 * n * 12) / 1e9)},
+                "roofline": {"bound": "hbm", "kernel": "csr_stream<%s>" % spk, "achieved": kk["GBps"], "peak": peak, "unit": "GB/s",
+                             "frac": kk["frac"], "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": kk["algorithmic_bytes"], "avg_launch_ms": kk["us"] / 1e3},
+                "variants": rows}
+        emit(line)
+    sess.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _REAL_STDOUT = None
 
 
@@ -481,6 +646,15 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=10, help="iterations of the cpu_baseline sample")
     ap.add_argument("--path", default="auto", choices=["auto", "stream", "persistent"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="headline", choices=["headline", "tail", "banded"],
+                    help="headline: configs[3] (default, the driver's contract); tail: configs[4] latency-bound 64^3 "
+                         "allreduce-hiding experiment; banded: the PETSc driver's banded model problem as a CSR benchmark")
+    ap.add_argument("--banded-n", type=int, default=650000)
+    ap.add_argument("--banded-k", type=int, default=32)
+    ap.add_argument("--banded-iters", type=int, default=4000)
+    ap.add_argument("--tail-grid", type=int, default=64)
+    ap.add_argument("--tail-iters", type=int, default=2000)
+    ap.add_argument("--tail-reps", type=int, default=5)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -492,6 +666,12 @@ def main():
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         ap.error("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
+    if args.config == "tail":
+        run_tail(args, rank, world, local_rank)
+        return
+    if args.config == "banded":
+        run_banded(args, rank, world, local_rank)
+        return
     run_ours(args, rank, world, local_rank)
 
 

@@ -218,6 +218,20 @@ int cgx_solve_host(cgx_ctx* ctx, int variant, const double* b_host, const double
  *      with the same arguments).  Histories are the global ones on every rank. */
 int cgx_set_stencil_slab(cgx_ctx* ctx, int64_t nx, int64_t ny, int64_t nz_local, int world,
                          int rank, double diag, double off);
+/* General CSR row partition (SURVEY.md section 8e "General CSR"; the layout of the reference's PETSc
+ * driver, ex2b.c:71, and what its mpi4py column blocks transpose to for a symmetric matrix): rank
+ * `rank` owns n_local consecutive rows.  indices are LOCAL: a column owned by this rank is its local
+ * row number (0 .. n_local-1), a column owned by another rank is n_local + j with j the position of
+ * that global column in this rank's sorted ghost list (n_ghost entries; the entries of one source
+ * rank are contiguous).  The stored order inside a row is unchanged, so row sums keep scipy's
+ * rounding.  recv_count[r] = ghost entries owned by rank r; send_count[r] / send_idx = the local rows
+ * rank r needs (concatenated per destination, in the order of r's ghost list); send_off[r] = where
+ * this rank's segment starts in r's ghost list; nghost_of[r] = n_ghost of rank r.
+ * Then the same set-up as for slabs: window handles -> cgx_dist_commit -> local problem vectors. */
+int cgx_set_csr_part_host(cgx_ctx* ctx, int64_t n_local, int64_t n_ghost, int64_t nnz, const int32_t* indptr_host,
+                          const int32_t* indices_host, const double* data_host, int world, int rank,
+                          const int32_t* recv_count, const int32_t* send_count, const int32_t* send_idx_host,
+                          const int32_t* send_off, const int32_t* nghost_of);
 int cgx_dist_ipc_handle(cgx_ctx* ctx, void* handle64);
 int cgx_dist_attach_ipc(cgx_ctx* ctx, int peer_rank, const void* handle64);
 int cgx_dist_attach_ctx(cgx_ctx* ctx, int peer_rank, cgx_ctx* peer);

@@ -69,6 +69,8 @@ PROTOTYPES = {
     "cgx_fetch_host": (C.c_int, [_P, c_double_p, c_double_p]),
     "cgx_fetch_dev": (C.c_int, [_P, _P, _P]),
     "cgx_fetch_vector_host": (C.c_int, [_P, C.c_char_p, c_double_p]),
+    "cgx_set_csr_part_host": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, c_int32_p, c_int32_p, c_double_p, C.c_int, C.c_int,
+                                        c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
     "cgx_set_capture": (C.c_int, [_P, C.c_uint]),
     "cgx_fetch_capture_host": (C.c_int, [_P, C.c_int, c_double_p]),
     "cgx_set_gv_replace": (C.c_int, [_P, C.POINTER(C.c_uint8), C.c_int]),

@@ -11,9 +11,12 @@ anything with those three methods, e.g. a real `MPI.COMM_WORLD` -- and the rows 
 partitioned in contiguous blocks as in the reference (rank r owns rows r*m .. (r+1)*m-1).
 
 `A` may be
-  * a `PoissonStencil` (the global operator; partitioned into slabs over the ranks), or
-  * on one rank: a scipy sparse / dense matrix (e.g. the reference's model problem
-    `np.diag(Lambda)`, scaling_tests.py:31-53, as `model_problem(n)` builds it).
+  * the reference's own operand: a dense `(n, n/P)` ndarray, this rank's COLUMN block of a symmetric
+    matrix (scaling_tests.py:44-50) -- its transpose is this rank's row block, which is what is
+    uploaded (general CSR row partition, ghost entries gathered through index lists);
+  * a square scipy sparse / dense matrix: the global operator, held by every rank (row blocks are cut
+    here; e.g. `model_problem(n)` or `experiments.banded_model_problem`);
+  * a `PoissonStencil` (the global operator; partitioned into z-slabs over the ranks).
 `b` is this rank's slice `(n/P,)`.  The reference's solvers count `max_iter` updates of x; the
 numerical-experiment functions count `max_iter - 1`, hence the `+ 1` below.
 """
@@ -49,6 +52,27 @@ class GpuComm:
         if self._dist:
             self._dist.barrier(self.group)
 
+    # the two collectives scaling_tests.py uses around the solvers (numpy buffers, mpi4py semantics)
+    def Scatter(self, sendbuf, recvbuf, root=0):
+        if not self._dist:
+            recvbuf[...] = np.asarray(sendbuf).reshape(recvbuf.shape)
+            return
+        size, rank = self.Get_size(), self.Get_rank()
+        parts = [np.ascontiguousarray(p) for p in np.asarray(sendbuf).reshape(size, -1)] if rank == root else None
+        out = [None]
+        self._dist.scatter_object_list(out, parts, src=root, group=self.group)
+        recvbuf[...] = out[0].reshape(recvbuf.shape)
+
+    def Gather(self, sendbuf, recvbuf, root=0):
+        if not self._dist:
+            recvbuf[...] = np.asarray(sendbuf).reshape(recvbuf.shape)
+            return
+        size, rank = self.Get_size(), self.Get_rank()
+        parts = [None] * size if rank == root else None
+        self._dist.gather_object(np.ascontiguousarray(sendbuf), parts, dst=root, group=self.group)
+        if rank == root:
+            recvbuf[...] = np.stack(parts).reshape(recvbuf.shape)
+
 
 _SESSIONS = {}          # (id(A), size, rank) -> (A, session); holding A keeps its id from being reused
 _MAX_SESSIONS = 4
@@ -64,18 +88,26 @@ def _operator_session(comm, A, m):
         return _SESSIONS[key][1]
     while len(_SESSIONS) >= _MAX_SESSIONS:
         _SESSIONS.pop(next(iter(_SESSIONS)))[1].close()
-    if isinstance(A, PoissonStencil):
+    shape = getattr(A, "shape", None)
+    column_block = (not isinstance(A, PoissonStencil)) and shape is not None and len(shape) == 2 and shape[0] != shape[1]
+    if column_block:                                   # (n, n/P): the reference's operand (scaling_tests.py:44-50)
+        n = shape[0]
+        if shape[1] != m or n != m * size:
+            raise ValueError(f"column block of shape {shape} does not match b of length {m} on {size} ranks")
+        rows = sps.csr_matrix(np.ascontiguousarray(np.asarray(A).T) if not sps.issparse(A) else A.T)
         if size == 1:
-            sess = Session(A)
+            sess = Session(rows)
         else:
             from .dist import DistSession
-            sess = DistSession(A, dinv=None, rank=rank, world=size, group=getattr(comm, "group", None))
+            sess = DistSession(rows, dinv=None, rank=rank, world=size, group=getattr(comm, "group", None),
+                               row_block=(rank * m, (rank + 1) * m), n_global=n)
     elif size == 1:
         sess = Session(A)
     else:
-        raise NotImplementedError("on several GPUs the operator must be a PoissonStencil (row-partitioned into "
-                                  "slabs); general matrices -- including the reference's dense column blocks -- "
-                                  "run on one rank")
+        from .dist import DistSession
+        sess = DistSession(A, dinv=None, rank=rank, world=size, group=getattr(comm, "group", None))
+        if sess.n != m:
+            raise ValueError(f"b has {m} entries on rank {rank}, the row block of A has {sess.n}")
     _SESSIONS[key] = (A, sess)
     return sess
 

@@ -61,8 +61,8 @@ static int nccl_load(const char* path) {
 const char* const kVecNames[V_COUNT] = {"x", "r", "rt", "p", "s", "st", "w", "wt", "u", "t"};
 
 static void free_op(cgx_ctx* c) {
-  cudaFree(c->d_ptr); cudaFree(c->d_idx); cudaFree(c->d_val); cudaFree(c->d_rowblk);
-  c->d_ptr = c->d_idx = c->d_rowblk = nullptr; c->d_val = nullptr;
+  cudaFree(c->d_ptr); cudaFree(c->d_idx); cudaFree(c->d_val); cudaFree(c->d_rowblk); cudaFree(c->d_send_idx);
+  c->d_ptr = c->d_idx = c->d_rowblk = c->d_send_idx = nullptr; c->d_val = nullptr;
   c->n_rowblk = 0;
   c->h_ptr.clear();
   c->op_kind = 0;
@@ -183,17 +183,7 @@ static void build_row_blocks(const int32_t* ptr, i64 n, std::vector<int>& blk) {
   }
 }
 
-extern "C" int cgx_set_csr_host(cgx_ctx* c, int64_t n, int64_t nnz, const int32_t* indptr,
-                                const int32_t* indices, const double* data) {
-  if (!c || n <= 0 || nnz < 0 || !indptr || (nnz > 0 && (!indices || !data)))
-    return fail(CGX_ERR_ARG, "cgx_set_csr_host: bad arguments");
-  if (n >= (1ll << 31) || nnz >= (1ll << 31))
-    return fail(CGX_ERR_UNSUPPORTED, "cgx_set_csr_host: int32 index range exceeded");
-  if (indptr[0] != 0 || indptr[n] != nnz)
-    return fail(CGX_ERR_ARG, "cgx_set_csr_host: indptr[0] != 0 or indptr[n] != nnz");
-  if (c->dist.world > 1)
-    return fail(CGX_ERR_UNSUPPORTED, "cgx_set_csr_host: row-partitioned runs take the stencil operator "
-                "(cgx_set_stencil_slab); CSR matrices are single-GPU");
+static int upload_csr(cgx_ctx* c, i64 n, i64 nnz, const int32_t* indptr, const int32_t* indices, const double* data) {
   CU(cudaSetDevice(c->device));
   free_op(c);
   reset_size(c, n);
@@ -215,6 +205,74 @@ extern "C" int cgx_set_csr_host(cgx_ctx* c, int64_t n, int64_t nnz, const int32_
   c->h_ptr.assign(indptr, indptr + n + 1);
   c->csr = CsrOp{c->d_ptr, c->d_idx, c->d_val, n};
   c->op_kind = 1;
+  return CGX_OK;
+}
+
+extern "C" int cgx_set_csr_host(cgx_ctx* c, int64_t n, int64_t nnz, const int32_t* indptr,
+                                const int32_t* indices, const double* data) {
+  if (!c || n <= 0 || nnz < 0 || !indptr || (nnz > 0 && (!indices || !data)))
+    return fail(CGX_ERR_ARG, "cgx_set_csr_host: bad arguments");
+  if (n >= (1ll << 31) || nnz >= (1ll << 31))
+    return fail(CGX_ERR_UNSUPPORTED, "cgx_set_csr_host: int32 index range exceeded");
+  if (indptr[0] != 0 || indptr[n] != nnz)
+    return fail(CGX_ERR_ARG, "cgx_set_csr_host: indptr[0] != 0 or indptr[n] != nnz");
+  if (c->dist.world > 1)
+    return fail(CGX_ERR_UNSUPPORTED, "cgx_set_csr_host: this context is a rank of a partitioned run; "
+                "use cgx_set_csr_part_host (row block + ghost lists)");
+  return upload_csr(c, n, nnz, indptr, indices, data);
+}
+
+static void dist_release(cgx_ctx* c);
+extern "C" int cgx_set_csr_part_host(cgx_ctx* c, int64_t n, int64_t n_ghost, int64_t nnz, const int32_t* indptr,
+                                     const int32_t* indices, const double* data, int world, int rank,
+                                     const int32_t* recv_count, const int32_t* send_count, const int32_t* send_idx,
+                                     const int32_t* send_off, const int32_t* nghost_of) {
+  if (!c || n <= 0 || nnz < 0 || n_ghost < 0 || !indptr || (nnz > 0 && (!indices || !data)) || world < 1 || world > kMaxWorld ||
+      rank < 0 || rank >= world || (world > 1 && (!recv_count || !send_count || !send_off || !nghost_of)))
+    return fail(CGX_ERR_ARG, "cgx_set_csr_part_host: bad arguments (world <= %d)", kMaxWorld);
+  if (n + n_ghost >= (1ll << 31) || nnz >= (1ll << 31))
+    return fail(CGX_ERR_UNSUPPORTED, "cgx_set_csr_part_host: int32 index range exceeded");
+  if (indptr[0] != 0 || indptr[n] != nnz) return fail(CGX_ERR_ARG, "cgx_set_csr_part_host: indptr[0] != 0 or indptr[n] != nnz");
+  for (i64 e = 0; e < nnz; ++e)
+    if (indices[e] < 0 || indices[e] >= n + n_ghost) return fail(CGX_ERR_ARG, "cgx_set_csr_part_host: column index out of range");
+  CU(cudaSetDevice(c->device));
+  dist_release(c);
+  int rc = upload_csr(c, n, nnz, indptr, indices, data);
+  if (rc || world == 1) return rc;
+  Dist& d = c->dist;
+  d.world = world; d.rank = rank; d.mode = 1; d.saved_mode = 1; d.csr = 1;
+  d.has_lo = d.has_hi = 0; d.plane = 0;
+  d.nghost = (int)n_ghost;
+  d.src_mask = 0;
+  i64 total_send = 0, total_recv = 0;
+  d.send_ptr[0] = 0;
+  for (int r = 0; r < world; ++r) {
+    if (recv_count[r] < 0 || send_count[r] < 0 || (r == rank && (recv_count[r] || send_count[r])))
+      return fail(CGX_ERR_ARG, "cgx_set_csr_part_host: bad send/receive counts");
+    if (recv_count[r] > 0) d.src_mask |= 1u << r;
+    total_recv += recv_count[r];
+    total_send += send_count[r];
+    d.send_ptr[r + 1] = (int)total_send;
+    d.send_off[r] = send_off[r];
+    d.nghost_of[r] = nghost_of[r];
+  }
+  if (total_recv != n_ghost || nghost_of[rank] != n_ghost) return fail(CGX_ERR_ARG, "cgx_set_csr_part_host: receive counts do not add up to n_ghost");
+  if (total_send > 0) {
+    if (!send_idx) return fail(CGX_ERR_ARG, "cgx_set_csr_part_host: send_idx is NULL");
+    for (i64 e = 0; e < total_send; ++e)
+      if (send_idx[e] < 0 || send_idx[e] >= n) return fail(CGX_ERR_ARG, "cgx_set_csr_part_host: send index out of range");
+    CU(cudaMalloc(&c->d_send_idx, sizeof(int) * total_send));
+    CU(cudaMemcpy(c->d_send_idx, send_idx, sizeof(int) * total_send, cudaMemcpyHostToDevice));
+  }
+  d.send_idx = c->d_send_idx;
+  c->win_bytes = kWinHdrBytes + sizeof(double) * (size_t)kChan * 2 * (size_t)std::max<i64>(n_ghost, 1);
+  CU(cudaMalloc(&c->d_win, c->win_bytes));
+  CU(cudaMemset(c->d_win, 0, c->win_bytes));
+  CU(cudaDeviceSynchronize());
+  c->peer_base[rank] = c->d_win;
+  c->epoch = 0; c->scpar = 0; c->pend.clear();
+  for (auto& h : c->hepoch) h = 0;
+  c->fepoch = 0;
   return CGX_OK;
 }
 
@@ -339,6 +397,10 @@ void plan_commit(cgx_ctx* c, const Args& g, const Plan& p) {
 
 VecIn vec_in(cgx_ctx* c, const double* v, int ch, const Args& g) {
   VecIn a{v, nullptr, nullptr};
+  if (c->dist.world > 1 && c->dist.csr) {
+    if (c->dist.ghost) a.lo = c->dist.ghost + (size_t)(ch * 2 + g.hin_par) * (size_t)c->dist.nghost;
+    return a;
+  }
   if (c->dist.world > 1 && c->dist.ghost) {
     a.lo = c->dist.ghost + ghost_off(c->dist, ch, g.hin_par, 0);
     a.hi = c->dist.ghost + ghost_off(c->dist, ch, g.hin_par, 1);
@@ -366,8 +428,13 @@ void launch_halo_push(cgx_ctx* c, Args g, const double* v, int ch) {
   p.hout_n = 1; p.hout_ch = ch;
   plan_apply(c, g, p);
   g.halo_ll = 0;                      // plain ghost planes + halo epoch flags (generic consumers)
-  halo_push_kernel<<<grid_for(c, c->dist.plane), kBlock, 0, c->stream>>>(g, v);
-  c->launches++;
+  if (c->dist.csr) {
+    const int total = c->dist.send_ptr[c->dist.world];
+    if (total > 0) { csr_halo_push_kernel<<<grid_for(c, total), kBlock, 0, c->stream>>>(g, v); c->launches++; }
+  } else {
+    halo_push_kernel<<<grid_for(c, c->dist.plane), kBlock, 0, c->stream>>>(g, v);
+    c->launches++;
+  }
   plan_commit(c, g, p);
 }
 
@@ -448,7 +515,9 @@ void launch_instrument(cgx_ctx* c, Args g) {
     ProfScope ps(c, PC_INSTR);
     const VecIn xin = vec_in(c, c->vec[V_X], 2, g);
     VecIn xtin{c->d_xtrue, nullptr, nullptr};
-    if (c->dist.world > 1 && c->dist.ghost) {
+    if (c->dist.world > 1 && c->dist.csr) {
+      if (c->dist.ghost) xtin.lo = c->dist.ghost + (size_t)(3 * 2 + g.xt_par) * (size_t)c->dist.nghost;
+    } else if (c->dist.world > 1 && c->dist.ghost) {
       xtin.lo = c->dist.ghost + ghost_off(c->dist, 3, g.xt_par, 0);
       xtin.hi = c->dist.ghost + ghost_off(c->dist, 3, g.xt_par, 1);
     }
@@ -794,7 +863,9 @@ static int begin_prepare(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
     // measured (profiles/r01d_overlap_*): on a partition the persistent kernel wins at 2 GPUs
     // (64^3: 10-25 vs 21-31 us/iteration) and loses at 8 (22-45 vs 17-29): its all-to-all record
     // exchange is on the critical path of a much shorter iteration
-    const bool world_ok = c->dist.world <= 2;
+    const bool world_ok = c->dist.world <= 2 && !csr_dist(c);
+    if (path == CGX_PATH_PERSISTENT && csr_dist(c))
+      return fail(CGX_ERR_UNSUPPORTED, "cgx_begin: CSR row partitions run the stream kernels");
     if (path == CGX_PATH_AUTO)
       path = (c->n < c->pers_threshold && G.ok && mode_ok && world_ok) ? CGX_PATH_PERSISTENT : CGX_PATH_STREAM;
     if (path == CGX_PATH_PERSISTENT && !G.ok)
@@ -1300,10 +1371,12 @@ extern "C" int cgx_dist_commit(cgx_ctx* c, int mode, const char* nccl_libpath, c
     d.win[r] = reinterpret_cast<WinHdr*>(c->peer_base[r]);
   }
   d.ghost = reinterpret_cast<double*>(c->d_win + kWinHdrBytes);
+  if (d.csr)
+    for (int r = 0; r < d.world; ++r) d.stage_of[r] = reinterpret_cast<double*>(c->peer_base[r] + kWinHdrBytes);
   d.ghost_lo = d.has_lo ? reinterpret_cast<double*>(c->peer_base[d.rank - 1] + kWinHdrBytes) : nullptr;
   d.ghost_hi = d.has_hi ? reinterpret_cast<double*>(c->peer_base[d.rank + 1] + kWinHdrBytes) : nullptr;
   const size_t ll_at = kWinHdrBytes + sizeof(double) * (size_t)kChan * 4 * (size_t)d.plane;
-  d.ghl = reinterpret_cast<u64*>(c->d_win + ll_at);
+  d.ghl = d.csr ? nullptr : reinterpret_cast<u64*>(c->d_win + ll_at);
   d.ghl_lo = d.has_lo ? reinterpret_cast<u64*>(c->peer_base[d.rank - 1] + ll_at) : nullptr;
   d.ghl_hi = d.has_hi ? reinterpret_cast<u64*>(c->peer_base[d.rank + 1] + ll_at) : nullptr;
   d.mode = mode; d.saved_mode = mode;

@@ -178,6 +178,7 @@ struct WinHdr {
   // across NVLink).  [slot][producer rank][2 words per value]
   u64 ll[kSlots][kMaxWorld][2 * kSumW];
   u64 hflag[kChan][2][2];          // [channel][parity][side]; side 0 = plane below, 1 = above
+  u64 gflag[kChan][2][kMaxWorld];  // general CSR partition: [channel][parity][source rank] ghost-entry epochs
   int error;                       // set when a bounded wait expired
   int pad;
 };
@@ -201,6 +202,18 @@ struct Dist {
   double* nccl_in;                 // mode 2: [kSlots][kSumW] local partials / reduced totals
   double* nccl_out;
   i64 plane;                       // points per exchanged plane
+  // ---- general CSR row partition (SURVEY.md section 8e "General CSR"): the ghost entries of an SpMV
+  //      input are gathered by index lists.  Rank r's window holds a staging array
+  //      [kChan][2 parity][nghost_of[r]] after the header; the column indices of the local matrix
+  //      address it as n_local + j.  A source rank's entries form one contiguous segment of it.
+  int csr;                         // 1: this partition is a CSR row partition (no slabs, no planes)
+  int nghost;                      // ghost entries of this rank
+  unsigned src_mask;               // ranks this rank receives ghost entries from
+  int send_ptr[kMaxWorld + 1];     // this rank's send entries per destination rank (prefix sums)
+  int send_off[kMaxWorld];         // where this rank's segment starts in the destination's staging array
+  int nghost_of[kMaxWorld];        // staging length of every rank
+  const int* send_idx;             // device: local row indices to send, concatenated per destination
+  double* stage_of[kMaxWorld];     // every rank's staging array (peer mapped)
 };
 
 __device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {

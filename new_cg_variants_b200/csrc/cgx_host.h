@@ -68,6 +68,7 @@ struct cgx_ctx {
   std::vector<int> h_ptr;          // host copy of indptr (persistent kernel: shared-memory slab sizing)
   bool no_elide = false;           // cgx_set_option("cg_elide", 0)
   bool no_slab = false;            // cgx_set_option("csr_slab", 0)
+  int* d_send_idx = nullptr;       // CSR row partition: local rows to send (Dist::send_idx)
   int* d_rowblk = nullptr;         // CSR-stream row blocks (cgx_kernels.cuh)
   int n_rowblk = 0;
   i64 n = 0, nnz = 0;
@@ -213,7 +214,9 @@ int ctx_occupancy(cgx_ctx* c, const void* fn, int threads, size_t smem);
 inline size_t tma_smem_bytes(int nv) { return (size_t)kRing * nv * kPlaneStride * sizeof(double) + 128; }
 
 // kernel launches ("stages") of one iteration without the instrumentation
-inline int core_stages(const cgx_ctx* c) { return c->pr_fused ? 1 : (c->variant == CGX_HS ? 3 : 2); }
+// (a CSR row partition adds one stage: the gather-and-push of the SpMV input's ghost entries)
+inline bool csr_dist(const cgx_ctx* c) { return c->dist.world > 1 && c->dist.csr; }
+inline int core_stages(const cgx_ctx* c) { return c->pr_fused ? 1 : (c->variant == CGX_HS ? 3 : 2) + (csr_dist(c) ? 1 : 0); }
 bool tma_encode_dims(double* ptr, i64 nx, i64 ny, i64 nz, CUtensorMap* out);
 // cgx_fused.cu
 int cgx_fused_prepare(cgx_ctx* c);              // second buffers + tensor maps; sets c->pr_fused

@@ -6,6 +6,20 @@
 #error "compile with -DCGX_PM=0|1|2"
 #endif
 
+// CSR row partition: the ghost entries of the vector(s) the SpMV pass is about to read
+static void csr_push_stage(cgx_ctx* c, const Args& g) {
+  switch (c->variant) {
+    case CGX_HS: case CGX_PR: case CGX_M: launch_halo_push(c, g, c->vec[V_P], 0); break;
+    case CGX_CG: launch_halo_push(c, g, c->vec[V_RT], 0); break;
+    case CGX_GV: launch_halo_push(c, g, c->vec[V_WT], 0); break;
+    case CGX_PIPE_PR: case CGX_PIPE_PR_M:
+      launch_halo_push(c, g, c->vec[V_ST], 0);
+      launch_halo_push(c, g, c->vec[V_RT], 1);
+      break;
+    default: launch_halo_push(c, g, c->vec[V_ST], 0); break;      // pipe_p, pipe_p_m
+  }
+}
+
 template <int PM>
 static void iter_stage_pm(cgx_ctx* c, int s, const Args& g) {
   const int core = core_stages(c);
@@ -20,6 +34,10 @@ static void iter_stage_pm(cgx_ctx* c, int s, const Args& g) {
       if (c->capture) launch_capture(c, g);
     }
     return;
+  }
+  if (csr_dist(c)) {                 // ... ew stage(s), push, SpMV pass
+    if (s == core - 2) { csr_push_stage(c, g); return; }
+    if (s == core - 1) s -= 1;
   }
   switch (c->variant) {
     case CGX_HS:

@@ -110,8 +110,11 @@ __device__ __forceinline__ double vload(const VecIn& a, i64 j, i64 n, i64 plane)
   if constexpr (SLAB) {
     if (j < 0) return a.lo[j + plane];
     if (j >= n) return a.hi[j - n];
+    return a.v[j];
+  } else {
+    // CSR row partition: columns >= n address the staging array of gathered ghost entries
+    return (j < n ? a.v : a.lo - n)[j];
   }
-  return a.v[j];
 }
 
 // Stage tags
@@ -331,9 +334,16 @@ __device__ __forceinline__ void halo_store(const Args& g, int c, i64 i, const Pk
 }
 // Generic (non-TMA) consumers: one thread waits for the ghost planes of channels
 // hin_ch .. hin_ch+nch-1 before the CTA reads them.
+__device__ __forceinline__ void csr_wait_channel(const Args& g, int ch, int par, u64 epoch) {
+  WinHdr* w = g.d.win[g.d.rank];
+  for (int r = 0; r < g.d.world; ++r)
+    if (g.d.src_mask & (1u << r)) wait_epoch(&w->gflag[ch][par][r], epoch, &w->error);
+}
 __device__ __forceinline__ void halo_wait_all(const Args& g, int nch) {
   if (g.d.world > 1) {
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && g.d.csr) {
+      for (int c = 0; c < nch; ++c) csr_wait_channel(g, g.hin_ch + c, g.hin_par, g.hin_epoch);
+    } else if (threadIdx.x == 0) {
       WinHdr* w = g.d.win[g.d.rank];
       for (int c = 0; c < nch; ++c) {
         if (g.d.has_lo) wait_epoch(&w->hflag[g.hin_ch + c][g.hin_par][0], g.hin_epoch, &w->error);
@@ -679,6 +689,11 @@ __global__ void __launch_bounds__(kBlock) csr_stream_kernel(const CsrOp A, const
   __shared__ double prod[NV][kCsrCap];
   double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
   const int tid = threadIdx.x;
+  halo_wait_all(g, NV);
+  // row partition: column >= n -> gathered ghost entry (same pointer otherwise: lo is never selected)
+  const int nloc = (int)g.n;
+  auto ld0 = [&](int cj) { return (cj < nloc ? in0.v : in0.lo - nloc)[cj]; };
+  auto ld1 = [&](int cj) { return (cj < nloc ? in1.v : in1.lo - nloc)[cj]; };
   for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
     const int r0 = __ldg(row_blocks + blk), r1 = __ldg(row_blocks + blk + 1);
     const int e0 = __ldg(A.ptr + r0), e1 = __ldg(A.ptr + r1);
@@ -693,7 +708,7 @@ __global__ void __launch_bounds__(kBlock) csr_stream_kernel(const CsrOp A, const
         for (int j = tid; j < cnt; j += kBlock) {
           const double av = __ldg(A.val + e0 + j);
           const int cj = __ldg(A.idx + e0 + j);
-          prod[0][j] = mul_(av, in0.v[cj]);
+          prod[0][j] = mul_(av, ld0(cj));
         }
       } else {
       constexpr int kU = kCsrCap / kBlock;
@@ -709,8 +724,8 @@ __global__ void __launch_bounds__(kBlock) csr_stream_kernel(const CsrOp A, const
       double x0v[kU], x1v[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-        x0v[u] = in0.v[col[u]];
-        if constexpr (NV == 2) x1v[u] = in1.v[col[u]]; else x1v[u] = 0.0;
+        x0v[u] = ld0(col[u]);
+        if constexpr (NV == 2) x1v[u] = ld1(col[u]); else x1v[u] = 0.0;
       }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
@@ -744,8 +759,8 @@ __global__ void __launch_bounds__(kBlock) csr_stream_kernel(const CsrOp A, const
         for (int j = tid; j < m; j += kBlock) {
           const double a = __ldg(A.val + e0 + base + j);
           const int col = __ldg(A.idx + e0 + base + j);
-          prod[0][j] = mul_(a, in0.v[col]);
-          if constexpr (NV == 2) prod[1][j] = mul_(a, in1.v[col]);
+          prod[0][j] = mul_(a, ld0(col));
+          if constexpr (NV == 2) prod[1][j] = mul_(a, ld1(col));
         }
         __syncthreads();
         if (tid == 0)
@@ -774,7 +789,9 @@ template <class Op, bool HAS_XTRUE>
 __global__ void __launch_bounds__(kBlock) instrument_kernel(const Op A, const Args g, const VecIn xin,
                                                            const VecIn xtin) {
   constexpr bool SL = Op::kSlab;
-  if (HAS_XTRUE && g.d.world > 1 && threadIdx.x == 0) {
+  if (HAS_XTRUE && g.d.world > 1 && threadIdx.x == 0 && g.d.csr) {
+    csr_wait_channel(g, 3, g.xt_par, g.xt_epoch);
+  } else if (HAS_XTRUE && g.d.world > 1 && threadIdx.x == 0) {
     WinHdr* w = g.d.win[g.d.rank];
     if (g.d.has_lo) wait_epoch(&w->hflag[3][g.xt_par][0], g.xt_epoch, &w->error);
     if (g.d.has_hi) wait_epoch(&w->hflag[3][g.xt_par][1], g.xt_epoch, &w->error);
@@ -837,6 +854,24 @@ static __global__ void __launch_bounds__(kBlock) halo_push_kernel(const Args g, 
     if (g.d.has_hi) g.d.ghost_hi[ghost_off(g.d, g.hout_ch, g.hout_par, 0) + i] = v[g.n - pl + i];
   }
   grid_last_finalize(g.ticket, [&]() { dist_publish<0>(g, nullptr); });
+}
+
+// CSR row partition: gather the entries of v the other ranks need and store them into their staging
+// arrays (channel hout_ch, parity hout_par), then publish the epoch to every destination.
+static __global__ void __launch_bounds__(kBlock) csr_halo_push_kernel(const Args g, const double* __restrict__ v) {
+  const int total = g.d.send_ptr[g.d.world];
+  const i64 stride = (i64)gridDim.x * kBlock;
+  for (i64 i = (i64)blockIdx.x * kBlock + threadIdx.x; i < total; i += stride) {
+    int q = 0;
+    while ((int)i >= g.d.send_ptr[q + 1]) ++q;
+    double* dst = g.d.stage_of[q] + (size_t)(g.hout_ch * 2 + g.hout_par) * (size_t)g.d.nghost_of[q] + g.d.send_off[q] +
+                  ((int)i - g.d.send_ptr[q]);
+    *dst = v[g.d.send_idx[i]];
+  }
+  grid_last_finalize(g.ticket, [&]() {
+    for (int q = 0; q < g.d.world; ++q)
+      if (g.d.send_ptr[q + 1] > g.d.send_ptr[q]) st_relaxed_sys(&g.d.win[q]->gflag[g.hout_ch][g.hout_par][g.d.rank], g.hout_epoch);
+  });
 }
 
 // -------------------------------------------------------------------------------------

@@ -2,6 +2,11 @@
 rank per GPU, halo planes by peer-to-peer stores over NVLink, the fused scalars summed in
 rank order on every GPU.
 
+Operators: a ``PoissonStencil`` is cut into z-slabs (halo = boundary planes); any scipy sparse or
+dense matrix is cut into contiguous row blocks whose ghost entries are gathered through per-neighbour
+index lists (the layout of the reference's PETSc driver, ex2b.c:71; the reference's mpi4py column
+blocks of a symmetric matrix transpose to exactly these row blocks).
+
 ``DistSession``  one rank of a torchrun job (one process per GPU); ``torch.distributed`` is
                  used only to hand the 64-byte window handles (and the NCCL id) around and
                  for barriers -- never on the data path.
@@ -17,6 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+from pickle import dumps as pickle_dumps, loads as pickle_loads
 
 import numpy as np
 
@@ -57,6 +63,60 @@ def row_range(S: PoissonStencil, world: int, rank: int):
     return z0 * nx * ny, z1 * nx * ny
 
 
+# ---- general CSR row partition (SURVEY.md section 8e "General CSR") ------------------------------
+def block_rows(n: int, world: int):
+    """Contiguous row ranges [r0, r1) per rank, sizes differing by at most one (the reference's
+    mpi4py drivers use n/P rows per rank, scaling_tests.py:44-50; PETSc's default split likewise)."""
+    if world < 1 or n < world:
+        raise ValueError(f"cannot cut {n} rows into {world} non-empty blocks")
+    base, extra = divmod(n, world)
+    out, r = [], 0
+    for k in range(world):
+        m = base + (1 if k < extra else 0)
+        out.append((r, r + m))
+        r += m
+    return out
+
+
+def csr_local_block(A_rows, row0, row1):
+    """Rows [row0, row1) of a global matrix given as a CSR block with GLOBAL column indices
+    (shape (row1-row0, n)) -> (local CSR arrays with columns remapped, sorted ghost column list).
+    A column owned by this rank becomes its local row number, any other column becomes
+    n_local + (its position in the ghost list); the stored order inside a row is untouched."""
+    import scipy.sparse as sps
+    A_rows = sps.csr_matrix(A_rows)
+    A_rows.sort_indices()
+    n_loc = row1 - row0
+    cols = A_rows.indices.astype(np.int64)
+    owned = (cols >= row0) & (cols < row1)
+    ghost = np.unique(cols[~owned])
+    new = np.where(owned, cols - row0, n_loc + np.searchsorted(ghost, cols))
+    return (A_rows.indptr.astype(np.int32), new.astype(np.int32), np.ascontiguousarray(A_rows.data, dtype=np.float64),
+            ghost.astype(np.int64))
+
+
+def csr_exchange_lists(ghosts, ranges, rank):
+    """From every rank's sorted ghost list: what `rank` receives and sends.
+    -> recv_count[r], send_count[r], send_idx (local rows, concatenated per destination),
+       send_off[r] (start of this rank's segment in r's ghost list), nghost_of[r]."""
+    world = len(ranges)
+    row0, row1 = ranges[rank]
+    mine = ghosts[rank]
+    recv = [int(np.count_nonzero((mine >= a) & (mine < b))) for a, b in ranges]
+    send_count, send_off, send_idx = [], [], []
+    for q in range(world):
+        g = ghosts[q]
+        lo, hi = int(np.searchsorted(g, row0)), int(np.searchsorted(g, row1))
+        if q == rank:
+            lo = hi = 0
+        send_count.append(hi - lo)
+        send_off.append(lo)
+        send_idx.append((g[lo:hi] - row0).astype(np.int32))
+    i32 = lambda v: np.ascontiguousarray(np.asarray(v, dtype=np.int32))          # noqa: E731
+    return (i32(recv), i32(send_count), i32(np.concatenate(send_idx) if send_idx else []), i32(send_off),
+            i32([len(g) for g in ghosts]))
+
+
 def nccl_library_path():
     """libnccl.so.2 bundled with torch (the library this process already has loaded)."""
     try:
@@ -91,9 +151,6 @@ class _RankBase:
     """Shared by DistSession / the members of a GroupSession."""
 
     def _create(self, S, world, rank, device):
-        if not isinstance(S, PoissonStencil):
-            raise NotImplementedError("row-partitioned runs take a PoissonStencil operator "
-                                      "(CSR matrices of the reference are single-GPU cases)")
         self._lib = _lib.load()
         self.S, self.world, self.rank, self.device = S, int(world), int(rank), int(device)
         self.n_global = S.shape[0]
@@ -105,6 +162,25 @@ class _RankBase:
         _lib.check(self._lib.cgx_ctx_create(self.device, C.byref(self._ctx)))
         _lib.check(self._lib.cgx_set_stencil_slab(self._ctx, nx, ny, z1 - z0, self.world, self.rank,
                                                   S.diag, S.off))
+        self.info = None
+        self._max_iter = 0
+
+    def _create_csr(self, blk, ghosts, ranges, world, rank, device, n_global):
+        """blk = csr_local_block(...) of this rank; ghosts = every rank's ghost list."""
+        self._lib = _lib.load()
+        self.S, self.world, self.rank, self.device = None, int(world), int(rank), int(device)
+        self.n_global = int(n_global)
+        self.row0, self.row1 = ranges[rank]
+        self.n = self.row1 - self.row0
+        indptr, indices, data, ghost = blk
+        self.nnz = int(indptr[-1])
+        recv, send_count, send_idx, send_off, nghost_of = csr_exchange_lists(ghosts, ranges, rank)
+        self._ctx = C.c_void_p()
+        _lib.check(self._lib.cgx_ctx_create(self.device, C.byref(self._ctx)))
+        _lib.check(self._lib.cgx_set_csr_part_host(
+            self._ctx, self.n, len(ghost), self.nnz, _lib.iptr(indptr), _lib.iptr(indices), _lib.dptr(data),
+            self.world, self.rank, _lib.iptr(recv), _lib.iptr(send_count),
+            _lib.iptr(send_idx) if len(send_idx) else None, _lib.iptr(send_off), _lib.iptr(nghost_of)))
         self.info = None
         self._max_iter = 0
 
@@ -166,13 +242,33 @@ class DistSession(_RankBase):
     """This process's rank of a partitioned operator (``torch.distributed`` must be
     initialised; any backend).  Every method is collective."""
 
-    def __init__(self, S, dinv=None, device=None, rank=None, world=None, mode="p2p", group=None):
+    def __init__(self, S, dinv=None, device=None, rank=None, world=None, mode="p2p", group=None, row_block=None,
+                 n_global=None):
+        """S: a PoissonStencil (z-slab partition), or a scipy sparse / dense matrix (general CSR row
+        partition: contiguous row blocks, ghost entries gathered through index lists).  A matrix is
+        either the GLOBAL one, held by every rank, or -- with ``row_block=(row0, row1)`` and
+        ``n_global`` -- only this rank's rows (shape (row1-row0, n_global), global column indices);
+        the ghost lists are then exchanged through torch.distributed."""
         import torch.distributed as dist
         self.group = group
         rank = dist.get_rank(group) if rank is None else rank
         world = dist.get_world_size(group) if world is None else world
         device = int(os.environ.get("LOCAL_RANK", rank)) if device is None else device
-        self._create(S, world, rank, device)
+        if isinstance(S, PoissonStencil):
+            self._create(S, world, rank, device)
+        else:
+            import scipy.sparse as sps
+            if row_block is None:
+                A = sps.csr_matrix(S)
+                n_global = A.shape[0]
+                ranges = block_rows(n_global, world)
+                blk = csr_local_block(A[ranges[rank][0]:ranges[rank][1]], *ranges[rank])
+            else:
+                ranges = [tuple(r) for r in (pickle_loads(x) for x in exchange_bytes(pickle_dumps(tuple(row_block)), group))] \
+                    if world > 1 else [tuple(row_block)]
+                blk = csr_local_block(S, *ranges[rank])
+            ghosts = [np.frombuffer(x, dtype=np.int64) for x in exchange_bytes(blk[3].tobytes(), group)] if world > 1 else [blk[3]]
+            self._create_csr(blk, ghosts, ranges, world, rank, device, n_global)
         self.mode = mode
         if self.world > 1:
             handle = (C.c_ubyte * 64)()
@@ -280,9 +376,18 @@ class GroupSession:
         self.n = S.shape[0]
         devices = [0] * self.world if devices is None else list(devices)
         self.members = []
+        if not isinstance(S, PoissonStencil):          # general CSR row partition
+            import scipy.sparse as sps
+            A = sps.csr_matrix(S)
+            ranges = block_rows(self.n, self.world)
+            blks = [csr_local_block(A[a:b], a, b) for a, b in ranges]
+            ghosts = [blk[3] for blk in blks]
         for r in range(self.world):
             m = GroupSession._Member()
-            m._create(S, self.world, r, devices[r])
+            if isinstance(S, PoissonStencil):
+                m._create(S, self.world, r, devices[r])
+            else:
+                m._create_csr(blks[r], ghosts, ranges, self.world, r, devices[r], self.n)
             self.members.append(m)
         if self.world > 1:
             for a in self.members:

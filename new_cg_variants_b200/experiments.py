@@ -72,6 +72,49 @@ def convergence_metrics(error_A_norm, error_tol=1e-5):
         return int(np.argmin(rel > error_tol)), float(np.log10(np.nanmin(rel)))
 
 
+def format_table_row(matrix_name, preconditioner, n, nnz, iters, accuracies):
+    r"""One row of figures/convergence_table_data.tex, written from the row format
+
+        \texttt{name} & prec & n & nnz & {it_1} ... & {it_m} &{acc_1} ... &{acc_m}\\
+
+    name with escaped underscores; prec "Jac." or "-"; an iteration count of 0 ("never reached
+    1e-5") prints as "-"; accuracies with two decimals.  A cell is wrapped in \tableemph when the
+    variant is visibly worse than the first column (HS-CG): more than 10 % more iterations or no
+    convergence; attainable accuracy (a negative log10) above 0.9 of the first column's."""
+    head = ["\\texttt{%s}" % matrix_name.replace("_", "\\_"), "Jac." if preconditioner == "jacobi" else "-", str(n), str(nnz)]
+    it_cells, acc_cells = [], []
+    for it, acc in zip(iters, accuracies):
+        slow = it == 0 or it > 1.1 * iters[0]
+        it_cells.append("& %s{%s}" % ("\\tableemph" if slow else "", it if it else "-"))
+        acc_cells.append("&%s{%.2f}" % ("\\tableemph" if acc > 0.9 * accuracies[0] else "", acc))
+    return " & ".join(head) + "".join(it_cells) + "".join(acc_cells) + "\\\\ \n"
+
+
+def banded_model_problem(n=650000, k=32, kappa=1e6, rho=0.95, off=1e-4):
+    """The PETSc driver's model problem (scaling_experiments_petsc/ex2b.c:86-97,
+    strong_scaling_tests.py:49-56) as a scipy CSR matrix: half-bandwidth k (2k+1 non-zeros per
+    interior row), off-diagonals `off`, diagonal 1 + (i/(n-1)) (kappa-1) rho^(n-1-i); the driver
+    solves A x = A 1 from x0 = 0 without preconditioner and prints ||x - 1||_2
+    (ex2b.c:138-139,192-200).  Returns (A, b, x_true)."""
+    import scipy.sparse as sps
+    i = np.arange(n, dtype=np.float64)
+    diag = 1.0 + (i / (n - 1)) * (kappa - 1) * rho ** (n - 1 - i)
+    offs = [o for o in range(-k, k + 1) if o != 0]
+    A = sps.diags([np.full(n - abs(o), off) for o in offs], offs, shape=(n, n), format="csr") + sps.diags(diag)
+    A = sps.csr_matrix(A)
+    A.sort_indices()
+    x_true = np.ones(n)
+    return A, A @ x_true, x_true
+
+
+# final errors ||x - 1||_2 after 4000 iterations printed by the reference's run on 336 / 280 MPI ranks
+# (scaling_experiments_petsc/config_info/slurm-864568.out:129,148,167,186,205 and :224-300); PETSc KSP
+# names -> ours (strong_scaling_plots.py:72-79): cg = HS, chcg = CG-CG, pipecg = GV, pipeprcg = pipe-PR,
+# pipeprcg_0 (-recompute_q 0) = pipe-P
+BANDED_KAT = {"hs": (1.60099e-07, 1.88385e-07), "cg": (2.46479e-07, 2.17013e-07), "gv": (0.000135586, 0.000125243),
+              "pipe_pr": (3.24332e-07, 3.10494e-07), "pipe_p": (8.94408e-05, 8.74067e-05)}
+
+
 def parse_convergence_data(matrix_name, preconditioner=None, variants=TABLE_METHODS, A=None, n=None, nnz=None,
                            data_dir="./data", trials=None, write=True):
     """figure_gen.py:62-124: one LaTeX table row (also written to <dir>/convergence.txt)."""
@@ -86,17 +129,7 @@ def parse_convergence_data(matrix_name, preconditioner=None, variants=TABLE_METH
         it, acc = convergence_metrics(trial["error_A_norm"])
         min_iters.append(it)
         min_errors.append(acc)
-    formatted_matrix_name = r"\texttt{" + matrix_name.replace("_", r"\_") + r"}"
-    formatted_preconditioner = "Jac." if preconditioner == "jacobi" else "-"
-    data = f"{formatted_matrix_name} & {formatted_preconditioner} & {n} & {nnz}"
-    data_iter = data_err = ""
-    for k in range(len(min_errors)):
-        formatted_min_iter = min_iters[k] if min_iters[k] != 0 else "-"
-        mi_bold = "\\tableemph" if ((min_iters[k] > 1.1 * min_iters[0]) or (min_iters[k] == 0)) else ""
-        me_bold = "\\tableemph" if (min_errors[k] > .9 * min_errors[0]) else ""
-        data_iter += f"& {mi_bold}{{{formatted_min_iter}}}"
-        data_err += f"&{me_bold}{{{min_errors[k]:1.2f}}}"
-    data += data_iter + data_err + "\\\\ \n"
+    data = format_table_row(matrix_name, preconditioner, n, nnz, min_iters, min_errors)
     if write:
         os.makedirs(out_dir, exist_ok=True)
         with open(os.path.join(out_dir, "convergence.txt"), "w") as fh:

@@ -57,6 +57,40 @@ def main():
                 ok = ok and same
             grp.close()
         dist.barrier()
+    # general CSR row partition: multi-process run == single-GPU emulation, bit for bit
+    import json
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import helpers
+    A = helpers.load_matrix("bcsstk16")
+    xt, bA, x0A = helpers.orc.setup_problem(A)
+    dA = helpers.orc.jacobi_dinv(A)
+    sess = DistSession(A, dinv=dA, device=local)
+    res = {}
+    for tag in ("hs", "cg", "gv", "pr", "pipe_pr"):
+        x_loc, h, info = sess.solve(tag, bA, x0A, 20, x_true=xt, histories=hist, path="stream")
+        res[tag] = (sess.gather_x(x_loc), h)
+    sess.close()
+    if rank == 0:
+        grp = GroupSession(A, world, dinv=dA, devices=[local] * world)
+        for tag, (x, h) in res.items():
+            xg, hg, _ = grp.solve(tag, bA, x0A, 20, x_true=xt)
+            same = np.array_equal(x, xg) and all(np.array_equal(h[k], hg[k], equal_nan=True) for k in hist)
+            print(f"[csr partition] {tag}: {'match' if same else 'MISMATCH'}", flush=True)
+            ok = ok and same
+        grp.close()
+    dist.barrier()
+    # the reference's scaling_tests.py protocol on its own model problem (dense column blocks), P ranks:
+    # final errors within x2 of the reference's 1-rank run (tests/golden/mpi_kat.json)
+    from new_cg_variants_b200 import scaling_tests as st
+    kat = json.load(open(os.path.join(helpers.GOLDEN, "mpi_kat.json")))
+    out = st.run(kat["pr"]["n"], kat["pr"]["max_iter"], "worker", save=False, verbose=False)
+    if rank == 0:
+        for tag, fn in (("hs", "hs_cg"), ("cg", "cg_cg"), ("gv", "gv_cg"), ("pr", "pr_cg"), ("pipe_pr", "pipe_pr_cg")):
+            ratio = out[fn]["error"] / kat[tag]["error"]
+            good = 0.5 <= ratio <= 2.0 and out[fn]["timings"]["tot"] > 0
+            print(f"[scaling_tests] {fn}: error {out[fn]['error']:.3e} (reference {kat[tag]['error']:.3e}) {'ok' if good else 'MISMATCH'}", flush=True)
+            ok = ok and good
+    dist.barrier()
     # the reference's distributed signature f(comm, A, b, max_iter) -> (x_local, times)
     from new_cg_variants_b200 import Session, cg_variants_mpi4py as m
     comm = m.GpuComm()

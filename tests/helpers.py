@@ -4,13 +4,15 @@ Parity rule (BASELINE.json north_star + SURVEY.md section 8c, made precise in DE
 section "Parity"):
 
   P1  for k < window: |dev - ref| / |ref| <= 1e-10 on updated_residual_2_norm and
-      residual_2_norm, where ``window`` (tests/golden/cases.json) = min(k*, ensemble):
-      k* = first k at which the reference leaves exact_pcg by 1e-10 (north_star: "until the
-      reference curve departs from exact arithmetic"), ensemble = iterations over which the
-      reference still agrees to 1e-10 with itself under five other inner-product summation
-      orders (oracle.DOT_ORDERS) -- past that point "1e-10" is a property of one BLAS build,
-      not of the algorithm.  The measured first-deviation index kd of every device run is
-      logged (gpurun_out/parity_kd.jsonl -> profiles/parity_r02.md);
+      residual_2_norm, where ``window`` (tests/golden/cases.json) = min(kstar11, ensemble11):
+      the iterations over which the reference has not yet left exact_pcg by 1e-11 (north_star:
+      "until the reference curve departs from exact arithmetic") and still agrees to 1e-11 with
+      itself under five other inner-product summation orders (oracle.DOT_ORDERS).  The device's
+      1e-10 thus has one decade of margin over the reference's own sensitivity to rounding
+      order; with both thresholds at 1e-10 (kstar10, ensemble -- also stored) the window would
+      end where a further summation order has an even chance of having crossed the line: the
+      measured first-deviation index kd of every device run is logged next to all four numbers
+      (gpurun_out/parity_kd.jsonl -> profiles/parity_r02.md);
   P2  attainable accuracy: log10(min_k rel. A-norm error) within log10(2) of the band the
       reference itself spans under those summation orders, widened by the band's width;
   P3  iterations to rel. A-norm error <= 1e-5 within max(1, 1 %) of that band, widened by
@@ -133,6 +135,10 @@ def check_metrics(dev, band, label=""):
     """P2 / P3 against the band the reference spans under re-ordered inner products."""
     it, acc = orc.convergence_metrics(dev["error_A_norm"])
     lo, hi = band["acc_band"]
+    # an error at or below machine precision (incl. exactly 0: diagonal matrices terminate exactly) is
+    # "converged to rounding", whatever its last digits
+    floor = math.log10(2.0 ** -52)
+    acc, lo, hi = max(acc, floor), max(lo, floor), max(hi, floor)
     width = hi - lo
     assert lo - width - math.log10(2) <= acc <= hi + width + math.log10(2), \
         f"{label}: attainable accuracy 1e{acc:.2f} outside reference band [{lo:.2f}, {hi:.2f}]"

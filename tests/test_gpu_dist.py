@@ -179,3 +179,60 @@ def test_partitioned_pr_fused_equals_two_kernel_path(shape, world):
             np.testing.assert_allclose(f[1], t[1], rtol=1e-9, atol=1e-13)
             for h in orc.HISTORIES:
                 np.testing.assert_allclose(f[2][h][:12], t[2][h][:12], rtol=1e-10, err_msg=f"{shape}x{world}/{tag}/{h}")
+
+
+def _csr_cases():
+    import scipy.sparse as sps
+    from new_cg_variants_b200.experiments import banded_model_problem
+    from new_cg_variants_b200.cg_variants_mpi4py import model_problem
+    return {
+        "bcsstk16": helpers.load_matrix("bcsstk16"),                       # ghost entries from several ranks
+        "1138_bus": helpers.load_matrix("1138_bus"),
+        "banded": banded_model_problem(n=3000, k=7)[0],                    # the PETSc driver's matrix, small
+        "model_diag": model_problem(1536)[0],                              # scaling_tests.py:31-53: no ghosts at all
+        "poisson2d_24": orc.poisson2d(24),
+    }
+
+
+@pytest.mark.parametrize("name", ["bcsstk16", "1138_bus", "banded", "model_diag", "poisson2d_24"])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_general_csr_row_partition_matches_single_gpu(name, world):
+    """SURVEY.md section 8e "General CSR": contiguous row blocks, ghost entries gathered through
+    per-neighbour index lists into staging arrays, rank-ordered scalar exchange.  Every variant
+    against the single-context run: the row sums are bit-identical (same stored order), the dots
+    are summed per rank then in rank order -> agreement to rounding; all ranks hold identical
+    histories; bitwise repeatable."""
+    A = _csr_cases()[name]
+    x_true, b, x0 = orc.setup_problem(A)
+    for dinv in (orc.jacobi_dinv(A), None):
+        grp = GroupSession(A, world, dinv=dinv)
+        one = Session(A, dinv=dinv)
+        try:
+            for tag in ALL_TAGS:
+                xg, hg, infos = grp.solve(tag, b, x0, 12, x_true=x_true)
+                xg2, hg2, _ = grp.solve(tag, b, x0, 12, x_true=x_true)
+                x1, h1, _ = one.solve(tag, b, x0, 12, x_true=x_true, path="stream")
+                assert all(i["kernel_launches"] > 0 and i["path"] == 1 for i in infos)
+                np.testing.assert_allclose(xg, x1, rtol=1e-8, atol=1e-12 * np.abs(x1).max(), err_msg=f"{name}x{world}/{tag}")
+                assert np.array_equal(xg, xg2)
+                for h in orc.HISTORIES:
+                    np.testing.assert_allclose(hg[h][:8], h1[h][:8], rtol=1e-10, err_msg=f"{name}x{world}/{tag}/{h}")
+                    assert np.array_equal(hg[h], hg2[h], equal_nan=True)
+        finally:
+            grp.close()
+            one.close()
+
+
+def test_csr_partition_parity_with_oracle():
+    """The parity rule on a CSR row partition (bcsstk15 + Jacobi fixture, 4 row blocks)."""
+    case = "bcsstk15_jacobi"
+    A, b, x0, x_true, dinv, max_iter = helpers.case_problem(case)
+    bands = helpers.cases()[case]["kstar"]
+    grp = GroupSession(A, 4, dinv=dinv)
+    try:
+        for tag in ("hs", "pr", "pipe_pr", "gv"):
+            _, dev, _ = grp.solve(tag, b, x0, max_iter, x_true=x_true)
+            live = orc.solve(tag, A, b, x0, max_iter, dinv=dinv, x_true=x_true)
+            helpers.check_parity(dev, live, bands[tag], f"{case}/{tag} x4 row blocks")
+    finally:
+        grp.close()

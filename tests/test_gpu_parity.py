@@ -88,7 +88,8 @@ def test_variants_match_oracle_and_goldens(case, path):
         kd = min(helpers.first_deviation(dev[h], live[h]) for h in helpers.RESIDUAL_HISTS)
         it, acc = orc.convergence_metrics(dev["error_A_norm"])
         helpers.log_kd(case=case, variant=tag, path=path, kd=kd, window=bands[tag]["window"],
-                       kstar10=bands[tag]["kstar10"], ensemble=bands[tag].get("ensemble"), max_iter=max_iter,
+                       kstar10=bands[tag]["kstar10"], ensemble=bands[tag].get("ensemble"),
+                       kstar11=bands[tag].get("kstar11"), ensemble11=bands[tag].get("ensemble11"), max_iter=max_iter,
                        iters=it, acc=acc, iters_band=bands[tag]["iters_band"], acc_band=bands[tag]["acc_band"])
         helpers.check_parity(dev, live, bands[tag], f"{case}/{tag} vs live oracle")
         gold = {h: helpers.golden_history(case, tag, h) for h in (orc.HISTORIES if full else helpers.RESIDUAL_HISTS)}
@@ -121,14 +122,18 @@ def test_long_runs_match_reference_metrics(case):
                        acc_band=band and band["acc_band"], stored=stored, published=pub)
         if band:
             helpers.check_metrics(dev, band, f"{case}/{tag}")
+        # coarse regression against the reference's 2019 runs: attainable accuracy
+        # within one decade, iterations-to-1e-5 within 5 % when both reached it -- each widened by the
+        # spread the reference itself shows under re-ordered dots (e.g. bcsstm24 GV: 1987 ... 34297
+        # iterations across the ensemble; the 2019 run took 19411)
+        aw = (band["acc_band"][1] - band["acc_band"][0]) if band else 0.0
+        iw = (band["iters_band"][1] - band["iters_band"][0]) if band and min(band["iters_band"]) > 0 else 0
         for src, ref in (("stored .npy", stored), ("published table", pub)):
             if ref is None:
                 continue
-            # coarse regression against the reference's 2019 runs: attainable
-            # accuracy within one decade, iterations-to-1e-5 within 5 % when both reached it
-            assert abs(acc - ref[1]) <= 1.0, (case, tag, src, acc, ref)
+            assert abs(acc - ref[1]) <= 1.0 + aw, (case, tag, src, acc, ref)
             if ref[0] and it:
-                assert abs(it - ref[0]) <= max(3, 0.05 * ref[0]), (case, tag, src, it, ref)
+                assert abs(it - ref[0]) <= max(3, 0.05 * ref[0]) + iw, (case, tag, src, it, ref)
 
 
 def test_unpreconditioned_twins_and_names():
@@ -539,3 +544,35 @@ def test_pr_fused_single_launch_equals_two_kernel_path(shape):
                 np.testing.assert_allclose(res[key][1], res["two"][1], rtol=1e-10, atol=1e-13, err_msg=f"{shape}/{tag}/{key}")
                 for h in orc.HISTORIES:
                     np.testing.assert_allclose(res[key][2][h], res["two"][2][h], rtol=1e-10, err_msg=f"{shape}/{tag}/{key}/{h}")
+
+
+def test_banded_model_problem_final_errors_match_the_petsc_run():
+    """the reference's PETSc driver problem (ex2b.c:86-97: n = 650 000,
+    half-bandwidth 32, kappa = 1e6, rho = 0.95, off-diagonals 1e-4, x* = 1, no preconditioner, 4000
+    fixed iterations) on the CSR kernels.  KAT: the final ||x - 1||_2 the reference printed for its
+    cg / chcg / pipecg / pipeprcg / pipeprcg_0 solvers (slurm-864568.out:129-205 on 336 ranks, :224-300
+    on 280 ranks -- they differ by up to 17 % between the two process counts, i.e. the value is an
+    attainable-accuracy level, pinned here within a factor 3)."""
+    from new_cg_variants_b200.experiments import BANDED_KAT, banded_model_problem
+    A, b, x_true = banded_model_problem()
+    assert A.shape[0] == 650000 and A.nnz == 650000 * 65 - 32 * 33
+    x0 = np.zeros(A.shape[0])
+    got = {}
+    with Session(A) as s:
+        s.load_problem(b, x0, None)
+        for tag in BANDED_KAT:
+            info = s.run(tag, 4001, histories=(), path="stream")
+            assert info["iterations"] == 4000
+            x, _ = s.fetch(want_hist=False)
+            got[tag] = float(np.linalg.norm(x - x_true))
+    print("banded model problem, ||x - 1||_2 after 4000 iterations (ours | reference 336 ranks, 280 ranks):",
+          {t: (f"{got[t]:.3e}", BANDED_KAT[t]) for t in got})
+    for tag, ref in BANDED_KAT.items():
+        # CG-CG: the reference's PYTHON cg_cg (what this library restates, parity-checked above) is an order of
+        # magnitude less accurate than PETSc's KSP chcg on such problems -- its own mpi4py model-problem errors
+        # are 1.1e-7 (hs) vs 2.1e-6 (cg), SURVEY.md section 8c -- so that row is only bounded within x10
+        f = 10 if tag == "cg" else 3
+        lo, hi = min(ref) / f, max(ref) * f
+        assert lo <= got[tag] <= hi, (tag, got[tag], ref)
+    # the paper's point on this problem: pipe-PR recovers HS-level accuracy, GV / pipe-P lose 2-3 digits
+    assert got["pipe_pr"] < 10 * got["hs"] and got["gv"] > 50 * got["hs"] and got["pipe_p"] > 50 * got["hs"]

@@ -51,7 +51,9 @@ def test_every_figure_gen_case_has_a_fixture():
     for k, m in c.items():
         if m["kstar"] is not None:
             for tag, band in m["kstar"].items():
-                assert band["window"] == (band["ensemble"] if band["kstar10"] is None else min(band["kstar10"], band["ensemble"]))
+                if "ensemble11" in band:
+                    assert band["window"] == (band["ensemble11"] if band["kstar11"] is None else min(band["kstar11"], band["ensemble11"]))
+                    assert band["window"] <= band["ensemble"] and (band["kstar10"] is None or band["window"] <= band["kstar10"])
 
 
 def test_goldens_match_reference_first_values():
