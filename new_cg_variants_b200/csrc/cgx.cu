@@ -422,18 +422,26 @@ int ctx_occupancy(cgx_ctx* c, const void* fn, int threads, size_t smem) {
 
 
 // multi-GPU: push the boundary planes of v into the neighbours' ghost planes of channel ch
-void launch_halo_push(cgx_ctx* c, Args g, const double* v, int ch) {
+void launch_halo_push(cgx_ctx* c, Args g, const double* v, int ch) { launch_halo_push2(c, g, v, nullptr, ch); }
+// one or two vectors (channels ch, ch + 1) under ONE halo epoch -- the consumer of a 2-RHS pass waits for
+// a single epoch (that of channel ch) on both channels
+void launch_halo_push2(cgx_ctx* c, Args g, const double* v0, const double* v1, int ch) {
   if (c->dist.world <= 1) return;
   Plan p;
-  p.hout_n = 1; p.hout_ch = ch;
+  p.hout_n = v1 ? 2 : 1; p.hout_ch = ch;
   plan_apply(c, g, p);
   g.halo_ll = 0;                      // plain ghost planes + halo epoch flags (generic consumers)
-  if (c->dist.csr) {
-    const int total = c->dist.send_ptr[c->dist.world];
-    if (total > 0) { csr_halo_push_kernel<<<grid_for(c, total), kBlock, 0, c->stream>>>(g, v); c->launches++; }
-  } else {
-    halo_push_kernel<<<grid_for(c, c->dist.plane), kBlock, 0, c->stream>>>(g, v);
-    c->launches++;
+  const double* vs[2] = {v0, v1};
+  for (int i = 0; i < p.hout_n; ++i) {
+    g.hout_ch = ch + i;
+    g.hout_n = 1;
+    if (c->dist.csr) {
+      const int total = c->dist.send_ptr[c->dist.world];
+      if (total > 0) { csr_halo_push_kernel<<<grid_for(c, total), kBlock, 0, c->stream>>>(g, vs[i]); c->launches++; }
+    } else {
+      halo_push_kernel<<<grid_for(c, c->dist.plane), kBlock, 0, c->stream>>>(g, vs[i]);
+      c->launches++;
+    }
   }
   plan_commit(c, g, p);
 }

@@ -225,6 +225,7 @@ void cgx_fused_push_initial_halo(cgx_ctx* c);   // partitioned runs: boundary pl
 double* cgx_cur_vec(cgx_ctx* c, int v);         // the buffer that currently holds state vector v
 
 void launch_halo_push(cgx_ctx* c, Args g, const double* v, int ch);
+void launch_halo_push2(cgx_ctx* c, Args g, const double* v0, const double* v1, int ch);
 void launch_instrument(cgx_ctx* c, Args g);
 void launch_hist_consume(cgx_ctx* c, Args g);
 void launch_capture(cgx_ctx* c, const Args& g);

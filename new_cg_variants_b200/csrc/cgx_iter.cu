@@ -13,8 +13,7 @@ static void csr_push_stage(cgx_ctx* c, const Args& g) {
     case CGX_CG: launch_halo_push(c, g, c->vec[V_RT], 0); break;
     case CGX_GV: launch_halo_push(c, g, c->vec[V_WT], 0); break;
     case CGX_PIPE_PR: case CGX_PIPE_PR_M:
-      launch_halo_push(c, g, c->vec[V_ST], 0);
-      launch_halo_push(c, g, c->vec[V_RT], 1);
+      launch_halo_push2(c, g, c->vec[V_ST], c->vec[V_RT], 0);
       break;
     default: launch_halo_push(c, g, c->vec[V_ST], 0); break;      // pipe_p, pipe_p_m
   }

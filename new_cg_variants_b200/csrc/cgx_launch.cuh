@@ -67,6 +67,7 @@ static void launch_ew(cgx_ctx* c, Args g) {
   p.produce = EwKind<KID>::FK;
   p.hout_ch = 0;
   p.hout_n = (KID == EW_HS1) ? 0 : (KID == EW_PIPE_R ? 2 : 1);
+  if (csr_dist(c)) p.hout_n = 0;      // CSR row partition: the ghost entries are gathered by a stage of their own
   plan_apply(c, g, p);
   {
     // One resident wave: on a partition every CTA folds the all-rank records before it streams

@@ -216,7 +216,10 @@ def test_general_csr_row_partition_matches_single_gpu(name, world):
                 np.testing.assert_allclose(xg, x1, rtol=1e-8, atol=1e-12 * np.abs(x1).max(), err_msg=f"{name}x{world}/{tag}")
                 assert np.array_equal(xg, xg2)
                 for h in orc.HISTORIES:
-                    np.testing.assert_allclose(hg[h][:8], h1[h][:8], rtol=1e-10, err_msg=f"{name}x{world}/{tag}/{h}")
+                    # (the banded / diagonal model problems converge to rounding level within a few
+                    # iterations: absolute floor relative to the k = 0 entry)
+                    np.testing.assert_allclose(hg[h][:8], h1[h][:8], rtol=1e-10, atol=1e-12 * h1[h][0],
+                                               err_msg=f"{name}x{world}/{tag}/{h}")
                     assert np.array_equal(hg[h], hg2[h], equal_nan=True)
         finally:
             grp.close()
