@@ -342,6 +342,9 @@ Args make_args(cgx_ctx* c) {
   g.n = c->n; g.k = c->cur_k;
   g.d = c->dist;
   g.halo_ll = c->halo_ll ? 1 : 0;
+  // L2 residency hint: measured at 2.1 M rows (one slab of 256^3 / 8) 2-6 % per iteration; auto = on when this
+  // GPU's state vectors (<= 10 x n) fit well inside the 126 MB L2
+  g.l2pol = (c->l2_keep == 1 || (c->l2_keep < 0 && c->n > 0 && (size_t)c->n * 8 * 6 < ((size_t)96 << 20))) ? kL2EvictLast : 0;
   g.dbg = c->dbg;
   g.dbg_t = c->d_dbg_t;
   return g;
@@ -505,6 +508,7 @@ static int setup_tma(cgx_ctx* c, unsigned need) {
   for (int i = 0; i < V_COUNT; ++i)
     if ((need & (1u << i)) && c->vec[i] && !c->tmap_ok[i]) all_ok = false;
   c->halo_ll = c->dist.world > 1 && all_ok;
+  if (c->halo_ll && !c->d_gscr) CU(cudaMalloc(&c->d_gscr, sizeof(double) * 4 * (size_t)c->dist.plane));   // [2 sides][2 rhs][plane]
   if (c->dist.world > 1 && !all_ok) {                 // mixed would mix the two ghost formats: all generic
     for (auto& ok : c->tmap_ok) ok = false;
     return CGX_OK;
@@ -1126,6 +1130,7 @@ extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
   if (!strcmp(name, "pr_fused")) { c->no_fused = (value == 0); return CGX_OK; }
   if (!strcmp(name, "gv_manual")) { c->gv_manual = value != 0; return CGX_OK; }
   if (!strcmp(name, "fused_min_planes")) { c->fused_min_planes = std::max(1, value); return CGX_OK; }
+  if (!strcmp(name, "l2_keep")) { c->l2_keep = value; return CGX_OK; }
   if (!strcmp(name, "fused_min_slab")) { c->fused_min_slab = std::max(1, value); return CGX_OK; }
   if (!strcmp(name, "fused_chunks")) { c->fused_chunks = std::max(0, value); return CGX_OK; }
   if (!strcmp(name, "persistent_threshold")) { c->pers_threshold = value; return CGX_OK; }
@@ -1429,9 +1434,12 @@ extern "C" int cgx_spmv_host(cgx_ctx* c, const double* v, double* y, int64_t n) 
   if (c->op_kind == 2 && tma_prepare_geom(c) && tma_encode_dims(dv, c->sten.nx, c->sten.ny, c->sten.nz, &tm)) {
     // the TMA-staged stencil kernel in its plainest mode (SP_PIPE_N: u = A v, no epilogue)
     g.u = dy;
-    ctx_occupancy(c, (const void*)stencil_tma_kernel<SP_PIPE_N, 0, false>, kTmaThreads, tma_smem_bytes(1));
-    stencil_tma_kernel<SP_PIPE_N, 0, false><<<c->tma_grid[0], kTmaThreads, tma_smem_bytes(1), c->stream>>>(
-        tm, tm, c->geom, g);
+    const int per_sm = ctx_occupancy(c, (const void*)stencil_tma_kernel<SP_PIPE_N, 0, false>, kSThreads, tma_smem_bytes(1));
+    TmaGeom G = c->geom;
+    const int cap = per_sm * c->sm_count, ncols = G.ntx * G.nty;
+    G.nchunk = std::max(1, std::min(cap / std::max(1, ncols), G.nz / std::max(1, c->tma_min_planes)));
+    stencil_tma_kernel<SP_PIPE_N, 0, false><<<(int)std::min<i64>((i64)ncols * G.nchunk, cap), kSThreads, tma_smem_bytes(1), c->stream>>>(
+        tm, tm, G, g);
     c->launches++;
   } else {
     launch_spmv<SP_PLAIN, 0, false>(c, g, dv, dy);

@@ -44,19 +44,25 @@ __device__ __forceinline__ double axmy_(double r, double a, double s) { return s
 // ---- 1- and 2-wide packs for 128-bit global accesses ----------------------------------
 template <int W> struct Pk { double v[W]; };
 
-template <int W> __device__ __forceinline__ Pk<W> ldp(const double* __restrict__ p, i64 i) {
+// pol != 0: an L2 cache-policy word (createpolicy encoding, e.g. kL2EvictLast) -- partitioned runs whose
+// per-GPU working set fits the 126 MB L2 ask the cache to keep the state vectors (global pointers only).
+constexpr unsigned long long kL2EvictLast = 0x14F0000000000000ull;     // fractional 1.0, L2::evict_last
+template <int W> __device__ __forceinline__ Pk<W> ldp(const double* __restrict__ p, i64 i, unsigned long long pol = 0) {
   Pk<W> o;
   if constexpr (W == 2) {
-    double2 t = *reinterpret_cast<const double2*>(p + i);
+    double2 t;
+    if (pol) asm volatile("ld.global.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(t.x), "=d"(t.y) : "l"(p + i), "l"(pol));
+    else t = *reinterpret_cast<const double2*>(p + i);
     o.v[0] = t.x; o.v[1] = t.y;
   } else {
     o.v[0] = p[i];
   }
   return o;
 }
-template <int W> __device__ __forceinline__ void stp(double* __restrict__ p, i64 i, const Pk<W>& o) {
+template <int W> __device__ __forceinline__ void stp(double* __restrict__ p, i64 i, const Pk<W>& o, unsigned long long pol = 0) {
   if constexpr (W == 2) {
-    *reinterpret_cast<double2*>(p + i) = make_double2(o.v[0], o.v[1]);
+    if (pol) asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p + i), "d"(o.v[0]), "d"(o.v[1]), "l"(pol) : "memory");
+    else *reinterpret_cast<double2*>(p + i) = make_double2(o.v[0], o.v[1]);
   } else {
     p[i] = o.v[0];
   }

@@ -33,7 +33,7 @@ int cgx_fused_prepare(cgx_ctx* c) {
   // the LL ghost planes are shared with the other partitioned kernels (tags = epochs): keep the
   // tags unique by starting above every epoch any of them has used
   for (int ch = 0; ch < 3; ++ch) c->fepoch = std::max(c->fepoch, c->hepoch[ch]);
-  if (c->dist.world > 1 && !c->d_gscr) CU(cudaMalloc(&c->d_gscr, sizeof(double) * 2 * (size_t)c->dist.plane));
+  if (c->dist.world > 1 && !c->d_gscr) CU(cudaMalloc(&c->d_gscr, sizeof(double) * 4 * (size_t)c->dist.plane));
   c->pr_fused = true;
   return CGX_OK;
 }

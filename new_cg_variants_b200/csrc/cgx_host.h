@@ -147,6 +147,7 @@ struct cgx_ctx {
   double* alt[3] = {};                     // second buffers of p, s, rt
   double* d_gscr = nullptr;                // partitioned: [2][plane] scratch (new p of the ghost planes)
   CUtensorMap ftmap[2][3];
+  int l2_keep = -1;                        // option "l2_keep": -1 auto (partitioned runs whose state fits L2), 0 off, 1 on
   int fused_min_slab = 64;                 // partitioned runs: planes per rank from which the fused kernel is used
   int fused_min_planes = 8, fused_chunks = 0;   // options: planes per CTA at least / force the chunk count
   // capture of x_k / r_k / (a, b) after every iteration, GV residual replacement (include/cgx.h)
@@ -211,7 +212,7 @@ VecIn vec_in(cgx_ctx* c, const double* v, int ch, const Args& g);
 // is a per-device attribute, so it is applied -- and the result cached -- per context).
 int ctx_occupancy(cgx_ctx* c, const void* fn, int threads, size_t smem);
 
-inline size_t tma_smem_bytes(int nv) { return (size_t)kRing * nv * kPlaneStride * sizeof(double) + 128; }
+inline size_t tma_smem_bytes(int nv) { return stencil_smem_bytes(nv); }
 
 // kernel launches ("stages") of one iteration without the instrumentation
 // (a CSR row partition adds one stage: the gather-and-push of the SpMV input's ghost entries)

@@ -98,6 +98,7 @@ struct Args {
   u64 xt_epoch;
   int meur;                        // Meurant predictor (kernels that are not templated on it)
   int halo_ll;                     // the consumer is the TMA stencil kernel: boundary planes travel as LL words
+  unsigned long long l2pol;        // 0, or an L2 cache-policy word for the state-vector accesses (kL2EvictLast)
   double* gscr;                    // fused PR kernel on a partition: [plane] new p of the ghost plane above the slab
   int dbg;                         // timing experiments (cgx_set_option "debug_skip"): 1 = no halo traffic, 2 = time stamps
   u64* dbg_t;                      // dbg & 2: CTA 0 writes %globaltimer at kernel start / after the scalar fold / at its end
@@ -364,30 +365,30 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
                                         double (&red)[kNRed]) {
   constexpr bool PREC = PM != 0;
   Pk<W> dv{};
-  if constexpr (PM == 1) dv = ldp<W>(g.dinv, i);
+  if constexpr (PM == 1) dv = ldp<W>(g.dinv, i, g.l2pol);
   const double ds = g.dinv_s;
   auto M = [&](double v, int l) { return PM == 1 ? mul_(dv.v[l], v) : (PM == 2 ? mul_(ds, v) : v); };
 
   if constexpr (KID == EW_HS1) {             // hs_cg.py:118-120
-    Pk<W> r = ldp<W>(g.r, i), s = ldp<W>(g.s, i);
+    Pk<W> r = ldp<W>(g.r, i, g.l2pol), s = ldp<W>(g.s, i, g.l2pol);
 #pragma unroll
     for (int l = 0; l < W; ++l) {
       r.v[l] = axmy_(r.v[l], a, s.v[l]);
       red[0] = fma(r.v[l], M(r.v[l], l), red[0]);
     }
-    stp<W>(g.r, i, r);
+    stp<W>(g.r, i, r, g.l2pol);
   } else if constexpr (KID == EW_HS2) {      // hs_cg.py:117,119,122
-    Pk<W> x = ldp<W>(g.x, i), p = ldp<W>(g.p, i), r = ldp<W>(g.r, i);
+    Pk<W> x = ldp<W>(g.x, i, g.l2pol), p = ldp<W>(g.p, i, g.l2pol), r = ldp<W>(g.r, i, g.l2pol);
 #pragma unroll
     for (int l = 0; l < W; ++l) {
       x.v[l] = axpy_(x.v[l], a, p.v[l]);
       p.v[l] = axpy_(M(r.v[l], l), b, p.v[l]);
     }
-    stp<W>(g.x, i, x); stp<W>(g.p, i, p);
+    stp<W>(g.x, i, x, g.l2pol); stp<W>(g.p, i, p, g.l2pol);
     halo_store<W>(g, 0, i, p);
   } else if constexpr (KID == EW_CG) {       // cg_cg.py:137-138 (deferred), :130-132
-    Pk<W> x = ldp<W>(g.x, i), r = ldp<W>(g.r, i), rt = ldp<W>(g.rt, i), p = ldp<W>(g.p, i),
-          s = ldp<W>(g.s, i), w = ldp<W>(g.w, i);
+    Pk<W> x = ldp<W>(g.x, i, g.l2pol), r = ldp<W>(g.r, i, g.l2pol), rt = ldp<W>(g.rt, i, g.l2pol), p = ldp<W>(g.p, i, g.l2pol),
+          s = ldp<W>(g.s, i, g.l2pol), w = ldp<W>(g.w, i, g.l2pol);
 #pragma unroll
     for (int l = 0; l < W; ++l) {
       p.v[l] = axpy_(rt.v[l], b, p.v[l]);
@@ -396,11 +397,11 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
       r.v[l] = axmy_(r.v[l], a, s.v[l]);
       rt.v[l] = M(r.v[l], l);
     }
-    stp<W>(g.p, i, p); stp<W>(g.s, i, s); stp<W>(g.x, i, x); stp<W>(g.r, i, r);
-    stp<W>(g.rt, i, rt);
+    stp<W>(g.p, i, p, g.l2pol); stp<W>(g.s, i, s, g.l2pol); stp<W>(g.x, i, x, g.l2pol); stp<W>(g.r, i, r, g.l2pol);
+    stp<W>(g.rt, i, rt, g.l2pol);
     halo_store<W>(g, 0, i, rt);
   } else if constexpr (KID == EW_CG_E) {     // EW_CG without the r~ stream (PM 0 / 2 only)
-    Pk<W> x = ldp<W>(g.x, i), r = ldp<W>(g.r, i), p = ldp<W>(g.p, i), s = ldp<W>(g.s, i), w = ldp<W>(g.w, i);
+    Pk<W> x = ldp<W>(g.x, i, g.l2pol), r = ldp<W>(g.r, i, g.l2pol), p = ldp<W>(g.p, i, g.l2pol), s = ldp<W>(g.s, i, g.l2pol), w = ldp<W>(g.w, i, g.l2pol);
 #pragma unroll
     for (int l = 0; l < W; ++l) {
       p.v[l] = axpy_(M(r.v[l], l), b, p.v[l]);          // r~_{k-1} = M r_{k-1}, the bits EW_CG stored
@@ -408,11 +409,11 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
       x.v[l] = axpy_(x.v[l], a, p.v[l]);
       r.v[l] = axmy_(r.v[l], a, s.v[l]);
     }
-    stp<W>(g.p, i, p); stp<W>(g.s, i, s); stp<W>(g.x, i, x); stp<W>(g.r, i, r);
+    stp<W>(g.p, i, p, g.l2pol); stp<W>(g.s, i, s, g.l2pol); stp<W>(g.x, i, x, g.l2pol); stp<W>(g.r, i, r, g.l2pol);
     halo_store<W>(g, 0, i, r);                           // the stencil pass scales it
   } else if constexpr (KID == EW_GV_E) {     // EW_GV without the w~ stream (PM 0 / 2 only)
-    Pk<W> x = ldp<W>(g.x, i), r = ldp<W>(g.r, i), rt = ldp<W>(g.rt, i), p = ldp<W>(g.p, i),
-          s = ldp<W>(g.s, i), st = ldp<W>(g.st, i), w = ldp<W>(g.w, i), u = ldp<W>(g.u, i), t = ldp<W>(g.t, i);
+    Pk<W> x = ldp<W>(g.x, i, g.l2pol), r = ldp<W>(g.r, i, g.l2pol), rt = ldp<W>(g.rt, i, g.l2pol), p = ldp<W>(g.p, i, g.l2pol),
+          s = ldp<W>(g.s, i, g.l2pol), st = ldp<W>(g.st, i, g.l2pol), w = ldp<W>(g.w, i, g.l2pol), u = ldp<W>(g.u, i, g.l2pol), t = ldp<W>(g.t, i, g.l2pol);
 #pragma unroll
     for (int l = 0; l < W; ++l) {
       p.v[l] = axpy_(rt.v[l], b, p.v[l]);
@@ -426,13 +427,13 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
       red[0] = fma(r.v[l], rt.v[l], red[0]);
       red[1] = fma(w.v[l], rt.v[l], red[1]);
     }
-    stp<W>(g.p, i, p); stp<W>(g.s, i, s); stp<W>(g.st, i, st); stp<W>(g.u, i, u);
-    stp<W>(g.x, i, x); stp<W>(g.r, i, r); stp<W>(g.rt, i, rt); stp<W>(g.w, i, w);
+    stp<W>(g.p, i, p, g.l2pol); stp<W>(g.s, i, s, g.l2pol); stp<W>(g.st, i, st, g.l2pol); stp<W>(g.u, i, u, g.l2pol);
+    stp<W>(g.x, i, x, g.l2pol); stp<W>(g.r, i, r, g.l2pol); stp<W>(g.rt, i, rt, g.l2pol); stp<W>(g.w, i, w, g.l2pol);
     halo_store<W>(g, 0, i, w);                           // the stencil pass scales it
   } else if constexpr (KID == EW_GV) {       // gv_cg.py:165-168 (deferred), :151-154,160,162-163
-    Pk<W> x = ldp<W>(g.x, i), r = ldp<W>(g.r, i), rt = ldp<W>(g.rt, i), p = ldp<W>(g.p, i),
-          s = ldp<W>(g.s, i), st = ldp<W>(g.st, i), w = ldp<W>(g.w, i), wt = ldp<W>(g.wt, i),
-          u = ldp<W>(g.u, i), t = ldp<W>(g.t, i);
+    Pk<W> x = ldp<W>(g.x, i, g.l2pol), r = ldp<W>(g.r, i, g.l2pol), rt = ldp<W>(g.rt, i, g.l2pol), p = ldp<W>(g.p, i, g.l2pol),
+          s = ldp<W>(g.s, i, g.l2pol), st = ldp<W>(g.st, i, g.l2pol), w = ldp<W>(g.w, i, g.l2pol), wt = ldp<W>(g.wt, i, g.l2pol),
+          u = ldp<W>(g.u, i, g.l2pol), t = ldp<W>(g.t, i, g.l2pol);
 #pragma unroll
     for (int l = 0; l < W; ++l) {
       p.v[l] = axpy_(rt.v[l], b, p.v[l]);
@@ -447,13 +448,13 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
       red[0] = fma(r.v[l], rt.v[l], red[0]);
       red[1] = fma(w.v[l], rt.v[l], red[1]);
     }
-    stp<W>(g.p, i, p); stp<W>(g.s, i, s); stp<W>(g.st, i, st); stp<W>(g.u, i, u);
-    stp<W>(g.x, i, x); stp<W>(g.r, i, r); stp<W>(g.rt, i, rt); stp<W>(g.w, i, w);
-    stp<W>(g.wt, i, wt);
+    stp<W>(g.p, i, p, g.l2pol); stp<W>(g.s, i, s, g.l2pol); stp<W>(g.st, i, st, g.l2pol); stp<W>(g.u, i, u, g.l2pol);
+    stp<W>(g.x, i, x, g.l2pol); stp<W>(g.r, i, r, g.l2pol); stp<W>(g.rt, i, rt, g.l2pol); stp<W>(g.w, i, w, g.l2pol);
+    stp<W>(g.wt, i, wt, g.l2pol);
     halo_store<W>(g, 0, i, wt);
   } else if constexpr (KID == EW_PR) {       // pr_cg.py:146-148,151,157
-    Pk<W> x = ldp<W>(g.x, i), r = ldp<W>(g.r, i), rt = ldp<W>(g.rt, i), p = ldp<W>(g.p, i),
-          s = ldp<W>(g.s, i);
+    Pk<W> x = ldp<W>(g.x, i, g.l2pol), r = ldp<W>(g.r, i, g.l2pol), rt = ldp<W>(g.rt, i, g.l2pol), p = ldp<W>(g.p, i, g.l2pol),
+          s = ldp<W>(g.s, i, g.l2pol);
 #pragma unroll
     for (int l = 0; l < W; ++l) {
       x.v[l] = axpy_(x.v[l], a, p.v[l]);
@@ -462,14 +463,14 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
       p.v[l] = axpy_(rt.v[l], b, p.v[l]);
       red[0] = fma(rt.v[l], r.v[l], red[0]);
     }
-    stp<W>(g.x, i, x); stp<W>(g.r, i, r); stp<W>(g.rt, i, rt); stp<W>(g.p, i, p);
+    stp<W>(g.x, i, x, g.l2pol); stp<W>(g.r, i, r, g.l2pol); stp<W>(g.rt, i, rt, g.l2pol); stp<W>(g.p, i, p, g.l2pol);
     halo_store<W>(g, 0, i, p);
   } else {                                   // pipe_pr_cg.py:169-178,183-186
     constexpr bool RECOMP = (KID == EW_PIPE_R);
-    Pk<W> x = ldp<W>(g.x, i), r = ldp<W>(g.r, i), rt = ldp<W>(g.rt, i), p = ldp<W>(g.p, i),
-          s = ldp<W>(g.s, i), st = ldp<W>(g.st, i), w = ldp<W>(g.w, i), u = ldp<W>(g.u, i);
+    Pk<W> x = ldp<W>(g.x, i, g.l2pol), r = ldp<W>(g.r, i, g.l2pol), rt = ldp<W>(g.rt, i, g.l2pol), p = ldp<W>(g.p, i, g.l2pol),
+          s = ldp<W>(g.s, i, g.l2pol), st = ldp<W>(g.st, i, g.l2pol), w = ldp<W>(g.w, i, g.l2pol), u = ldp<W>(g.u, i, g.l2pol);
     Pk<W> wt;
-    if constexpr (!RECOMP && PREC) wt = ldp<W>(g.wt, i);
+    if constexpr (!RECOMP && PREC) wt = ldp<W>(g.wt, i, g.l2pol);
 #pragma unroll
     for (int l = 0; l < W; ++l) {
       x.v[l] = axpy_(x.v[l], a, p.v[l]);
@@ -491,13 +492,13 @@ __device__ __forceinline__ void ew_body(const Args& g, i64 i, double a, double b
       red[2] = fma(st.v[l], s.v[l], red[2]);     // gamma
       red[3] = fma(rt.v[l], r.v[l], red[3]);     // nu (recomputed)
     }
-    stp<W>(g.x, i, x); stp<W>(g.r, i, r); stp<W>(g.rt, i, rt); stp<W>(g.p, i, p);
-    stp<W>(g.s, i, s); stp<W>(g.st, i, st);
+    stp<W>(g.x, i, x, g.l2pol); stp<W>(g.r, i, r, g.l2pol); stp<W>(g.rt, i, rt, g.l2pol); stp<W>(g.p, i, p, g.l2pol);
+    stp<W>(g.s, i, s, g.l2pol); stp<W>(g.st, i, st, g.l2pol);
     halo_store<W>(g, 0, i, st);
     if constexpr (RECOMP) halo_store<W>(g, 1, i, rt);
     if constexpr (!RECOMP) {
-      stp<W>(g.w, i, w);
-      if constexpr (PREC) stp<W>(g.wt, i, wt);
+      stp<W>(g.w, i, w, g.l2pol);
+      if constexpr (PREC) stp<W>(g.wt, i, wt, g.l2pol);
     }
   }
 }

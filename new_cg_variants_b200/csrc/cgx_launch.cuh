@@ -31,11 +31,15 @@ static void launch_spmv(cgx_ctx* c, Args g, const double* vin, double* vout) {
       if (c->op_kind == 2 && c->use_tma && c->tmap_ok[v0] && (v1 < 0 || c->tmap_ok[v1 < 0 ? 0 : v1])) {
         // grid = the CTAs that are actually co-resident (one wave): the kernel splits the work
         // evenly over gridDim.x, so a partial second wave would cost a full extra pass
-        const int per_sm = ctx_occupancy(c, (const void*)stencil_tma_kernel<MODE, PM, MEUR>, kTmaThreads,
-                                         tma_smem_bytes(nv));
-        const int tgrid = std::min(c->tma_grid[nv - 1], per_sm * c->sm_count);
-        stencil_tma_kernel<MODE, PM, MEUR><<<tgrid, kTmaThreads, tma_smem_bytes(nv), c->stream>>>(
-            c->tmap[v0], c->tmap[v1 < 0 ? v0 : v1], c->geom, g);
+        const int per_sm = ctx_occupancy(c, (const void*)stencil_tma_kernel<MODE, PM, MEUR>, kSThreads, tma_smem_bytes(nv));
+        // (column, z-chunk) work units, all co-resident when the columns fit (cgx_stencil_tma.cuh)
+        TmaGeom G = c->geom;
+        const int cap = per_sm * c->sm_count, ncols = G.ntx * G.nty;
+        G.nchunk = std::max(1, std::min(cap / std::max(1, ncols), G.nz / std::max(1, c->tma_min_planes)));
+        const int tgrid = (int)std::min<i64>((i64)ncols * G.nchunk, cap);
+        g.gscr = c->d_gscr;
+        stencil_tma_kernel<MODE, PM, MEUR><<<tgrid, kSThreads, tma_smem_bytes(nv), c->stream>>>(
+            c->tmap[v0], c->tmap[v1 < 0 ? v0 : v1], G, g);
         done = true;
       }
     }

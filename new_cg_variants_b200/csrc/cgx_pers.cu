@@ -19,6 +19,7 @@ static int pers_launch_pm(cgx_ctx** cs, int count, const PersGeom& G, int k0, in
     Plan p;                                         // fills scpar / x_true epochs
     plan_apply(c, g, p);
     r.g = g;
+    r.g.l2pol = 0;                                  // (the persistent kernel addresses shared memory)
     for (int v = 0; v < V_COUNT; ++v) r.vecs[v] = c->vec[v];
     r.vecs[10] = c->d_dinv; r.vecs[11] = nullptr;
     for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) r.exp_[a][b] = c->d_exp[a][b];

@@ -94,234 +94,258 @@ struct TmaGeom {
 };
 
 #define NV_OF(MODE) ((MODE) == SP_PIPE_R ? 2 : 1)
+
+// ---- warp-specialised march ------------------------------------------------------------------
+// 8 compute warps (warp w <-> row w of the 128 x 8 tile, a lane owns the point pairs 2 lx + 64 j)
+// + 1 producer warp.  The producer's elected lane issues the bulk-tensor copies of the planes a
+// unit needs into a ring of kRingOf(NV) slots, each guarded by a full (transaction) and an empty
+// (one arrival per compute warp) mbarrier, and runs ahead across unit changes; a compute warp waits
+// only for the planes it reads and releases plane z-1 when it has computed plane z.  There is NO
+// CTA-wide barrier in the march.
+// Work units are (column, z-chunk), chunk-major, one CTA per unit when they are co-resident: all
+// columns of a chunk then march in lockstep and the tile halos neighbouring columns share come from
+// L2 (cgx_stencil_fused.cuh uses the same decomposition).
+constexpr int kSConsumers = 256;
+constexpr int kSThreads = kSConsumers + 32;
+constexpr int kSPairs = kTX / 64;
+__host__ __device__ constexpr int kRingOf(int nv) { return nv == 2 ? 4 : 8; }
+__host__ __device__ constexpr size_t stencil_smem_bytes(int nv) {
+  return (size_t)kRingOf(nv) * nv * kPlaneStride * sizeof(double) + 128;
+}
+
 // MODE: SP_* of cgx_kernels.cuh.  PM: 0 identity, 1 Jacobi vector, 2 Jacobi scalar.
-// Resident CTAs per SM: 5 (one RHS; shared-memory bound, registers capped to match) or 2.
 template <int MODE, int PM, bool MEUR>
-__global__ void __launch_bounds__(kTmaThreads, (NV_OF(MODE) == 2) ? 2 : 4)
+__global__ void __launch_bounds__(kSThreads, 2)
 stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                    const TmaGeom G, const Args g) {
-  constexpr int NV = (MODE == SP_PIPE_R) ? 2 : 1;
+  constexpr int NV = NV_OF(MODE);
+  constexpr int R = kRingOf(NV);
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // [kRing][NV][kPlaneStride], 128-byte aligned whatever static shared memory precedes it
-  double* smem = reinterpret_cast<double*>(
-      smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
-  __shared__ __align__(8) uint64_t bar[kRing];
+  double* smem = reinterpret_cast<double*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+  __shared__ __align__(8) uint64_t full_bar[R], empty_bar[R];
 
   const int tid = threadIdx.x;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kRing; ++s) mbar_init(&bar[s], 1);
+    for (int s = 0; s < R; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kSConsumers / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  const int ly = tid >> 5;              // 0..7   row of the tile
-  const int lx = tid & 31;              // lane: points lx, lx+32, lx+64, lx+96
-  const i64 plane_pts = (i64)G.nx * G.ny;
+  const int ncols = G.ntx * G.nty;
+  const int nunits = ncols * G.nchunk;
   constexpr uint32_t kBytes = (uint32_t)(kPlane * 8 * NV);
-
   double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
-  uint32_t L = 0;                        // loads issued so far by this CTA (ring position)
 
-  // Static even split: the (column, plane) pairs, column-major, are cut into gridDim.x
-  // contiguous ranges, so every CTA streams the same number of planes (+-1) whatever the
-  // grid shape, and the assignment (hence the summation order of the fused dots) is a
-  // function of the problem size only.  A range that crosses a column end is processed as
-  // two z-segments.
-  const i64 total = (i64)G.ntx * G.nty * G.nz;
-  const i64 range_end = ((i64)blockIdx.x + 1) * total / gridDim.x;
-  for (i64 pos = (i64)blockIdx.x * total / gridDim.x; pos < range_end;) {
-    const int col = (int)(pos / G.nz);
-    const int z0 = (int)(pos - (i64)col * G.nz);
-    const int z1 = (int)min((i64)G.nz, (i64)z0 + (range_end - pos));
-    pos += z1 - z0;
-    const int tx = col % G.ntx;
-    const int ty = col / G.ntx;
-    const int x0 = tx * kTX, y0 = ty * kTY;
-    const uint32_t Lbase = L;            // load index of plane z0-1
-
-    auto issue = [&](int z, uint32_t li) {          // one thread: plane z -> slot li % kRing
-      const int slot = li % kRing;
-      const bool exists = (z >= 0 || G.has_zlo) && (z < G.nz || G.has_zhi);
-      if (!exists) {                                // beyond the domain: never read (selects)
-        mbar_arrive(&bar[slot]);
-        return;
-      }
-      double* dst = smem + (size_t)slot * NV * kPlaneStride;
-      if (z < 0 || z >= G.nz) return;               // ghost plane: filled by fill_ghost (all threads)
-      mbar_arrive_expect_tx(&bar[slot], kBytes);
-      const int ty0 = G.march_y ? z * kTY : y0, tz = G.march_y ? 0 : z;
-      tma_load_3d(dst, &tm0, x0 - 2, ty0 - 1, tz, &bar[slot]);
-      if constexpr (NV == 2) tma_load_3d(dst + kPlaneStride, &tm1, x0 - 2, ty0 - 1, tz, &bar[slot]);
-    };
-    auto wait_load = [&](uint32_t li) { mbar_wait(&bar[li % kRing], (li / kRing) & 1u, G.err); };
-    // Ghost plane of a slab (multi-GPU): the neighbour rank's vector pass stored it into this
-    // rank's window as LL words (each 8-byte word = half a double + the halo epoch).  All
-    // threads poll their elements and write the tile -- zero outside the domain, like the TMA
-    // fill -- into the ring slot; no flag, no fence.  Uniform call (every thread of the CTA).
-    auto is_ghost = [&](int z) { return (z < 0 && G.has_zlo) || (z >= G.nz && G.has_zhi); };
-    auto fill_ghost = [&](int z, uint32_t li) {
-      const int slot = li % kRing;
-      const int side = z < 0 ? 0 : 1;
-      WinHdr* w = g.d.win[g.d.rank];
-      double* dst = smem + (size_t)slot * NV * kPlaneStride;
-      constexpr int kPer = (kPlane + kTmaThreads - 1) / kTmaThreads;      // elements per thread
-      const u64 tag = g.hin_epoch & 0xffffffffull;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const u64* q = g.d.ghl + ghl_off(g.d, g.hin_ch + v, g.hin_par, side);
-        u64 lo[kPer], hi[kPer];
-        const u64* src[kPer];
-        // all loads first (16 bytes = both words of a value), then validate / re-poll
-#pragma unroll
-        for (int m = 0; m < kPer; ++m) {
-          const int idx = tid + m * kTmaThreads;
-          const int py = idx / kPX, px = idx - py * kPX;
-          const int gx = x0 - 2 + px, gyy = y0 - 1 + py;
-          src[m] = (idx < kPlane && gx >= 0 && gx < G.nx && gyy >= 0 && gyy < G.ny) ? q + 2 * (gyy * G.nx + gx) : nullptr;
-          lo[m] = hi[m] = tag << 32;                                       // outside the domain: +0.0, "valid"
-          if (g.dbg & 1) src[m] = nullptr;                                 // timing experiment: no halo traffic
-          if (src[m])
-            asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo[m]), "=l"(hi[m]) : "l"(src[m]) : "memory");
-        }
-#pragma unroll
-        for (int m = 0; m < kPer; ++m) {
-          const int idx = tid + m * kTmaThreads;
-          if (src[m] && ((lo[m] >> 32) != tag || (hi[m] >> 32) != tag)) {
-            lo[m] = ll_poll(src[m], tag, &w->error);
-            hi[m] = ll_poll(src[m] + 1, tag, &w->error);
-          }
-          if (idx < kPlane)
-            dst[v * kPlaneStride + idx] = __longlong_as_double((long long)((lo[m] & 0xffffffffull) | (hi[m] << 32)));
+  if (tid >= kSConsumers) {
+    // ------------------------------------------------------------------ producer warp
+    if (tid == kSConsumers) {
+      uint32_t li = 0;
+      for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const int col = unit % ncols, chunk = unit / ncols;
+        const int z0 = (int)((i64)chunk * G.nz / G.nchunk), z1 = (int)((i64)(chunk + 1) * G.nz / G.nchunk);
+        const int x0 = (col % G.ntx) * kTX, y0 = (col / G.ntx) * kTY;
+        const int lo = G.march_y ? z0 : max(z0 - 1, 0), hi = G.march_y ? z1 - 1 : min(z1, G.nz - 1);
+        for (int zz = lo; zz <= hi; ++zz, ++li) {
+          const int slot = li % R;
+          if (li >= (uint32_t)R) mbar_wait(&empty_bar[slot], ((li / R) - 1) & 1u, G.err);
+          double* dst = smem + (size_t)slot * NV * kPlaneStride;
+          mbar_arrive_expect_tx(&full_bar[slot], kBytes);
+          const int ty0 = G.march_y ? zz * kTY : y0, tz = G.march_y ? 0 : zz;
+          tma_load_3d(dst, &tm0, x0 - 2, ty0 - 1, tz, &full_bar[slot]);
+          if constexpr (NV == 2) tma_load_3d(dst + kPlaneStride, &tm1, x0 - 2, ty0 - 1, tz, &full_bar[slot]);
         }
       }
-      __syncthreads();
-      if (tid == 0) mbar_arrive(&bar[slot]);
-    };
-
-    if (tid == 0) {
-      issue(z0 - 1, Lbase);
-      issue(z0, Lbase + 1);
-      issue(z0 + 1, Lbase + 2);
     }
-    if (is_ghost(z0 - 1)) fill_ghost(z0 - 1, Lbase);
-    if (is_ghost(z0 + 1)) fill_ghost(z0 + 1, Lbase + 2);
-    wait_load(Lbase);
-    wait_load(Lbase + 1);
-
-    int gy = y0 + ly;                                  // (march_y: set per step)
-    bool row_ok = gy < G.ny;
-
-    // Operands that do not go through shared memory (r for the fused dots, a Jacobi vector)
-    // are fetched ONE PLANE AHEAD into registers: their global-load latency is covered by a
-    // whole plane of work instead of stalling the first fused dot (ncu: 29 % of the stall
-    // samples sat on that DFMA when the load was issued in the same iteration).
+  } else {
+    // ------------------------------------------------------------------ compute warps
+    const int ly = tid >> 5, lx = tid & 31;
+    uint32_t li = 0;
     constexpr bool kNeedR = (MODE == SP_CG || MODE == SP_PR);
     constexpr bool kNeedD = (MODE == SP_PR && PM == 1);
-    double rv_n[kPtsPerThread], dvv_n[kPtsPerThread];
-    auto fetch_direct = [&](int z) {
-      const int gyz = G.march_y ? z * kTY + ly : gy;
-      const bool rok = gyz < G.ny;
-      const i64 ib = (G.march_y ? 0 : (i64)z * plane_pts) + (i64)gyz * G.nx + x0 + lx;
+    constexpr bool kScaleIn = (MODE == SP_CG_E || MODE == SP_GV_E) && PM == 2;   // tile holds r / w: operand is M r / M w
+    for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+      const int col = unit % ncols, chunk = unit / ncols;
+      const int z0 = (int)((i64)chunk * G.nz / G.nchunk), z1 = (int)((i64)(chunk + 1) * G.nz / G.nchunk);
+      const int x0 = (col % G.ntx) * kTX, y0 = (col / G.ntx) * kTY;
+      const int lo = G.march_y ? z0 : max(z0 - 1, 0), hi = G.march_y ? z1 - 1 : min(z1, G.nz - 1);
+      const uint32_t Lbase = li;                            // load index of plane lo
+      const int step_stride = G.march_y ? kTY * G.nx : G.nx * G.ny;
+      const int idx0 = (G.march_y ? ly : y0 + ly) * G.nx + x0 + 2 * lx;
+      const int ybase = G.march_y ? ly : y0 + ly, ystep = G.march_y ? kTY : 0;
+      bool okx[kSPairs];
 #pragma unroll
-      for (int m = 0; m < kPtsPerThread; ++m) {
-        const bool ok = rok && (x0 + lx + 32 * m) < G.nx;
-        rv_n[m] = (kNeedR && ok) ? g.r[ib + 32 * m] : 0.0;
-        dvv_n[m] = (kNeedD && ok) ? g.dinv[ib + 32 * m] : 0.0;
+      for (int j = 0; j < kSPairs; ++j) okx[j] = (x0 + 2 * lx + 64 * j) < G.nx;
+
+      // Slab of a partition: the planes below z = 0 / above z = nz-1 live in the rank's window as LL
+      // words stored by the neighbours' vector passes.  Only the z-1 / z+1 TERMS of this lane's own
+      // points need them: they are decoded once, before the march, into the scratch planes
+      // (g.gscr[(side * 2 + v) * plane + e]) and read back by the same thread -- no ring slot, no
+      // synchronisation, nothing of the polling inside the plane loop.
+      const bool ghost_lo = !G.march_y && z0 == 0 && G.has_zlo, ghost_hi = !G.march_y && z1 == G.nz && G.has_zhi;
+      if (ghost_lo || ghost_hi) {
+        int* err = &g.d.win[g.d.rank]->error;
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+          if (side == 0 ? !ghost_lo : !ghost_hi) continue;
+#pragma unroll 1
+          for (int v = 0; v < NV; ++v) {
+            const u64* gh = g.d.ghl + ghl_off(g.d, g.hin_ch + v, g.hin_par, side);
+#pragma unroll 1
+            for (int j = 0; j < kSPairs; ++j) {
+              if (!(ybase < G.ny && okx[j])) continue;
+              const int e = idx0 + 64 * j;
+              double t0 = 0.0, t1 = 0.0;
+              if (!(g.dbg & 1)) {
+                LLReq q0, q1;
+                q0.src = gh + 2 * (size_t)e; q1.src = gh + 2 * (size_t)(e + 1);
+                ll_issue(q0); ll_issue(q1);
+                t0 = ll_finish(q0, g.hin_epoch, err); t1 = ll_finish(q1, g.hin_epoch, err);
+              }
+              *reinterpret_cast<double2*>(g.gscr + (size_t)(side * 2 + v) * g.d.plane + e) = make_double2(t0, t1);
+            }
+          }
+        }
       }
-    };
-    if constexpr (kNeedR || kNeedD) fetch_direct(z0);
 
-    for (int z = z0; z < z1; ++z) {
-      const uint32_t j = (uint32_t)(z - z0);
-      if (tid == 0 && z + 2 <= z1) issue(z + 2, Lbase + j + 3);    // slot of plane z-2: free
-      if (z + 2 <= z1 && is_ghost(z + 2)) fill_ghost(z + 2, Lbase + j + 3);
-      double rv[kPtsPerThread], dvv[kPtsPerThread];
-      if (G.march_y) { gy = z * kTY + ly; row_ok = gy < G.ny; }
-      const i64 ibase = (G.march_y ? 0 : (i64)z * plane_pts) + (i64)gy * G.nx + x0 + lx;
+      // operands that do not go through shared memory (r for the fused dots, a Jacobi vector): one
+      // plane ahead, two alternating register sets (no copies of values in flight)
+      typedef double Set[kSPairs][2];
+      auto fetch_direct = [&](int q, Set& rs, Set& dsv) {
+        if constexpr (kNeedR || kNeedD) {
+          const bool oky = ybase + q * ystep < G.ny;
+          const int ib = idx0 + q * step_stride;
 #pragma unroll
-      for (int m = 0; m < kPtsPerThread; ++m) { rv[m] = rv_n[m]; dvv[m] = dvv_n[m]; }
-      if constexpr (kNeedR || kNeedD) { if (z + 1 < z1) fetch_direct(z + 1); }
-      wait_load(Lbase + j + 2);                                     // plane z+1 has landed
-      const double* pm = smem + (size_t)((Lbase + j) % kRing) * NV * kPlaneStride;
-      const double* pc = smem + (size_t)((Lbase + j + 1) % kRing) * NV * kPlaneStride;
-      const double* pp = smem + (size_t)((Lbase + j + 2) % kRing) * NV * kPlaneStride;
-      const bool has_zm = !G.march_y && ((z > 0) || G.has_zlo);
-      const bool has_zp = !G.march_y && ((z < G.nz - 1) || G.has_zhi);
-
-      if (row_ok) {
+          for (int j = 0; j < kSPairs; ++j) {
+            const int i = (oky && okx[j]) ? ib + 64 * j : 0;
+            if constexpr (kNeedR) { const double2 t = *reinterpret_cast<const double2*>(g.r + i); rs[j][0] = t.x; rs[j][1] = t.y; }
+            if constexpr (kNeedD) { const double2 t = *reinterpret_cast<const double2*>(g.dinv + i); dsv[j][0] = t.x; dsv[j][1] = t.y; }
+          }
+        }
+      };
+      int nwait = 0;                                        // planes lo .. lo + nwait - 1 have landed
+      auto plane_step = [&](const int q, Set& rc, Set& dc, Set& rn, Set& dn) {
+        if (q + 1 < z1) fetch_direct(q + 1, rn, dn);
+        const int need = G.march_y ? q : min(q + 1, hi);
+        while (lo + nwait <= need) {
+          const uint32_t l = Lbase + (uint32_t)nwait;
+          mbar_wait(&full_bar[l % R], (l / R) & 1u, G.err);
+          ++nwait;
+        }
+        const double* pc = smem + (size_t)((Lbase + (uint32_t)(q - lo)) % R) * NV * kPlaneStride;
+        const double* pm = smem + (size_t)((Lbase + (uint32_t)(q - 1 - lo)) % R) * NV * kPlaneStride;   // (never read when q-1 < lo)
+        const double* pp = smem + (size_t)((Lbase + (uint32_t)(q + 1 - lo)) % R) * NV * kPlaneStride;
+        const bool has_zm = !G.march_y && ((q > 0) || G.has_zlo);
+        const bool has_zp = !G.march_y && ((q < G.nz - 1) || G.has_zhi);
+        const bool zm_scr = ghost_lo && q == 0, zp_scr = ghost_hi && q == G.nz - 1;
+        const bool oky = ybase + q * ystep < G.ny;
+        const int ib = idx0 + q * step_stride;
 #pragma unroll
-        for (int m = 0; m < kPtsPerThread; ++m) {
-          const int px = lx + 32 * m;              // 0..127 within the tile
-          const int gx = x0 + px;
-          if (gx < G.nx) {
-            const int c = (ly + 1) * kPX + (px + 2);
-            double y[NV], ctr[NV], raw[NV];
+        for (int j = 0; j < kSPairs; ++j) {
+          if (oky && okx[j]) {
+            const int c = (ly + 1) * kPX + 2 * lx + 64 * j + 2;
+            double y[NV][2], ctr[NV][2], raw[NV][2];
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
               const double* qm = pm + v * kPlaneStride;
               const double* qc = pc + v * kPlaneStride;
               const double* qp = pp + v * kPlaneStride;
-              // x/y neighbours outside the domain were zero-filled by the TMA unit: their term is
-              // off * (+0.0) = +-0.0, and adding a signed zero never changes a running sum that
-              // started at +0.0 (such a sum can never be -0.0), so no select is needed and the
-              // bits equal scipy's sum over the stored entries only.  Absent z-planes are not
-              // loaded at all (stale shared memory): those two terms keep their select.
-              // SP_CG_E: the tile holds r; the operand is r~ = M r, formed here (the product
-              // EW_CG would have stored), so r~ is neither written nor read from HBM
-              auto in = [&](double q) {
-                if constexpr ((MODE == SP_CG_E || MODE == SP_GV_E) && PM == 2) return mul_(g.dinv_s, q);
-                else return q;
-              };
-              double acc = 0.0, t;
-              t = add_(acc, mul_(G.off, in(qm[c])));        acc = has_zm ? t : acc;
-              acc = add_(acc, mul_(G.off, in(qc[c - kPX])));
-              acc = add_(acc, mul_(G.off, in(qc[c - 1])));
-              raw[v] = qc[c];
-              ctr[v] = in(raw[v]);
-              acc = add_(acc, mul_(G.diag, ctr[v]));
-              acc = add_(acc, mul_(G.off, in(qc[c + 1])));
-              acc = add_(acc, mul_(G.off, in(qc[c + kPX])));
-              t = add_(acc, mul_(G.off, in(qp[c])));        acc = has_zp ? t : acc;
-              y[v] = acc;
+              const double* zmp = zm_scr ? g.gscr + (size_t)v * g.d.plane + idx0 + 64 * j : qm + c;
+              const double* zpp = zp_scr ? g.gscr + (size_t)(2 + v) * g.d.plane + idx0 + 64 * j : qp + c;
+              const double2 zm = *reinterpret_cast<const double2*>(zmp), zp = *reinterpret_cast<const double2*>(zpp);
+              const double2 ym = *reinterpret_cast<const double2*>(qc + c - kPX), yp = *reinterpret_cast<const double2*>(qc + c + kPX),
+                            ct = *reinterpret_cast<const double2*>(qc + c);
+              const double xm = qc[c - 1], xp = qc[c + 2];
+              auto in = [&](double t) { if constexpr (kScaleIn) return mul_(g.dinv_s, t); else return t; };
+              const double zmv[2] = {in(zm.x), in(zm.y)}, zpv[2] = {in(zp.x), in(zp.y)}, ymv[2] = {in(ym.x), in(ym.y)},
+                           ypv[2] = {in(yp.x), in(yp.y)}, ctv[2] = {in(ct.x), in(ct.y)};
+              const double xmv[2] = {in(xm), ctv[0]}, xpv[2] = {ctv[1], in(xp)};
+              raw[v][0] = ct.x; raw[v][1] = ct.y;
+#pragma unroll
+              for (int l = 0; l < 2; ++l) {
+                // canonical CSR order z-1, y-1, x-1, centre, x+1, y+1, z+1.  xy neighbours outside the
+                // domain were zero-filled by the TMA unit: off * (+0.0) never changes a running sum that
+                // started at +0.0, so the bits equal scipy's sum over the stored entries.  Absent
+                // z-planes are not loaded at all (stale shared memory): those two terms keep a select.
+                double acc = 0.0, t;
+                t = add_(acc, mul_(G.off, zmv[l]));          acc = has_zm ? t : acc;
+                acc = add_(acc, mul_(G.off, ymv[l]));
+                acc = add_(acc, mul_(G.off, xmv[l]));
+                acc = add_(acc, mul_(G.diag, ctv[l]));
+                acc = add_(acc, mul_(G.off, xpv[l]));
+                acc = add_(acc, mul_(G.off, ypv[l]));
+                t = add_(acc, mul_(G.off, zpv[l]));          acc = has_zp ? t : acc;
+                y[v][l] = acc;
+                ctr[v][l] = ctv[l];
+              }
             }
-            const i64 i = ibase + 32 * m;
-            auto M = [&](double v) {
-              if constexpr (PM == 1) return mul_(dvv[m], v);
-              else if constexpr (PM == 2) return mul_(g.dinv_s, v);
-              else return v;
+            const int i = ib + 64 * j;
+            auto M = [&](double t, int l) {
+              if constexpr (PM == 1) return mul_(dc[j][l], t);
+              else if constexpr (PM == 2) return mul_(g.dinv_s, t);
+              else return t;
             };
+            auto st2 = [&](double* dst, const double (&t)[2]) { *reinterpret_cast<double2*>(dst + i) = make_double2(t[0], t[1]); };
             if constexpr (MODE == SP_HS) {                 // hs_cg.py:123-124
-              g.s[i] = y[0];
-              red[0] = fma(ctr[0], y[0], red[0]);
+              st2(g.s, y[0]);
+#pragma unroll
+              for (int l = 0; l < 2; ++l) red[0] = fma(ctr[0][l], y[0][l], red[0]);
             } else if constexpr (MODE == SP_CG_E) {        // cg_cg.py:133-135 with r from the tile
-              g.w[i] = y[0];
-              red[0] = fma(raw[0], ctr[0], red[0]);
-              red[1] = fma(y[0], ctr[0], red[1]);
+              st2(g.w, y[0]);
+#pragma unroll
+              for (int l = 0; l < 2; ++l) { red[0] = fma(raw[0][l], ctr[0][l], red[0]); red[1] = fma(y[0][l], ctr[0][l], red[1]); }
             } else if constexpr (MODE == SP_CG) {          // cg_cg.py:133-135
-              g.w[i] = y[0];
-              red[0] = fma(rv[m], ctr[0], red[0]);
-              red[1] = fma(y[0], ctr[0], red[1]);
+              st2(g.w, y[0]);
+#pragma unroll
+              for (int l = 0; l < 2; ++l) { red[0] = fma(rc[j][l], ctr[0][l], red[0]); red[1] = fma(y[0][l], ctr[0][l], red[1]); }
             } else if constexpr (MODE == SP_GV || MODE == SP_GV_E) {          // gv_cg.py:161
-              g.t[i] = y[0];
+              st2(g.t, y[0]);
             } else if constexpr (MODE == SP_PR) {          // pr_cg.py:152-156
-              g.s[i] = y[0];
-              const double sti = M(y[0]);
-              red[0] = fma(ctr[0], y[0], red[0]);
-              red[1] = fma(rv[m], sti, red[1]);
-              red[2] = fma(sti, y[0], red[2]);
+              st2(g.s, y[0]);
+#pragma unroll
+              for (int l = 0; l < 2; ++l) {
+                const double sti = M(y[0][l], l);
+                red[0] = fma(ctr[0][l], y[0][l], red[0]);
+                red[1] = fma(rc[j][l], sti, red[1]);
+                red[2] = fma(sti, y[0][l], red[2]);
+              }
             } else if constexpr (MODE == SP_PIPE_R) {      // pipe_pr_cg.py:179-182
-              g.u[i] = y[0];
-              g.w[i] = y[NV - 1];
+              st2(g.u, y[0]);
+              st2(g.w, y[NV - 1]);
             } else {                                       // SP_PIPE_N
-              g.u[i] = y[0];
+              st2(g.u, y[0]);
             }
           }
         }
+        if (q - 1 >= lo) {                                  // plane q-1 is not needed any more
+          __syncwarp();
+          const uint32_t l = Lbase + (uint32_t)(q - 1 - lo);
+          if (lx == 0) mbar_arrive(&empty_bar[l % R]);
+        }
+      };
+
+      Set ra, da, rb, db;
+      fetch_direct(z0, ra, da);
+      int q = z0;
+      for (; q + 1 < z1; q += 2) {
+        plane_step(q, ra, da, rb, db);
+        plane_step(q + 1, rb, db, ra, da);
       }
-      __syncthreads();       // everyone is done with plane z-1 before its slot is refilled
+      if (q < z1) plane_step(q, ra, da, rb, db);
+      // release what is still held (plane z1-1 and, when loaded, z1); planes never waited for must be
+      // waited for first so that the slot's phase bookkeeping stays in step
+      while (lo + nwait <= hi) {
+        const uint32_t l = Lbase + (uint32_t)nwait;
+        mbar_wait(&full_bar[l % R], (l / R) & 1u, G.err);
+        ++nwait;
+      }
+      __syncwarp();
+      for (int zz = max(lo, z1 - 1); zz <= hi; ++zz) {
+        const uint32_t l = Lbase + (uint32_t)(zz - lo);
+        if (lx == 0) mbar_arrive(&empty_bar[l % R]);
+      }
+      li = Lbase + (uint32_t)(hi - lo + 1);
     }
-    L = Lbase + (uint32_t)(z1 - z0) + 2;   // planes z0-1 .. z1 were issued
   }
 
   spmv_close<MODE, MEUR>(g, red);

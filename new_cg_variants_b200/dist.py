@@ -450,3 +450,6 @@ class GroupSession:
             if name in histories and (x_true is not None or "error" not in name):
                 out[name] = hists[0][i].copy()
         return np.concatenate(xs), out, [m.get_info() for m in self.members]
+
+
+CsrDistSession = DistSession      # (a DistSession given a matrix instead of a PoissonStencil)
