@@ -682,96 +682,145 @@ __global__ void __launch_bounds__(kBlock) spmv_kernel(const Op A, const Args g, 
 // order by one thread chunk after chunk.
 constexpr int kCsrCap = 2048;
 
-template <int MODE, int PM, bool MEURANT>
+// GHOST: this launch is a rank of a CSR row partition -- columns >= n address the staging array of
+// gathered ghost entries (a pointer select per gather; compiled out for single-GPU runs, where it
+// cost 30 % of the pass on the banded model problem).
+//
+// Software-pipelined: while the CTA adds up the rows of block k (shared memory only), the (value,
+// column) stream of block k + gridDim.x is already in flight into registers and its gathers follow
+// as soon as the columns have landed; the products are double-buffered in shared memory, so there
+// is ONE CTA barrier per block.  (ncu on the un-pipelined form: 61 % of the stall samples waited on
+// the load -> gather chain, 27 % at the two barriers.)
+__host__ __device__ constexpr size_t csr_stream_smem_bytes(int nv) { return (size_t)2 * nv * kCsrCap * sizeof(double); }
+
+template <int MODE, int PM, bool MEURANT, bool GHOST>
 __global__ void __launch_bounds__(kBlock) csr_stream_kernel(const CsrOp A, const int* __restrict__ row_blocks,
                                                            int nblocks, const Args g, const VecIn in0,
                                                            const VecIn in1, double* vout) {
   constexpr int NV = SpTraits<MODE>::NV;
-  __shared__ double prod[NV][kCsrCap];
+  constexpr int kU = kCsrCap / kBlock;
+  extern __shared__ __align__(16) double prod_dyn[];          // [2][NV][kCsrCap]
   double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
   const int tid = threadIdx.x;
-  halo_wait_all(g, NV);
-  // row partition: column >= n -> gathered ghost entry (same pointer otherwise: lo is never selected)
+  if constexpr (GHOST) halo_wait_all(g, NV);
   const int nloc = (int)g.n;
-  auto ld0 = [&](int cj) { return (cj < nloc ? in0.v : in0.lo - nloc)[cj]; };
-  auto ld1 = [&](int cj) { return (cj < nloc ? in1.v : in1.lo - nloc)[cj]; };
-  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-    const int r0 = __ldg(row_blocks + blk), r1 = __ldg(row_blocks + blk + 1);
-    const int e0 = __ldg(A.ptr + r0), e1 = __ldg(A.ptr + r1);
-    const int cnt = e1 - e0;
-    if (cnt <= kCsrCap) {
-      // all (value, column) loads of the thread first, then all gathers, then the products:
-      // 16 + 8 (16) independent loads in flight per thread instead of a load -> gather chain
-      // per element (ncu: the chain was 70 % of the stall samples)
-      if constexpr (MODE == SP_PR) {
-        // (measured on the banded model problem: for this epilogue the batched form is slower,
-        // 159 vs 126 us -- it keeps the simple element loop)
-        for (int j = tid; j < cnt; j += kBlock) {
-          const double av = __ldg(A.val + e0 + j);
-          const int cj = __ldg(A.idx + e0 + j);
-          prod[0][j] = mul_(av, ld0(cj));
-        }
-      } else {
-      constexpr int kU = kCsrCap / kBlock;
-      double a[kU];
-      int col[kU];
+  auto ld0 = [&](int cj) { if constexpr (GHOST) return (cj < nloc ? in0.v : in0.lo - nloc)[cj]; else return in0.v[cj]; };
+  auto ld1 = [&](int cj) { if constexpr (GHOST) return (cj < nloc ? in1.v : in1.lo - nloc)[cj]; else return in1.v[cj]; };
+
+  // register stage of the NEXT block
+  double a[kU], x0v[kU], x1v[kU];
+  int col[kU];
+  int n_r0 = 0, n_r1 = 0, n_e0 = 0, n_cnt = 0;
+  // ... and of this thread's row of it: its extent and the operands of the fused epilogue (the SpMV input
+  // at the row, r or b, a Jacobi entry) -- fetched with the stream, so that the row-sum stage of a block
+  // never waits on global memory
+  int n_b0 = 0, n_b1 = 0;
+  double n_pv = 0.0, n_rv = 0.0, n_dv = 0.0;
+  constexpr bool kEpP = (MODE == SP_HS || MODE == SP_CG || MODE == SP_PR);
+  constexpr bool kEpR = (MODE == SP_CG || MODE == SP_PR || MODE == SP_RESID);
+  constexpr bool kEpD = (MODE == SP_PR && PM == 1);
+  auto load_block = [&](int blk) {                             // (value, column) stream: coalesced, all in flight
+    n_r0 = __ldg(row_blocks + blk); n_r1 = __ldg(row_blocks + blk + 1);
+    n_e0 = __ldg(A.ptr + n_r0);
+    n_cnt = __ldg(A.ptr + n_r1) - n_e0;
+    {
+      const int row = n_r0 + tid;
+      const bool ok = row < n_r1;
+      n_b0 = ok ? __ldg(A.ptr + row) : 0;
+      n_b1 = ok ? __ldg(A.ptr + row + 1) : 0;
+      const int rr = ok ? row : n_r0;
+      if constexpr (kEpP) n_pv = in0.v[rr];
+      if constexpr (kEpR) n_rv = (MODE == SP_RESID) ? g.b[rr] : g.r[rr];
+      if constexpr (kEpD) n_dv = g.dinv[rr];
+    }
+    if (n_cnt <= kCsrCap) {
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int j = tid + u * kBlock;
-        const bool ok = j < cnt;
-        a[u] = ok ? __ldg(A.val + e0 + j) : 0.0;
-        col[u] = ok ? __ldg(A.idx + e0 + j) : r0;
+        const bool ok = j < n_cnt;
+        a[u] = ok ? __ldg(A.val + n_e0 + j) : 0.0;
+        col[u] = ok ? __ldg(A.idx + n_e0 + j) : n_r0;
       }
-      double x0v[kU], x1v[kU];
+    }
+  };
+  auto gather_block = [&]() {
+    if (n_cnt <= kCsrCap) {
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         x0v[u] = ld0(col[u]);
         if constexpr (NV == 2) x1v[u] = ld1(col[u]); else x1v[u] = 0.0;
       }
+    }
+  };
+
+  int blk = blockIdx.x;
+  if (blk < nblocks) { load_block(blk); gather_block(); }
+  int buf = 0;
+  for (; blk < nblocks; blk += gridDim.x, buf ^= 1) {
+    double* prod = prod_dyn + (size_t)buf * NV * kCsrCap;
+    const int r0 = n_r0, r1 = n_r1, e0 = n_e0, cnt = n_cnt;
+    const int b0 = n_b0 - n_e0, b1 = n_b1 - n_e0;
+    const double pv = n_pv, rv = n_rv, dv = n_dv;
+    const int nblk = blk + gridDim.x;
+    if (cnt <= kCsrCap) {
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int j = tid + u * kBlock;
         if (j < cnt) {
-          prod[0][j] = mul_(a[u], x0v[u]);
-          if constexpr (NV == 2) prod[1][j] = mul_(a[u], x1v[u]);
+          prod[j] = mul_(a[u], x0v[u]);
+          if constexpr (NV == 2) prod[kCsrCap + j] = mul_(a[u], x1v[u]);
         }
       }
-      }
-      __syncthreads();
+      __syncthreads();               // products of this block visible (and: everyone has left the block before last)
+      if (nblk < nblocks) load_block(nblk);
       const int row = r0 + tid;
       if (row < r1) {
-        const int b0 = __ldg(A.ptr + row) - e0, b1 = __ldg(A.ptr + row + 1) - e0;
         double y[NV];
 #pragma unroll
         for (int c = 0; c < NV; ++c) y[c] = 0.0;
         for (int j = b0; j < b1; ++j) {
 #pragma unroll
-          for (int c = 0; c < NV; ++c) y[c] = add_(y[c], prod[c][j]);
+          for (int c = 0; c < NV; ++c) y[c] = add_(y[c], prod[c * kCsrCap + j]);
         }
-        sp_epilogue<MODE, PM, NV>(g, in0, (i64)row, y, red, vout);
+        // fused epilogue on the prefetched operands (same statements as sp_epilogue)
+        if constexpr (MODE == SP_PIPE_R) { g.u[row] = y[0]; g.w[row] = y[NV - 1]; }
+        else if constexpr (MODE == SP_PLAIN) vout[row] = y[0];
+        else if constexpr (MODE == SP_RESID) vout[row] = sub_(rv, y[0]);
+        else if constexpr (MODE == SP_HS) { g.s[row] = y[0]; red[0] = fma(pv, y[0], red[0]); }
+        else if constexpr (MODE == SP_CG) { g.w[row] = y[0]; red[0] = fma(rv, pv, red[0]); red[1] = fma(y[0], pv, red[1]); }
+        else if constexpr (MODE == SP_GV) g.t[row] = y[0];
+        else if constexpr (MODE == SP_PR) {
+          g.s[row] = y[0];
+          const double sti = PM == 1 ? mul_(dv, y[0]) : (PM == 2 ? mul_(g.dinv_s, y[0]) : y[0]);
+          red[0] = fma(pv, y[0], red[0]);
+          red[1] = fma(rv, sti, red[1]);
+          red[2] = fma(sti, y[0], red[2]);
+        } else g.u[row] = y[0];                                  // SP_PIPE_N
       }
-      __syncthreads();
-    } else {                                   // one long row
+      if (nblk < nblocks) gather_block();
+    } else {                                   // one long row: chunk after chunk, summed in order by one thread
       double y[NV];
 #pragma unroll
       for (int c = 0; c < NV; ++c) y[c] = 0.0;
       for (int base = 0; base < cnt; base += kCsrCap) {
         const int m = min(kCsrCap, cnt - base);
+        __syncthreads();
         for (int j = tid; j < m; j += kBlock) {
-          const double a = __ldg(A.val + e0 + base + j);
-          const int col = __ldg(A.idx + e0 + base + j);
-          prod[0][j] = mul_(a, ld0(col));
-          if constexpr (NV == 2) prod[1][j] = mul_(a, ld1(col));
+          const double av = __ldg(A.val + e0 + base + j);
+          const int cj = __ldg(A.idx + e0 + base + j);
+          prod[j] = mul_(av, ld0(cj));
+          if constexpr (NV == 2) prod[kCsrCap + j] = mul_(av, ld1(cj));
         }
         __syncthreads();
         if (tid == 0)
           for (int j = 0; j < m; ++j) {
 #pragma unroll
-            for (int c = 0; c < NV; ++c) y[c] = add_(y[c], prod[c][j]);
+            for (int c = 0; c < NV; ++c) y[c] = add_(y[c], prod[c * kCsrCap + j]);
           }
-        __syncthreads();
       }
       if (tid == 0) sp_epilogue<MODE, PM, NV>(g, in0, (i64)r0, y, red, vout);
+      __syncthreads();
+      if (nblk < nblocks) { load_block(nblk); gather_block(); }
     }
   }
   spmv_close<MODE, MEURANT>(g, red);

@@ -93,10 +93,21 @@ def test_canonical_csr():
         canonical_csr(sps.csr_matrix(np.ones((2, 3))))
 
 
-def test_gv_rejects_residual_replacement():
-    A = helpers.load_matrix("nos4")
-    with pytest.raises(NotImplementedError):
-        cg_variants.gv_pcg(A, np.ones(100), np.zeros(100), 5, w_replace=lambda **kw: True)
+def test_gv_w_replace_is_planned_not_rejected():
+    """gv_cg.py:156-158: a predicate that only looks at k becomes a device schedule, one that reads
+    vectors is evaluated on the host every iteration ("host"), the reference's default never fires."""
+    from new_cg_variants_b200.cg_variants import _plan_w_replace, _never
+    assert _plan_w_replace(_never, 50) is None
+    assert _plan_w_replace(lambda **kw: False, 50) is None
+    sched = _plan_w_replace(lambda **kw: kw["k"] % 10 == 0, 35)
+    assert sched.dtype == np.uint8 and list(np.nonzero(sched)[0]) == [10, 20, 30]
+    assert _plan_w_replace(lambda **kw: np.linalg.norm(kw["w"]) > 1.0, 20) == "host"
+    # stateful predicates get the reference's scratch dict, in iteration order
+    def every_third(**kw):
+        f = kw["wk_replace_flags"]
+        f["n"] = f.get("n", 0) + 1
+        return f["n"] % 3 == 0
+    assert list(np.nonzero(_plan_w_replace(every_third, 10))[0]) == [3, 6, 9]
 
 
 def test_convergence_metrics_definition():
