@@ -61,8 +61,8 @@ static int nccl_load(const char* path) {
 const char* const kVecNames[V_COUNT] = {"x", "r", "rt", "p", "s", "st", "w", "wt", "u", "t"};
 
 static void free_op(cgx_ctx* c) {
-  cudaFree(c->d_ptr); cudaFree(c->d_idx); cudaFree(c->d_val); cudaFree(c->d_rowblk); cudaFree(c->d_send_idx);
-  c->d_ptr = c->d_idx = c->d_rowblk = c->d_send_idx = nullptr; c->d_val = nullptr;
+  cudaFree(c->d_ptr); cudaFree(c->d_idx); cudaFree(c->d_val); cudaFree(c->d_rowblk); cudaFree(c->d_send_idx); cudaFree(c->d_rowblk_e0);
+  c->d_ptr = c->d_idx = c->d_rowblk = c->d_send_idx = c->d_rowblk_e0 = nullptr; c->d_val = nullptr;
   c->n_rowblk = 0;
   c->h_ptr.clear();
   c->op_kind = 0;
@@ -169,7 +169,7 @@ extern "C" int cgx_ctx_destroy(cgx_ctx* c) {
 // ---------------------------------------------------------------------------------------
 // operator / preconditioner / problem
 // ---------------------------------------------------------------------------------------
-// CSR-stream row blocks: consecutive rows, at most kBlock of them and kCsrCap non-zeros
+// CSR-stream row blocks: consecutive rows, at most kCsrRows of them and kCsrCap non-zeros
 // (a single longer row is a block of its own).
 static void build_row_blocks(const int32_t* ptr, i64 n, std::vector<int>& blk) {
   blk.clear();
@@ -177,7 +177,7 @@ static void build_row_blocks(const int32_t* ptr, i64 n, std::vector<int>& blk) {
   i64 r = 0;
   while (r < n) {
     i64 e = r + 1;
-    while (e < n && e - r < kBlock && (i64)ptr[e + 1] - ptr[r] <= kCsrCap) ++e;
+    while (e < n && e - r < kCsrRows && (i64)ptr[e + 1] - ptr[r] <= kCsrCap) ++e;
     blk.push_back((int)e);
     r = e;
   }
@@ -194,6 +194,10 @@ static int upload_csr(cgx_ctx* c, i64 n, i64 nnz, const int32_t* indptr, const i
   CU(cudaMalloc(&c->d_idx, sizeof(int) * std::max<i64>(nnz, 1)));
   CU(cudaMalloc(&c->d_val, sizeof(double) * std::max<i64>(nnz, 1)));
   CU(cudaMalloc(&c->d_rowblk, sizeof(int) * blk.size()));
+  CU(cudaMalloc(&c->d_rowblk_e0, sizeof(int) * blk.size()));
+  std::vector<int> blk_e0(blk.size());
+  for (size_t q = 0; q < blk.size(); ++q) blk_e0[q] = indptr[blk[q]];
+  CU(cudaMemcpyAsync(c->d_rowblk_e0, blk_e0.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_ptr, indptr, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_rowblk, blk.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice, c->stream));
   if (nnz) {
@@ -342,6 +346,7 @@ Args make_args(cgx_ctx* c) {
   g.n = c->n; g.k = c->cur_k;
   g.d = c->dist;
   g.halo_ll = c->halo_ll ? 1 : 0;
+  g.errflag = c->d_tma_err;
   // L2 residency hint: measured at 2.1 M rows (one slab of 256^3 / 8) 2-6 % per iteration; auto = on when this
   // GPU's state vectors (<= 10 x n) fit well inside the 126 MB L2
   g.l2pol = (c->l2_keep == 1 || (c->l2_keep < 0 && c->n > 0 && (size_t)c->n * 8 * 6 < ((size_t)96 << 20))) ? kL2EvictLast : 0;
@@ -919,10 +924,10 @@ static int begin_finish(cgx_ctx* c, i64 launches0) {
 }
 
 static int check_device_flags(cgx_ctx* c, const char* who) {
-  if (c->use_tma) {
+  if (c->use_tma || c->op_kind == 1) {
     int flag = 0;
     CU(cudaMemcpy(&flag, c->d_tma_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) return fail(CGX_ERR_CUDA, "%s: a TMA plane copy did not complete within 1 s", who);
+    if (flag) return fail(CGX_ERR_CUDA, "%s: an in-kernel pipeline wait (TMA plane copy / CSR product slot) did not complete within 1 s", who);
   }
   if (c->dist.world > 1 && c->d_win) {
     int err = 0;
@@ -1430,6 +1435,7 @@ extern "C" int cgx_spmv_host(cgx_ctx* c, const double* v, double* y, int64_t n) 
   Args g{};
   g.n = n;
   g.d.world = 1;
+  g.errflag = c->d_tma_err;
   CUtensorMap tm;
   if (c->op_kind == 2 && tma_prepare_geom(c) && tma_encode_dims(dv, c->sten.nx, c->sten.ny, c->sten.nz, &tm)) {
     // the TMA-staged stencil kernel in its plainest mode (SP_PIPE_N: u = A v, no epilogue)

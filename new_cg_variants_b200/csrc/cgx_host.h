@@ -70,6 +70,7 @@ struct cgx_ctx {
   bool no_slab = false;            // cgx_set_option("csr_slab", 0)
   int* d_send_idx = nullptr;       // CSR row partition: local rows to send (Dist::send_idx)
   int* d_rowblk = nullptr;         // CSR-stream row blocks (cgx_kernels.cuh)
+  int* d_rowblk_e0 = nullptr;      // first non-zero of every row block (= indptr[row_blocks[b]])
   int n_rowblk = 0;
   i64 n = 0, nnz = 0;
   // preconditioner: pm = 0 identity, 1 Jacobi vector, 2 Jacobi with a constant diagonal

@@ -98,6 +98,7 @@ struct Args {
   u64 xt_epoch;
   int meur;                        // Meurant predictor (kernels that are not templated on it)
   int halo_ll;                     // the consumer is the TMA stencil kernel: boundary planes travel as LL words
+  int* errflag;                    // device word set by a bounded in-kernel wait that expired
   unsigned long long l2pol;        // 0, or an L2 cache-policy word for the state-vector accesses (kL2EvictLast)
   double* gscr;                    // fused PR kernel on a partition: [plane] new p of the ghost plane above the slab
   int dbg;                         // timing experiments (cgx_set_option "debug_skip"): 1 = no halo traffic, 2 = time stamps
@@ -681,146 +682,240 @@ __global__ void __launch_bounds__(kBlock) spmv_kernel(const Op A, const Args g, 
 // csr_matvec rounding exactly.  A row longer than kCsrCap is a block of its own, summed in
 // order by one thread chunk after chunk.
 constexpr int kCsrCap = 2048;
+constexpr int kCsrRows = 223;          // rows per block at most: a loader thread per row extent (rows + 1 of them)
 
-// GHOST: this launch is a rank of a CSR row partition -- columns >= n address the staging array of
-// gathered ghost entries (a pointer select per gather; compiled out for single-GPU runs, where it
-// cost 30 % of the pass on the banded model problem).
-//
-// Software-pipelined: while the CTA adds up the rows of block k (shared memory only), the (value,
-// column) stream of block k + gridDim.x is already in flight into registers and its gathers follow
-// as soon as the columns have landed; the products are double-buffered in shared memory, so there
-// is ONE CTA barrier per block.  (ncu on the un-pipelined form: 61 % of the stall samples waited on
-// the load -> gather chain, 27 % at the two barriers.)
-__host__ __device__ constexpr size_t csr_stream_smem_bytes(int nv) { return (size_t)2 * nv * kCsrCap * sizeof(double); }
+// Warp-specialised: 7 LOADER warps stream a block's (value, column) pairs with coalesced loads -- all of
+// a thread's loads in flight at once, then all its gathers --, multiply and store the products into one
+// slot of a ring in shared memory, together with the block's row extents and the operands of the fused
+// epilogue (SpMV input at the row, r or b, Jacobi entry); 1 SUMMING warp adds up every row's products in
+// stored order (lane l: rows l, l+32, ... of the block) and applies the epilogue, all from shared memory.
+// Slots are handed over through full / empty mbarriers, so the (latency-bound, few-threads) row sums of
+// block k overlap the streaming of blocks k+1, k+2 in the SAME CTA; there is no CTA-wide barrier.
+// (History: the one-phase-at-a-time form reached 0.63-0.79 of the HBM peak on the banded model problem
+// and 0.45 with two right-hand sides -- ncu: 61 % of the stall samples on the load -> gather chain, 27 % at
+// the two barriers around the row sums, which a single warp's worth of threads executed.)
+// A row longer than kCsrCap is a block of its own, handed over chunk by chunk.
+// GHOST: this launch is a rank of a CSR row partition -- columns >= n address the staging array of gathered
+// ghost entries (a pointer select per gather; compiled out for single-GPU runs).
+constexpr int kCsrLoaders = kBlock - 32;                       // 224 loader threads
+constexpr int kCsrUL = (kCsrCap + kCsrLoaders - 1) / kCsrLoaders;   // elements per loader thread per block
+__host__ __device__ constexpr int csr_ring(int nv) { return nv == 2 ? 2 : 3; }
+struct CsrSlotMeta { int r0, r1, cnt, last; };                 // rows, products in the slot, last chunk of its block
+__host__ __device__ constexpr size_t csr_slot_doubles(int nv) { return (size_t)nv * kCsrCap + 3 * kBlock; }
+__host__ __device__ constexpr size_t csr_stream_smem_bytes(int nv) {
+  return (size_t)csr_ring(nv) * (csr_slot_doubles(nv) * sizeof(double) + (kBlock + 4) * sizeof(int) + sizeof(CsrSlotMeta));
+}
 
 template <int MODE, int PM, bool MEURANT, bool GHOST>
-__global__ void __launch_bounds__(kBlock) csr_stream_kernel(const CsrOp A, const int* __restrict__ row_blocks,
-                                                           int nblocks, const Args g, const VecIn in0,
-                                                           const VecIn in1, double* vout) {
+__global__ void __launch_bounds__(kBlock)
+csr_stream_kernel(const CsrOp A, const int* __restrict__ row_blocks, const int* __restrict__ blk_e0, int nblocks, const Args g,
+                                                           const VecIn in0, const VecIn in1, double* vout) {
   constexpr int NV = SpTraits<MODE>::NV;
-  constexpr int kU = kCsrCap / kBlock;
-  extern __shared__ __align__(16) double prod_dyn[];          // [2][NV][kCsrCap]
-  double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
+  constexpr int S = csr_ring(NV);
+  extern __shared__ __align__(16) unsigned char csr_smem[];
+  double* sm_d = reinterpret_cast<double*>(csr_smem);                                   // [S][NV*cap + 3*kBlock]
+  int* sm_rp = reinterpret_cast<int*>(sm_d + (size_t)S * csr_slot_doubles(NV));         // [S][kBlock + 4] row extents
+  CsrSlotMeta* sm_meta = reinterpret_cast<CsrSlotMeta*>(sm_rp + S * (kBlock + 4));      // [S]
+  __shared__ __align__(8) uint64_t full_bar[3], empty_bar[3];
   const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], kCsrLoaders / 32); mbar_init(&empty_bar[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   if constexpr (GHOST) halo_wait_all(g, NV);
+  double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
   const int nloc = (int)g.n;
   auto ld0 = [&](int cj) { if constexpr (GHOST) return (cj < nloc ? in0.v : in0.lo - nloc)[cj]; else return in0.v[cj]; };
   auto ld1 = [&](int cj) { if constexpr (GHOST) return (cj < nloc ? in1.v : in1.lo - nloc)[cj]; else return in1.v[cj]; };
-
-  // register stage of the NEXT block
-  double a[kU], x0v[kU], x1v[kU];
-  int col[kU];
-  int n_r0 = 0, n_r1 = 0, n_e0 = 0, n_cnt = 0;
-  // ... and of this thread's row of it: its extent and the operands of the fused epilogue (the SpMV input
-  // at the row, r or b, a Jacobi entry) -- fetched with the stream, so that the row-sum stage of a block
-  // never waits on global memory
-  int n_b0 = 0, n_b1 = 0;
-  double n_pv = 0.0, n_rv = 0.0, n_dv = 0.0;
   constexpr bool kEpP = (MODE == SP_HS || MODE == SP_CG || MODE == SP_PR);
   constexpr bool kEpR = (MODE == SP_CG || MODE == SP_PR || MODE == SP_RESID);
   constexpr bool kEpD = (MODE == SP_PR && PM == 1);
-  auto load_block = [&](int blk) {                             // (value, column) stream: coalesced, all in flight
-    n_r0 = __ldg(row_blocks + blk); n_r1 = __ldg(row_blocks + blk + 1);
-    n_e0 = __ldg(A.ptr + n_r0);
-    n_cnt = __ldg(A.ptr + n_r1) - n_e0;
-    {
-      const int row = n_r0 + tid;
-      const bool ok = row < n_r1;
-      n_b0 = ok ? __ldg(A.ptr + row) : 0;
-      n_b1 = ok ? __ldg(A.ptr + row + 1) : 0;
-      const int rr = ok ? row : n_r0;
-      if constexpr (kEpP) n_pv = in0.v[rr];
-      if constexpr (kEpR) n_rv = (MODE == SP_RESID) ? g.b[rr] : g.r[rr];
-      if constexpr (kEpD) n_dv = g.dinv[rr];
-    }
-    if (n_cnt <= kCsrCap) {
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int j = tid + u * kBlock;
-        const bool ok = j < n_cnt;
-        a[u] = ok ? __ldg(A.val + n_e0 + j) : 0.0;
-        col[u] = ok ? __ldg(A.idx + n_e0 + j) : n_r0;
-      }
-    }
-  };
-  auto gather_block = [&]() {
-    if (n_cnt <= kCsrCap) {
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        x0v[u] = ld0(col[u]);
-        if constexpr (NV == 2) x1v[u] = ld1(col[u]); else x1v[u] = 0.0;
-      }
-    }
-  };
 
-  int blk = blockIdx.x;
-  if (blk < nblocks) { load_block(blk); gather_block(); }
-  int buf = 0;
-  for (; blk < nblocks; blk += gridDim.x, buf ^= 1) {
-    double* prod = prod_dyn + (size_t)buf * NV * kCsrCap;
-    const int r0 = n_r0, r1 = n_r1, e0 = n_e0, cnt = n_cnt;
-    const int b0 = n_b0 - n_e0, b1 = n_b1 - n_e0;
-    const double pv = n_pv, rv = n_rv, dv = n_dv;
-    const int nblk = blk + gridDim.x;
-    if (cnt <= kCsrCap) {
+  if (tid < kCsrLoaders) {
+    // ------------------------------------------------------------------ loader warps
+    // Work items = (row block, chunk) in launch order.  The (value, column) loads of item i+1 are issued
+    // BEFORE item i is gathered / multiplied / handed over (two alternating register sets), so that each
+    // loader thread keeps two blocks' worth of the matrix stream in flight.
+    // Block metadata (rows and first non-zero of the block: row_blocks / blk_e0, host-built) is fetched TWO
+    // blocks ahead, so that neither the stream loads nor the gathers ever wait on a pointer chase.
+    struct Item { int blk, base, r0, r1, e0, total; bool ok; };
+    auto load_meta = [&](int blk) {
+      Item t{blk, 0, 0, 0, 0, 0, blk < nblocks};
+      if (t.ok) {
+        t.r0 = __ldg(row_blocks + blk); t.r1 = __ldg(row_blocks + blk + 1);
+        t.e0 = __ldg(blk_e0 + blk); t.total = __ldg(blk_e0 + blk + 1) - t.e0;
+      }
+      return t;
+    };
+    Item ahead = load_meta((int)blockIdx.x + (int)gridDim.x);
+    auto first_item = [&]() { return load_meta((int)blockIdx.x); };
+    auto next_item = [&](const Item& c) {
+      Item t = c;
+      if (c.base + kCsrCap < c.total) { t.base = c.base + kCsrCap; return t; }
+      t = ahead;
+      ahead = load_meta(t.blk + (int)gridDim.x);
+      return t;
+    };
+    struct Regs { double a[kCsrUL]; int col[kCsrUL]; };
+    auto issue = [&](const Item& t, Regs& R) {
+      const int cnt = min(kCsrCap, t.total - t.base);
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int j = tid + u * kBlock;
+      for (int u = 0; u < kCsrUL; ++u) {
+        const int j = tid + u * kCsrLoaders;
+        const bool ok = j < cnt;
+        R.a[u] = ok ? __ldg(A.val + t.e0 + t.base + j) : 0.0;
+        R.col[u] = ok ? __ldg(A.idx + t.e0 + t.base + j) : t.r0;
+      }
+    };
+    uint32_t it = 0;
+    auto process = [&](const Item& t, Regs& R) {
+      const int cnt = min(kCsrCap, t.total - t.base);
+      const int slot = it % S;
+      double x0v[kCsrUL], x1v[kCsrUL];
+#pragma unroll
+      for (int u = 0; u < kCsrUL; ++u) {
+        x0v[u] = ld0(R.col[u]);
+        if constexpr (NV == 2) x1v[u] = ld1(R.col[u]); else x1v[u] = 0.0;
+      }
+      // row extent and epilogue operands of this thread's row of the block (first chunk only): fetched
+      // with the gathers (same round trip)
+      const int row = t.r0 + tid;
+      const bool hasrow = t.base == 0 && row <= t.r1;
+      int rp = 0;
+      double pv = 0.0, rv = 0.0, dv = 0.0;
+      if (hasrow) {
+        rp = __ldg(A.ptr + row) - t.e0;
+        if (row < t.r1) {
+          if constexpr (kEpP) pv = in0.v[row];
+          if constexpr (kEpR) rv = (MODE == SP_RESID) ? g.b[row] : g.r[row];
+          if constexpr (kEpD) dv = g.dinv[row];
+        }
+      }
+      if (it >= (uint32_t)S) mbar_wait(&empty_bar[slot], ((it / S) - 1) & 1u, g.errflag);
+      double* prod = sm_d + (size_t)slot * csr_slot_doubles(NV);
+      double* ep = prod + (size_t)NV * kCsrCap;                  // [3][kBlock]: pv, rv, dv
+      int* rps = sm_rp + slot * (kBlock + 4);
+#pragma unroll
+      for (int u = 0; u < kCsrUL; ++u) {
+        const int j = tid + u * kCsrLoaders;
         if (j < cnt) {
-          prod[j] = mul_(a[u], x0v[u]);
-          if constexpr (NV == 2) prod[kCsrCap + j] = mul_(a[u], x1v[u]);
+          prod[j] = mul_(R.a[u], x0v[u]);
+          if constexpr (NV == 2) prod[kCsrCap + j] = mul_(R.a[u], x1v[u]);
         }
       }
-      __syncthreads();               // products of this block visible (and: everyone has left the block before last)
-      if (nblk < nblocks) load_block(nblk);
-      const int row = r0 + tid;
-      if (row < r1) {
-        double y[NV];
+      if (hasrow) { rps[tid] = rp; ep[tid] = pv; ep[kBlock + tid] = rv; ep[2 * kBlock + tid] = dv; }
+      if (tid == 0) sm_meta[slot] = CsrSlotMeta{t.r0, t.r1, cnt, t.base + kCsrCap >= t.total ? 1 : 0};
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&full_bar[slot]);
+      ++it;
+    };
+    Regs RA, RB;
+    Item ia = first_item(), ib;
+    if (ia.ok) issue(ia, RA);
+    while (ia.ok) {
+      ib = next_item(ia);
+      if (ib.ok) issue(ib, RB);
+      process(ia, RA);
+      if (!ib.ok) break;
+      ia = next_item(ib);
+      if (ia.ok) issue(ia, RA);
+      process(ib, RB);
+    }
+  } else {
+    // ------------------------------------------------------------------ summing warp
+    const int lane = tid - kCsrLoaders;
+    uint32_t it = 0;
+    double ylong[NV];
 #pragma unroll
-        for (int c = 0; c < NV; ++c) y[c] = 0.0;
-        for (int j = b0; j < b1; ++j) {
+    for (int c = 0; c < NV; ++c) ylong[c] = 0.0;
+    for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+      const int total = __ldg(blk_e0 + blk + 1) - __ldg(blk_e0 + blk);
+      for (int base = 0; base == 0 || base < total; base += kCsrCap, ++it) {
+        const int slot = it % S;
+        mbar_wait(&full_bar[slot], (it / S) & 1u, g.errflag);
+        const double* prod = sm_d + (size_t)slot * csr_slot_doubles(NV);
+        const double* ep = prod + (size_t)NV * kCsrCap;
+        const int* rps = sm_rp + slot * (kBlock + 4);
+        const CsrSlotMeta m = sm_meta[slot];
+        auto epilogue = [&](int row, int t, const double (&y)[NV]) {     // same statements as sp_epilogue
+          const double pv = ep[t], rv = ep[kBlock + t], dv = ep[2 * kBlock + t];
+          if constexpr (MODE == SP_PIPE_R) { g.u[row] = y[0]; g.w[row] = y[NV - 1]; }
+          else if constexpr (MODE == SP_PLAIN) vout[row] = y[0];
+          else if constexpr (MODE == SP_RESID) vout[row] = sub_(rv, y[0]);
+          else if constexpr (MODE == SP_HS) { g.s[row] = y[0]; red[0] = fma(pv, y[0], red[0]); }
+          else if constexpr (MODE == SP_CG) { g.w[row] = y[0]; red[0] = fma(rv, pv, red[0]); red[1] = fma(y[0], pv, red[1]); }
+          else if constexpr (MODE == SP_GV) g.t[row] = y[0];
+          else if constexpr (MODE == SP_PR) {
+            g.s[row] = y[0];
+            const double sti = PM == 1 ? mul_(dv, y[0]) : (PM == 2 ? mul_(g.dinv_s, y[0]) : y[0]);
+            red[0] = fma(pv, y[0], red[0]);
+            red[1] = fma(rv, sti, red[1]);
+            red[2] = fma(sti, y[0], red[2]);
+          } else g.u[row] = y[0];                                  // SP_PIPE_N
+          (void)pv; (void)rv; (void)dv;
+        };
+        if (total <= kCsrCap) {
+          for (int t = lane; t < m.r1 - m.r0; t += 32) {
+            const int b0 = rps[t], b1 = rps[t + 1];
+            double y[NV];
 #pragma unroll
-          for (int c = 0; c < NV; ++c) y[c] = add_(y[c], prod[c * kCsrCap + j]);
-        }
-        // fused epilogue on the prefetched operands (same statements as sp_epilogue)
-        if constexpr (MODE == SP_PIPE_R) { g.u[row] = y[0]; g.w[row] = y[NV - 1]; }
-        else if constexpr (MODE == SP_PLAIN) vout[row] = y[0];
-        else if constexpr (MODE == SP_RESID) vout[row] = sub_(rv, y[0]);
-        else if constexpr (MODE == SP_HS) { g.s[row] = y[0]; red[0] = fma(pv, y[0], red[0]); }
-        else if constexpr (MODE == SP_CG) { g.w[row] = y[0]; red[0] = fma(rv, pv, red[0]); red[1] = fma(y[0], pv, red[1]); }
-        else if constexpr (MODE == SP_GV) g.t[row] = y[0];
-        else if constexpr (MODE == SP_PR) {
-          g.s[row] = y[0];
-          const double sti = PM == 1 ? mul_(dv, y[0]) : (PM == 2 ? mul_(g.dinv_s, y[0]) : y[0]);
-          red[0] = fma(pv, y[0], red[0]);
-          red[1] = fma(rv, sti, red[1]);
-          red[2] = fma(sti, y[0], red[2]);
-        } else g.u[row] = y[0];                                  // SP_PIPE_N
-      }
-      if (nblk < nblocks) gather_block();
-    } else {                                   // one long row: chunk after chunk, summed in order by one thread
-      double y[NV];
+            for (int c = 0; c < NV; ++c) y[c] = 0.0;
+            // products fetched eight at a time (independent shared-memory loads), then added in stored
+            // order: the chain the hardware must serialise is the additions only
+            int j = b0;
+            for (; j + 8 <= b1; j += 8) {
+              double t8[NV][8];
 #pragma unroll
-      for (int c = 0; c < NV; ++c) y[c] = 0.0;
-      for (int base = 0; base < cnt; base += kCsrCap) {
-        const int m = min(kCsrCap, cnt - base);
-        __syncthreads();
-        for (int j = tid; j < m; j += kBlock) {
-          const double av = __ldg(A.val + e0 + base + j);
-          const int cj = __ldg(A.idx + e0 + base + j);
-          prod[j] = mul_(av, ld0(cj));
-          if constexpr (NV == 2) prod[kCsrCap + j] = mul_(av, ld1(cj));
-        }
-        __syncthreads();
-        if (tid == 0)
-          for (int j = 0; j < m; ++j) {
+              for (int c = 0; c < NV; ++c)
 #pragma unroll
-            for (int c = 0; c < NV; ++c) y[c] = add_(y[c], prod[c * kCsrCap + j]);
+                for (int q = 0; q < 8; ++q) t8[c][q] = prod[c * kCsrCap + j + q];
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+#pragma unroll
+                for (int c = 0; c < NV; ++c) y[c] = add_(y[c], t8[c][q]);
+            }
+            for (; j < b1; ++j) {
+#pragma unroll
+              for (int c = 0; c < NV; ++c) y[c] = add_(y[c], prod[c * kCsrCap + j]);
+            }
+            epilogue(m.r0 + t, t, y);
           }
+        } else {                                                   // one long row, chunk by chunk, in order
+          if (lane == 0) {
+            for (int j = 0; j < m.cnt; ++j) {
+#pragma unroll
+              for (int c = 0; c < NV; ++c) ylong[c] = add_(ylong[c], prod[c * kCsrCap + j]);
+            }
+            if (m.last) {
+              // (the operands of the first chunk's slot are gone: fetch them here, once per long row)
+              double pv = 0.0, rv = 0.0, dv = 0.0;
+              if constexpr (kEpP) pv = in0.v[m.r0];
+              if constexpr (kEpR) rv = (MODE == SP_RESID) ? g.b[m.r0] : g.r[m.r0];
+              if constexpr (kEpD) dv = g.dinv[m.r0];
+              const int row = m.r0;
+              if constexpr (MODE == SP_PIPE_R) { g.u[row] = ylong[0]; g.w[row] = ylong[NV - 1]; }
+              else if constexpr (MODE == SP_PLAIN) vout[row] = ylong[0];
+              else if constexpr (MODE == SP_RESID) vout[row] = sub_(rv, ylong[0]);
+              else if constexpr (MODE == SP_HS) { g.s[row] = ylong[0]; red[0] = fma(pv, ylong[0], red[0]); }
+              else if constexpr (MODE == SP_CG) { g.w[row] = ylong[0]; red[0] = fma(rv, pv, red[0]); red[1] = fma(ylong[0], pv, red[1]); }
+              else if constexpr (MODE == SP_GV) g.t[row] = ylong[0];
+              else if constexpr (MODE == SP_PR) {
+                g.s[row] = ylong[0];
+                const double sti = PM == 1 ? mul_(dv, ylong[0]) : (PM == 2 ? mul_(g.dinv_s, ylong[0]) : ylong[0]);
+                red[0] = fma(pv, ylong[0], red[0]);
+                red[1] = fma(rv, sti, red[1]);
+                red[2] = fma(sti, ylong[0], red[2]);
+              } else g.u[row] = ylong[0];
+              (void)pv; (void)rv; (void)dv;
+#pragma unroll
+              for (int c = 0; c < NV; ++c) ylong[c] = 0.0;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[slot]);
       }
-      if (tid == 0) sp_epilogue<MODE, PM, NV>(g, in0, (i64)r0, y, red, vout);
-      __syncthreads();
-      if (nblk < nblocks) { load_block(nblk); gather_block(); }
     }
   }
   spmv_close<MODE, MEURANT>(g, red);

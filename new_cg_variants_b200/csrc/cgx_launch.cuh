@@ -54,11 +54,11 @@ static void launch_spmv(cgx_ctx* c, Args g, const double* vin, double* vout) {
           if (csr_dist(c)) {
             const int per_sm = ctx_occupancy(c, (const void*)csr_stream_kernel<MODE, PM, MEUR, true>, kBlock, sm);
             const int grid1 = std::max(1, std::min(c->n_rowblk, c->sm_count * per_sm));
-            csr_stream_kernel<MODE, PM, MEUR, true><<<grid1, kBlock, sm, c->stream>>>(c->csr, c->d_rowblk, c->n_rowblk, g, in0, in1, vout);
+            csr_stream_kernel<MODE, PM, MEUR, true><<<grid1, kBlock, sm, c->stream>>>(c->csr, c->d_rowblk, c->d_rowblk_e0, c->n_rowblk, g, in0, in1, vout);
           } else {
             const int per_sm = ctx_occupancy(c, (const void*)csr_stream_kernel<MODE, PM, MEUR, false>, kBlock, sm);
             const int grid1 = std::max(1, std::min(c->n_rowblk, c->sm_count * per_sm));
-            csr_stream_kernel<MODE, PM, MEUR, false><<<grid1, kBlock, sm, c->stream>>>(c->csr, c->d_rowblk, c->n_rowblk, g, in0, in1, vout);
+            csr_stream_kernel<MODE, PM, MEUR, false><<<grid1, kBlock, sm, c->stream>>>(c->csr, c->d_rowblk, c->d_rowblk_e0, c->n_rowblk, g, in0, in1, vout);
           }
         } else {
           spmv_kernel<CsrOp, MODE, PM, MEUR><<<grid_for(c, c->n), kBlock, 0, c->stream>>>(c->csr, g, in0, in1, vout);
