@@ -43,7 +43,8 @@ def main():
         lines.append("    stalls (warps per issue-active cycle): " + json.dumps(stalls))
     path = os.path.join(ROOT, "profiles", "traffic.json")
     t = json.load(open(path)) if os.path.exists(path) else {}
-    t = {k: v for k, v in t.items() if isinstance(v, dict)}          # drop un-stamped legacy entries
+    fp = _b.kernel_fingerprint()
+    t = {k: v for k, v in t.items() if isinstance(v, dict) and v.get("kernel_sources_sha") == fp}   # drop stale / legacy entries
     t[cls] = {"dram_bytes_per_launch": sum(per) / len(per), "launches": len(per),
               "kernel_sources_sha": _b.kernel_fingerprint(),
               "source": f"ncu --set full --clock-control none ({os.path.basename(rep)}): dram__bytes_read.sum + dram__bytes_write.sum"}
