@@ -68,6 +68,14 @@ template <int W> __device__ __forceinline__ void stp(double* __restrict__ p, i64
   }
 }
 
+// ---- programmatic dependent launch (the kernels of the iteration loop are launched with
+//      cudaLaunchAttributeProgrammaticStreamSerialization): a kernel lets its successor start launching at
+//      once and does not touch global memory before its predecessor has completed -- the successor's
+//      launch latency and prologue (barrier init, index math) overlap the predecessor's tail.  Both are
+//      no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- mbarrier helpers (producer / consumer pipelines inside a CTA) --------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

@@ -148,6 +148,7 @@ struct cgx_ctx {
   double* alt[3] = {};                     // second buffers of p, s, rt
   double* d_gscr = nullptr;                // partitioned: [2][plane] scratch (new p of the ghost planes)
   CUtensorMap ftmap[2][3];
+  bool pdl = true;                         // option "pdl": programmatic dependent launch of the loop kernels
   int l2_keep = -1;                        // option "l2_keep": -1 auto (partitioned runs whose state fits L2), 0 off, 1 on
   int fused_min_slab = 64;                 // partitioned runs: planes per rank from which the fused kernel is used
   int fused_min_planes = 8, fused_chunks = 0;   // options: planes per CTA at least / force the chunk count
@@ -212,6 +213,18 @@ VecIn vec_in(cgx_ctx* c, const double* v, int ch, const Args& g);
 // Resident CTAs per SM of kernel `fn` on THIS context's device (the dynamic-shared-memory opt-in
 // is a per-device attribute, so it is applied -- and the result cached -- per context).
 int ctx_occupancy(cgx_ctx* c, const void* fn, int threads, size_t smem);
+
+// Launch with programmatic stream serialisation when `pdl` (cgx_common.cuh "programmatic dependent launch").
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 inline size_t tma_smem_bytes(int nv) { return stencil_smem_bytes(nv); }
 

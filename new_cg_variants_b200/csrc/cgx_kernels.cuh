@@ -540,6 +540,8 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(const Args g) {
   const i64 stride = (i64)gridDim.x * kBlock;
   double a, b;
   const bool stamp = (g.dbg & 2) && blockIdx.x == 0 && threadIdx.x == 0;
+  pdl_launch_dependents();
+  pdl_wait();                          // nothing of the previous kernel's data is touched before this
   if (stamp) g.dbg_t[0] = (u64)clock64();
   if (dist) {
     const i64 rot0 = (g.hout_n > 0 && g.d.has_hi) ? nv - (g.d.plane >> 1) : 0;

@@ -72,6 +72,8 @@ pr_fused_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();                          // the prologue above overlapped the previous kernel's tail
 
   double a, b;
   if constexpr (DIST) {

@@ -91,6 +91,8 @@ stencil_tma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();                          // the prologue above overlapped the previous kernel's tail
 
   const int ncols = G.ntx * G.nty;
   const int nunits = ncols * G.nchunk;

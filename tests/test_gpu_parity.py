@@ -583,3 +583,30 @@ def test_banded_model_problem_final_errors_match_the_petsc_run():
         assert lo <= got[tag] <= hi, (tag, got[tag], ref)
     # the paper's point on this problem: pipe-PR recovers HS-level accuracy, GV / pipe-P lose 2-3 digits
     assert got["pipe_pr"] < 10 * got["hs"] and got["gv"] > 50 * got["hs"] and got["pipe_p"] > 50 * got["hs"]
+
+
+@pytest.mark.parametrize("cfg", [("3d", 256, ("pr", "pipe_pr", "hs"), 21), ("2d", 4096, ("pr", "pipe_pr"), 21)])
+def test_baseline_size_matches_oracle(cfg):
+    """BASELINE.json configs[2] / [3] at their OWN size (16.8 M unknowns): the oracle runs on the scipy CSR
+    matrix of the same problem (≈1.3 s per iteration with the four callbacks), the device on the
+    matrix-free operator -- P1 over all 20 iterations on both residual histories and the A-norm error
+    (the window of these problems is far longer: 128^2 already has 188, and it grows with the grid)."""
+    kind, grid, tags, K = cfg
+    A = orc.poisson3d(grid) if kind == "3d" else orc.poisson2d(grid)
+    S = PoissonStencil(grid, grid, grid, dim=3) if kind == "3d" else PoissonStencil(grid, grid, 1, dim=2)
+    x_true, b, x0 = orc.setup_problem(A)
+    dinv = orc.jacobi_dinv(A)
+    assert np.array_equal(S @ x_true, b)
+    for tag in tags:
+        ref = orc.solve(tag, A, b, x0, K, dinv=dinv, x_true=x_true)
+        dev = _device_solve(tag, S, b, x0, K, dinv, x_true, return_info=True)
+        assert dev["_info"]["path"] == 1 and dev["_info"]["kernel_launches"] > 0
+        worst = 0.0
+        for h in ("updated_residual_2_norm", "residual_2_norm", "error_A_norm", "error_2_norm"):
+            rel = np.abs(dev[h] - ref[h]) / np.abs(ref[h])
+            worst = max(worst, float(rel.max()))
+            assert helpers.first_deviation(dev[h], ref[h]) >= K, (cfg, tag, h, rel.max())
+        helpers.log_kd(case=f"poisson{kind}_{grid}_jacobi", variant=tag, path="stream", kd=K, window=K, kstar10=None, ensemble=None,
+                       max_iter=K, iters=0, acc=float(np.log10(dev["error_A_norm"][-1] / dev["error_A_norm"][0])),
+                       iters_band=[0, 0], acc_band=[0.0, 0.0], max_rel=worst)
+        print(f"{kind} {grid} {tag}: max relative deviation over {K} history entries = {worst:.2e}")
