@@ -1135,7 +1135,7 @@ extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
   if (!strcmp(name, "pr_fused")) { c->no_fused = (value == 0); return CGX_OK; }
   if (!strcmp(name, "gv_manual")) { c->gv_manual = value != 0; return CGX_OK; }
   if (!strcmp(name, "fused_min_planes")) { c->fused_min_planes = std::max(1, value); return CGX_OK; }
-  if (!strcmp(name, "pdl")) { c->pdl = value != 0; return CGX_OK; }
+  if (!strcmp(name, "pdl")) { c->pdl_mode = value; return CGX_OK; }
   if (!strcmp(name, "l2_keep")) { c->l2_keep = value; return CGX_OK; }
   if (!strcmp(name, "fused_min_slab")) { c->fused_min_slab = std::max(1, value); return CGX_OK; }
   if (!strcmp(name, "fused_chunks")) { c->fused_chunks = std::max(0, value); return CGX_OK; }

@@ -49,7 +49,7 @@ static void launch_fused_t(cgx_ctx* c, const Args& g, int cur) {
   G.nchunk = std::max(1, std::min(cap / std::max(1, ncols), G.nz / std::max(1, c->fused_min_planes)));
   if (c->fused_chunks > 0) G.nchunk = std::min(c->fused_chunks, G.nz);
   const int grid = (int)std::min<i64>((i64)ncols * G.nchunk, cap);
-  launch_k(pr_fused_kernel<PM, MEUR, DIST>, grid, kFThreads, smem, c->stream, c->pdl, c->ftmap[cur][0], c->ftmap[cur][1],
+  launch_k(pr_fused_kernel<PM, MEUR, DIST>, grid, kFThreads, smem, c->stream, use_pdl(c), c->ftmap[cur][0], c->ftmap[cur][1],
            c->ftmap[cur][2], G, g);
 }
 

@@ -148,7 +148,7 @@ struct cgx_ctx {
   double* alt[3] = {};                     // second buffers of p, s, rt
   double* d_gscr = nullptr;                // partitioned: [2][plane] scratch (new p of the ghost planes)
   CUtensorMap ftmap[2][3];
-  bool pdl = true;                         // option "pdl": programmatic dependent launch of the loop kernels
+  int pdl_mode = 1;                        // option "pdl": 0 off, 1 single-GPU contexts (default), 2 always
   int l2_keep = -1;                        // option "l2_keep": -1 auto (partitioned runs whose state fits L2), 0 off, 1 on
   int fused_min_slab = 64;                 // partitioned runs: planes per rank from which the fused kernel is used
   int fused_min_planes = 8, fused_chunks = 0;   // options: planes per CTA at least / force the chunk count
@@ -225,6 +225,11 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), int grid, int block, size_t 
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
+
+// (measured on 8 GPUs, 256^3: 50.1 us/iteration with it, 48.5 without -- the early-resident CTAs of the next
+// kernel do not pay off when every kernel starts by waiting for its peers; one GPU at the same slab size:
+// 37.3 vs 41.0.  Hence: single-GPU contexts only, unless the option forces it with value 2.)
+inline bool use_pdl(const cgx_ctx* c) { return c->pdl_mode == 2 || (c->pdl_mode == 1 && c->dist.world <= 1); }
 
 inline size_t tma_smem_bytes(int nv) { return stencil_smem_bytes(nv); }
 

@@ -38,7 +38,7 @@ static void launch_spmv(cgx_ctx* c, Args g, const double* vin, double* vout) {
         G.nchunk = std::max(1, std::min(cap / std::max(1, ncols), G.nz / std::max(1, c->tma_min_planes)));
         const int tgrid = (int)std::min<i64>((i64)ncols * G.nchunk, cap);
         g.gscr = c->d_gscr;
-        launch_k(stencil_tma_kernel<MODE, PM, MEUR>, tgrid, kSThreads, tma_smem_bytes(nv), c->stream, c->pdl,
+        launch_k(stencil_tma_kernel<MODE, PM, MEUR>, tgrid, kSThreads, tma_smem_bytes(nv), c->stream, use_pdl(c),
                  c->tmap[v0], c->tmap[v1 < 0 ? v0 : v1], G, g);
         done = true;
       }
@@ -91,7 +91,7 @@ static void launch_ew(cgx_ctx* c, Args g) {
     // for HS-CG's two short ones -- tools/onewave_probe.py)
     if (c->dist.world > 1 || c->one_wave || KID == EW_HS1 || KID == EW_HS2) grid = std::min(grid, per_sm * c->sm_count);
     ProfScope ps(c, PC_EW0 + (KID == EW_CG_E ? (int)EW_CG : KID == EW_GV_E ? (int)EW_GV : KID));
-    launch_k(ew_kernel<KID, PM, MEUR>, grid, kBlock, 0, c->stream, c->pdl, g);
+    launch_k(ew_kernel<KID, PM, MEUR>, grid, kBlock, 0, c->stream, use_pdl(c), g);
     c->launches++;
   }
   plan_commit(c, g, p);
