@@ -12,7 +12,8 @@ Passed in ``callbacks=[...]`` to the solvers of ``new_cg_variants_b200.cg_varian
   bodies below run once on the host afterwards, fed from one device-to-host copy;
 * any other callable makes the solver step the GPU one iteration at a time and call it with
   the reference's keyword protocol (``output, A, b, x_k, r_k, k, max_iter, kwargs, a_k1, a_k2,
-  b_k1, r_k1, ...``).
+  b_k1, r_k1, ...``); further state vectors (``p_k, s_k, rt_k, st_k, w_k, wt_k, u_k, t_k``) are
+  copied off the device for callables that name them as parameters.
 
 The bodies here are plain host-side instrumentation with the reference's semantics, so
 the same objects also work with any solver that follows the ``callback(**locals())``

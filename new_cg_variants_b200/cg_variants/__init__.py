@@ -261,6 +261,14 @@ def _solve_stepwise(sess, tag, A, b, x0, max_iter, x_true, dev_hist, generic, ou
         sess.set_option("gv_manual", 0)
         sess.set_gv_replace(None)
     wk_flags = {}
+    import inspect
+    state_names = {"rt_k", "p_k", "s_k", "st_k", "w_k", "wt_k", "u_k", "t_k"}
+    extra_vectors = set()
+    for cb in generic:
+        try:
+            extra_vectors |= state_names & set(inspect.signature(cb).parameters)
+        except (TypeError, ValueError):
+            pass
     predicted = tag in ("pr", "m") or tag.startswith("pipe")
     b_arr = np.asarray(b, dtype=np.float64)
     a_k1 = a_k2 = 0.0
@@ -291,6 +299,10 @@ def _solve_stepwise(sess, tag, A, b, x0, max_iter, x_true, dev_hist, generic, ou
         loc = dict(output=output, A=A, b=b_arr, x0=x0, x_k=x_k, r_k=r_k, k=k, max_iter=max_iter,
                    n=len(b_arr), kwargs=extra, a_k=sc["a"], a_k1=a_k1, a_k2=a_k2, b_k=b_k, b_k1=b_k1,
                    nu_k=sc["nu"], mu_k=sc["mu"], x_k1=x_k1, r_k1=r_k1)
+        # the reference hands every local to a callback (`callback(**locals())`); the other state vectors
+        # are copied off the device only for callables that NAME them as parameters (p_k, s_k, rt_k, ...)
+        for name in extra_vectors:
+            loc[name] = sess.vector(name[:-2])
         for cb in generic:
             cb(**loc)
         x_k1, r_k1 = x_k, r_k

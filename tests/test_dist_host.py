@@ -70,6 +70,16 @@ def _worker(rank, world, port, q):
             loud = False
         except Exception as e:          # CgxError (no CUDA device) -- never a silent CPU path
             loud = "CUDA" in str(e) or "cuda" in str(e) or "device" in str(e)
+        # the two collectives of the reference's scaling_tests.py around the solvers (mpi4py semantics)
+        from new_cg_variants_b200 import cg_variants_mpi4py as m
+        comm = m.GpuComm()
+        part = np.empty(3)
+        comm.Scatter(np.arange(6.0).reshape(world, -1) if rank == 0 else None, part, root=0)
+        ok_scatter = np.array_equal(part, np.arange(6.0)[3 * rank:3 * rank + 3])
+        full = np.empty((world, 3)) if rank == 0 else None
+        comm.Gather(part * 2, full, root=0)
+        ok_scatter = ok_scatter and (rank != 0 or np.array_equal(full.reshape(-1), 2 * np.arange(6.0)))
+        ok_gather = ok_gather and ok_scatter
         q.put((rank, ok_handles, ok_gather, loud))
     finally:
         dist.destroy_process_group()
