@@ -4,7 +4,8 @@
 Run in the build container only (it needs /root/reference, which does not exist on the
 GPU box):
 
-    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py [case ...]      (one process per case;
+                                        the long cases take up to 50 minutes each; naming cases regenerates only those)
 
 What it does
   1. converts every MatrixMarket file of predict_and_recompute/matrices/ to a compressed
@@ -16,8 +17,13 @@ What it does
      figure_gen.py:37 on the cases below, plus ``exact_pcg`` in longdouble
      (figure_gen.py:53-56) to find the departure index k* (SURVEY.md section 8c);
   3. asserts that oracle/cg_oracle.py reproduces every reference history BIT FOR BIT;
-  4. stores the reference histories, k*, and the published table metrics
-     (figures/convergence_table_data.tex) in ``histories.npz`` / ``table.json``;
+  4. measures how sensitive the reference's OWN curves are to the summation order of its inner products
+     (five re-ordered-dot twins of every run) and stores, per case and variant (``cases.json``): k* at
+     1e-10 / 1e-11 / 1e-12, the ensemble agreement at 1e-10 / 1e-11, the P1 window = min(k*11, ens11), the
+     bands of the two figure_gen.py:80-89 summary metrics, the metrics of the live run and of the
+     reference's stored 2019 runs (data/<case>/*.npy); the histories themselves (``histories.npz``) in
+     full, as a prefix, or not at all according to the case's tier (see CASES); and the published table
+     (figures/convergence_table_data.tex -> ``table.json``);
   5. runs the reference's mpi4py solvers on one rank through a 15-line fake ``mpi4py``
      module and stores their final errors in ``mpi_kat.json``.
 """
