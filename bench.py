@@ -228,7 +228,7 @@ def read_traffic(kernel_class):
         ent = t.get(kernel_class)
         if not isinstance(ent, dict):
             return None, "no ncu capture recorded for this kernel"
-        if ent.get("kernel_sources_sha") != _b.kernel_fingerprint():
+        if ent.get("kernel_sources_sha") != _b.kernel_fingerprint(kernel_class):
             return None, "stale: profiles/traffic.json was captured for other kernel sources"
         return ent["dram_bytes_per_launch"], ent.get("source", "profiles/traffic.json")
     except Exception as e:                                    # noqa: BLE001

@@ -64,14 +64,32 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
-def kernel_fingerprint() -> str:
-    """sha256 over the device-code sources only (profiles/traffic.json is stamped with it)."""
+# device-code headers a kernel class (a key of profiles/traffic.json) is compiled from
+_COMMON_CUH = ["cgx_common.cuh", "cgx_kernels.cuh"]
+KERNEL_SOURCES = {
+    "pr_fused": _COMMON_CUH + ["cgx_stencil_tma.cuh", "cgx_stencil_fused.cuh"],
+    "ew_": _COMMON_CUH,
+    "sp_": _COMMON_CUH + ["cgx_stencil_tma.cuh"],
+    "csr_": _COMMON_CUH + ["cgx_csr_bulk.cuh"],
+}
+
+
+def kernel_fingerprint(kernel_class: str | None = None) -> str:
+    """sha256 over the device-code headers `kernel_class` is compiled from (all of them when the
+    class is unknown or None); profiles/traffic.json entries are stamped with it."""
+    files = None
+    if kernel_class:
+        for prefix, lst in KERNEL_SOURCES.items():
+            if kernel_class.startswith(prefix):
+                files = [f for f in lst if os.path.exists(os.path.join(CSRC, f))]
+                break
+    if files is None:
+        files = [f for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")]
     h = hashlib.sha256()
-    for f in sorted(os.listdir(CSRC)):
-        if f.endswith(".cuh"):
-            with open(os.path.join(CSRC, f), "rb") as fh:
-                h.update(f.encode())
-                h.update(fh.read())
+    for f in sorted(files):
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
     return h.hexdigest()[:16]
 
 

@@ -43,10 +43,10 @@ def main():
         lines.append("    stalls (warps per issue-active cycle): " + json.dumps(stalls))
     path = os.path.join(ROOT, "profiles", "traffic.json")
     t = json.load(open(path)) if os.path.exists(path) else {}
-    fp = _b.kernel_fingerprint()
-    t = {k: v for k, v in t.items() if isinstance(v, dict) and v.get("kernel_sources_sha") == fp}   # drop stale / legacy entries
+    t = {k: v for k, v in t.items()
+         if isinstance(v, dict) and v.get("kernel_sources_sha") == _b.kernel_fingerprint(k)}   # drop stale / legacy entries
     t[cls] = {"dram_bytes_per_launch": sum(per) / len(per), "launches": len(per),
-              "kernel_sources_sha": _b.kernel_fingerprint(),
+              "kernel_sources_sha": _b.kernel_fingerprint(cls),
               "source": f"ncu --set full --clock-control none ({os.path.basename(rep)}): dram__bytes_read.sum + dram__bytes_write.sum"}
     json.dump(t, open(path, "w"), indent=1)
     if len(sys.argv) > 3:
