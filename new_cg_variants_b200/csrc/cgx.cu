@@ -62,7 +62,9 @@ const char* const kVecNames[V_COUNT] = {"x", "r", "rt", "p", "s", "st", "w", "wt
 
 static void free_op(cgx_ctx* c) {
   cudaFree(c->d_ptr); cudaFree(c->d_idx); cudaFree(c->d_val); cudaFree(c->d_rowblk); cudaFree(c->d_send_idx); cudaFree(c->d_rowblk_e0);
-  c->d_ptr = c->d_idx = c->d_rowblk = c->d_send_idx = c->d_rowblk_e0 = nullptr; c->d_val = nullptr;
+  cudaFree(c->d_rowblk_b); cudaFree(c->d_rowblk_b_e0);
+  c->d_ptr = c->d_idx = c->d_rowblk = c->d_send_idx = c->d_rowblk_e0 = c->d_rowblk_b = c->d_rowblk_b_e0 = nullptr; c->d_val = nullptr;
+  c->n_rowblk_b = 0;
   c->n_rowblk = 0;
   c->h_ptr.clear();
   c->op_kind = 0;
@@ -111,6 +113,7 @@ extern "C" int cgx_ctx_create(int device, cgx_ctx** out) {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
+  c->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   for (auto& e : c->ev) CU(cudaEventCreate(&e));
@@ -171,13 +174,13 @@ extern "C" int cgx_ctx_destroy(cgx_ctx* c) {
 // ---------------------------------------------------------------------------------------
 // CSR-stream row blocks: consecutive rows, at most kCsrRows of them and kCsrCap non-zeros
 // (a single longer row is a block of its own).
-static void build_row_blocks(const int32_t* ptr, i64 n, std::vector<int>& blk) {
+static void build_row_blocks(const int32_t* ptr, i64 n, std::vector<int>& blk, int max_rows = kCsrRows, int cap = kCsrCap) {
   blk.clear();
   blk.push_back(0);
   i64 r = 0;
   while (r < n) {
     i64 e = r + 1;
-    while (e < n && e - r < kCsrRows && (i64)ptr[e + 1] - ptr[r] <= kCsrCap) ++e;
+    while (e < n && e - r < max_rows && (i64)ptr[e + 1] - ptr[r] <= cap) ++e;
     blk.push_back((int)e);
     r = e;
   }
@@ -190,14 +193,24 @@ static int upload_csr(cgx_ctx* c, i64 n, i64 nnz, const int32_t* indptr, const i
   c->nnz = nnz;
   std::vector<int> blk;
   build_row_blocks(indptr, n, blk);
-  CU(cudaMalloc(&c->d_ptr, sizeof(int) * (n + 1)));
-  CU(cudaMalloc(&c->d_idx, sizeof(int) * std::max<i64>(nnz, 1)));
-  CU(cudaMalloc(&c->d_val, sizeof(double) * std::max<i64>(nnz, 1)));
+  // (kCbPadBytes of slack: the bulk copies of csr_bulk_kernel read whole 16-byte units)
+  CU(cudaMalloc(&c->d_ptr, sizeof(int) * (n + 1) + kCbPadBytes));
+  CU(cudaMalloc(&c->d_idx, sizeof(int) * std::max<i64>(nnz, 1) + kCbPadBytes));
+  CU(cudaMalloc(&c->d_val, sizeof(double) * std::max<i64>(nnz, 1) + kCbPadBytes));
   CU(cudaMalloc(&c->d_rowblk, sizeof(int) * blk.size()));
   CU(cudaMalloc(&c->d_rowblk_e0, sizeof(int) * blk.size()));
   std::vector<int> blk_e0(blk.size());
   for (size_t q = 0; q < blk.size(); ++q) blk_e0[q] = indptr[blk[q]];
   CU(cudaMemcpyAsync(c->d_rowblk_e0, blk_e0.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice, c->stream));
+  std::vector<int> blkb, blkb_e0;
+  build_row_blocks(indptr, n, blkb, kCbRows, kCbCap);
+  blkb_e0.resize(blkb.size());
+  for (size_t q = 0; q < blkb.size(); ++q) blkb_e0[q] = indptr[blkb[q]];
+  CU(cudaMalloc(&c->d_rowblk_b, sizeof(int) * blkb.size()));
+  CU(cudaMalloc(&c->d_rowblk_b_e0, sizeof(int) * blkb.size()));
+  CU(cudaMemcpyAsync(c->d_rowblk_b, blkb.data(), sizeof(int) * blkb.size(), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_rowblk_b_e0, blkb_e0.data(), sizeof(int) * blkb.size(), cudaMemcpyHostToDevice, c->stream));
+  c->n_rowblk_b = (int)blkb.size() - 1;
   CU(cudaMemcpyAsync(c->d_ptr, indptr, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_rowblk, blk.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice, c->stream));
   if (nnz) {
@@ -310,7 +323,7 @@ extern "C" int cgx_set_jacobi_host(cgx_ctx* c, const double* dinv, int64_t n) {
   if (c->op_kind == 0 || n != c->n)
     return fail(CGX_ERR_ARG, "cgx_set_jacobi_host: set the operator first; n must match (%lld vs %lld)",
                 (long long)n, (long long)c->n);
-  if (!c->d_dinv) CU(cudaMalloc(&c->d_dinv, sizeof(double) * n));
+  if (!c->d_dinv) CU(cudaMalloc(&c->d_dinv, sizeof(double) * n + kCbPadBytes));
   CU(cudaMemcpyAsync(c->d_dinv, dinv, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   // constant diagonal (every Poisson stencil): the same products with one HBM stream less
@@ -418,13 +431,14 @@ VecIn vec_in(cgx_ctx* c, const double* v, int ch, const Args& g) {
 
 
 int ctx_occupancy(cgx_ctx* c, const void* fn, int threads, size_t smem) {
-  auto it = c->occ.find({fn, smem});
+  const size_t key = smem | ((size_t)threads << 40);          // (kernels launched with more than one CTA width)
+  auto it = c->occ.find({fn, key});
   if (it != c->occ.end()) return it->second;
   int per_sm = 0;
   if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
   if (per_sm < 1) per_sm = 1;
-  c->occ[{fn, smem}] = per_sm;
+  c->occ[{fn, key}] = per_sm;
   return per_sm;
 }
 
@@ -734,7 +748,7 @@ static int load_problem(cgx_ctx* c, const double* b, const double* x0, const dou
   CU(cudaSetDevice(c->device));
   if (!c->own_problem) {
     c->d_b = c->d_x0 = c->d_xtrue = nullptr;
-    CU(cudaMalloc(&c->d_b, sizeof(double) * n));
+    CU(cudaMalloc(&c->d_b, sizeof(double) * n + kCbPadBytes));
     CU(cudaMalloc(&c->d_x0, sizeof(double) * n));
     CU(cudaMalloc(&c->d_xtrue, sizeof(double) * n));
     c->own_problem = true;
@@ -849,7 +863,7 @@ static int begin_prepare(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
 
   // state vectors (allocated on demand, kept across runs)
   for (int i = 0; i < V_COUNT; ++i)
-    if ((vi.need & (1u << i)) && !c->vec[i]) CU(cudaMalloc(&c->vec[i], sizeof(double) * c->n));
+    if ((vi.need & (1u << i)) && !c->vec[i]) CU(cudaMalloc(&c->vec[i], sizeof(double) * c->n + kCbPadBytes));
   if (c->hist_len != max_iter) {
     cudaFree(c->d_hist); c->d_hist = nullptr;
     CU(cudaMalloc(&c->d_hist, sizeof(double) * CGX_HIST_ROWS * (size_t)max_iter));
@@ -894,7 +908,7 @@ static int begin_prepare(cgx_ctx* c, int variant, int max_iter, unsigned hist_ma
   if (path == CGX_PATH_PERSISTENT)
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < (vi.pipe && vi.recompute ? 2 : 1); ++b)
-        if (!c->d_exp[a][b]) CU(cudaMalloc(&c->d_exp[a][b], sizeof(double) * c->n));
+        if (!c->d_exp[a][b]) CU(cudaMalloc(&c->d_exp[a][b], sizeof(double) * c->n + kCbPadBytes));
   c->path = path;
   c->cg_elide = (variant == CGX_CG || variant == CGX_GV) && path == CGX_PATH_STREAM && c->op_kind == 2 && c->use_tma &&
                 c->tmap_ok[variant == CGX_CG ? V_R : V_W] &&
@@ -1130,6 +1144,10 @@ extern "C" int cgx_set_option(cgx_ctx* c, const char* name, int value) {
   if (!c || !name) return fail(CGX_ERR_ARG, "cgx_set_option: bad arguments");
   if (!strcmp(name, "tma")) { c->no_tma = (value == 0); return CGX_OK; }
   if (!strcmp(name, "csr_stream")) { c->no_csr_stream = (value == 0); return CGX_OK; }
+  if (!strcmp(name, "csr_bulk")) { c->csr_bulk = value; return CGX_OK; }
+  if (!strcmp(name, "csr_bulk_ring")) { c->csr_bulk_ring = std::max(0, std::min(value, (int)kCbMaxRing)); return CGX_OK; }
+  if (!strcmp(name, "csr_bulk_sum")) { c->csr_bulk_sum = value; return CGX_OK; }
+  if (!strcmp(name, "csr_bulk_ctas")) { c->csr_bulk_ctas = std::max(1, std::min(value, 4)); return CGX_OK; }
   if (!strcmp(name, "csr_slab")) { c->no_slab = (value == 0); return CGX_OK; }
   if (!strcmp(name, "cg_elide")) { c->no_elide = (value == 0); return CGX_OK; }
   if (!strcmp(name, "pr_fused")) { c->no_fused = (value == 0); return CGX_OK; }

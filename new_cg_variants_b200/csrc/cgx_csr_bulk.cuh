@@ -1,0 +1,381 @@
+// cgx_csr_bulk.cuh -- CSR pass with the matrix stream staged by bulk async copies (sm_100a).
+//
+// Same work decomposition and the same arithmetic as csr_stream_kernel (cgx_kernels.cuh): a work
+// item is a block of consecutive rows holding at most kCbCap non-zeros (or one chunk of a longer
+// row); every product a_ij * v_j is rounded on its own and a row's products are added in stored
+// order, so the result equals scipy's csr_matvec bit for bit.  What changed is who moves the bytes:
+//
+//   producer warp   one lane issues `cp.async.bulk` (SASS UBLKCP) copies of the item's values,
+//                   columns, row extents and the epilogue operands of its rows (contiguous ranges of
+//                   the SpMV input, r or b, the Jacobi diagonal) into one slot of a ring in shared
+//                   memory; they complete on the slot's transaction mbarrier.  No register is held
+//                   for a byte in flight, so the ring depth -- not the register file -- sets how
+//                   much of the matrix stream a CTA keeps in flight.  The block metadata of 32 items
+//                   is fetched by the 32 lanes at once.
+//   7 gather warps  read the columns from the slot, gather v_j (L1/L2), multiply with the values
+//                   and write the products over the values (in place; second right-hand side into
+//                   an array of its own).  The gathers of item i+1 are issued before the products of
+//                   item i are written.
+//   summing warps   (blockDim.x / 32 - 8 of them, items dealt round robin) lane l adds up the products of
+//                   rows l, l+32, ... of the item in stored order and applies the stage's epilogue, all
+//                   from shared memory, then frees the slot.  A row sum is one dependent chain of
+//                   additions (that is what "stored order" means), so what this stage needs is rows in
+//                   flight: with one summing warp per CTA the kernel was bound by that chain (banded
+//                   model problem, 17 rows of 65 per item: 154 us per pass; csr_stream_kernel 108 us).
+//                   The chunks of a row longer than an item are chained through shared memory.
+//
+// Bulk copies need 16-byte aligned addresses and sizes: a range is widened to the enclosing aligned
+// range (at most 3 elements before and after), which is why the host pads every array the copies
+// read by kCbPadBytes (cgx.cu).
+#pragma once
+#include "cgx_kernels.cuh"
+
+namespace cgx {
+
+constexpr int kCbCap = 1120;                         // non-zeros per work item (5 per gather thread)
+constexpr int kCbRows = 159;                         // rows per block at most
+constexpr int kCbGather = 224;                       // gather threads (7 warps)
+constexpr int kCbProducer = kCbGather;               // first thread of the producer warp
+constexpr int kCbSum0 = kCbGather + 32;              // first thread of the summing warps
+constexpr int kCbMaxSum = 4;
+constexpr int kCbMaxThreads = kCbSum0 + 32 * kCbMaxSum;
+constexpr int kCbUL = kCbCap / kCbGather;
+constexpr int kCbPadBytes = 64;                      // slack behind every array a bulk copy may read
+constexpr int kCbMaxRing = 16;
+static_assert(kCbCap % kCbGather == 0, "one gather batch per thread");
+
+__host__ __device__ constexpr size_t cb_align(size_t b) { return (b + 127) / 128 * 128; }
+__host__ __device__ constexpr size_t cb_val_bytes() { return cb_align((size_t)(kCbCap + 8) * 8); }
+__host__ __device__ constexpr size_t cb_col_bytes() { return cb_align((size_t)(kCbCap + 8) * 4); }
+__host__ __device__ constexpr size_t cb_ptr_bytes() { return cb_align((size_t)(kCbRows + 1 + 7) * 4); }
+__host__ __device__ constexpr size_t cb_op_bytes() { return cb_align((size_t)(kCbRows + 3) * 8); }
+// which epilogue operands a stage reads per row: bit 0 the SpMV input, bit 1 r (b for SP_RESID), bit 2 the Jacobi entry
+__host__ __device__ constexpr int cb_ops(int mode, int pm) {
+  return ((mode == SP_HS || mode == SP_CG || mode == SP_PR) ? 1 : 0) |
+         ((mode == SP_CG || mode == SP_PR || mode == SP_RESID) ? 2 : 0) | ((mode == SP_PR && pm == 1) ? 4 : 0);
+}
+__host__ __device__ constexpr int cb_nops(int ops) { return (ops & 1) + ((ops >> 1) & 1) + ((ops >> 2) & 1); }
+__host__ __device__ constexpr size_t cb_slot_bytes(int nv, int ops) {
+  return cb_val_bytes() * nv + cb_col_bytes() + cb_ptr_bytes() + cb_op_bytes() * cb_nops(ops);
+}
+
+struct CbMeta {
+  int cnt;        // products of the item (-1: no more items)
+  int off;        // index of the first one in the slot's arrays
+  int r0, nrows;  // rows of the block
+  int poff;       // index of row r0's extent in the slot's extent array
+  int pbase;      // extent of a row minus pbase = index of its first product in the slot
+                  // (chunk of a long row: how many such chunks this CTA was handed before this one)
+  int ooff;       // index of row r0 in the slot's operand arrays
+  int flags;      // 1: chunk of a long row, 2: its last chunk
+};
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait that also gives up as soon as ANY thread of the grid has given up (the error word): a role
+// that sees `false` leaves its loop, so a broken pipeline ends within about a second instead of hanging.
+// The bound is kept on the SM's cycle counter and consulted every 256th attempt only: these waits DO block
+// (several per work item), and a %globaltimer read per attempt is far slower than the wake-up itself.
+__device__ __forceinline__ bool cb_wait(uint64_t* bar, uint32_t parity, int* err) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins) {
+    if ((spins & 255u) == 0 && (clock64() - t0 > 3000000000ll || *reinterpret_cast<volatile int*>(err) != 0)) {
+      atomicExch(err, 1);
+      return false;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int MODE, int PM, bool MEURANT, bool GHOST>
+__global__ void __launch_bounds__(kCbMaxThreads, 2)
+csr_bulk_kernel(const CsrOp A, const int* __restrict__ row_blocks, const int* __restrict__ blk_e0, int nblocks, int ring,
+                const Args g, const VecIn in0, const VecIn in1, double* vout) {
+  constexpr int NV = SpTraits<MODE>::NV;
+  constexpr int OPS = cb_ops(MODE, PM);
+  constexpr bool kEpP = OPS & 1, kEpR = (OPS & 2) != 0, kEpD = (OPS & 4) != 0;
+  constexpr size_t kSlot = cb_slot_bytes(NV, OPS);
+  extern __shared__ __align__(128) unsigned char cb_raw[];
+  unsigned char* base = cb_raw + ((128u - (smem_u32(cb_raw) & 127u)) & 127u);
+  __shared__ __align__(8) uint64_t full_bar[kCbMaxRing], prod_bar[kCbMaxRing], empty_bar[kCbMaxRing];
+  __shared__ CbMeta meta[kCbMaxRing];
+  __shared__ double sh_ylong[2];                     // running sum of a long row, handed from chunk to chunk
+  __shared__ int sh_long_done;                       // chunks of long rows summed so far
+  const int tid = threadIdx.x;
+  const int R = ring;
+  const int nsum = ((int)blockDim.x - kCbSum0) / 32;
+  if (tid == 0) {
+    sh_ylong[0] = sh_ylong[1] = 0.0; sh_long_done = 0;
+    for (int s = 0; s < R; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&prod_bar[s], kCbGather / 32); mbar_init(&empty_bar[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto slot_val = [&](int s, int c) { return reinterpret_cast<double*>(base + (size_t)s * kSlot + (size_t)c * cb_val_bytes()); };
+  auto slot_col = [&](int s) { return reinterpret_cast<int*>(base + (size_t)s * kSlot + (size_t)NV * cb_val_bytes()); };
+  auto slot_ptr = [&](int s) { return reinterpret_cast<int*>(base + (size_t)s * kSlot + (size_t)NV * cb_val_bytes() + cb_col_bytes()); };
+  auto slot_op = [&](int s, int q) {
+    return reinterpret_cast<double*>(base + (size_t)s * kSlot + (size_t)NV * cb_val_bytes() + cb_col_bytes() + cb_ptr_bytes() +
+                                     (size_t)q * cb_op_bytes());
+  };
+  double red[kNRed] = {0.0, 0.0, 0.0, 0.0};
+  // timing experiment 2: CTA 0 records, per role, the cycles its first warp spent blocked and its total
+  // (dbg_t[10..15]: producer total / blocked, gather total / blocked, summing total / blocked)
+  const bool stamp = (g.dbg & 2) && blockIdx.x == 0;
+  long long t_blocked = 0;
+  const long long t_begin = stamp ? clock64() : 0;
+  auto wait = [&](uint64_t* bar, uint32_t parity) {
+    if (!stamp) return cb_wait(bar, parity, g.errflag);
+    const long long t0 = clock64();
+    const bool ok = cb_wait(bar, parity, g.errflag);
+    t_blocked += clock64() - t0;
+    return ok;
+  };
+
+  if (tid >= kCbProducer && tid < kCbSum0) {
+    // ------------------------------------------------------------------ producer warp
+    const int lane = tid & 31;
+    uint32_t it = 0;
+    int nlong = 0;
+    bool alive = true;
+    auto acquire = [&]() {                                 // lane 0: the slot of item `it` is free again
+      const int s = it % R;
+      if (alive && it >= (uint32_t)R) alive = wait(&empty_bar[s], ((it / R) - 1) & 1u);
+      return s;
+    };
+    (void)nlong;
+    for (int b0 = blockIdx.x;; b0 += 32 * (int)gridDim.x) {
+      const int blk = b0 + lane * (int)gridDim.x;
+      int r0 = 0, r1 = 0, e0 = 0, e1 = 0;
+      if (blk < nblocks) {
+        r0 = __ldg(row_blocks + blk); r1 = __ldg(row_blocks + blk + 1);
+        e0 = __ldg(blk_e0 + blk); e1 = __ldg(blk_e0 + blk + 1);
+      }
+      bool done = false;
+      for (int l = 0; l < 32; ++l) {
+        const int bl = __shfl_sync(0xffffffffu, blk, l);
+        const int R0 = __shfl_sync(0xffffffffu, r0, l), R1 = __shfl_sync(0xffffffffu, r1, l);
+        const int E0 = __shfl_sync(0xffffffffu, e0, l), E1 = __shfl_sync(0xffffffffu, e1, l);
+        if (bl >= nblocks) { done = true; break; }
+        const int total = E1 - E0;
+        const bool longrow = total > kCbCap;                 // one long row, chunk after chunk
+        for (int cb = 0; cb == 0 || cb < total; cb += kCbCap) {
+          // lane 0 claims the slot, describes the item and announces the bytes; then lanes 0..5 issue one
+          // copy each (a single thread issuing them back to back was the slowest stage of the pipeline)
+          const int s = it % R;
+          const int cnt = longrow ? min(kCbCap, total - cb) : total;
+          const int ea = (E0 + cb) & ~3, na = (E0 + cb - ea + cnt + 3) & ~3;
+          const int pa = R0 & ~3, np = (R0 - pa + (R1 - R0) + 1 + 3) & ~3;
+          const int oa = R0 & ~1, no = (R0 - oa + (R1 - R0) + 1) & ~1;
+          const bool stream = na > 0 && !(g.dbg & 16);       // (timing experiments: 16 = the matrix stream is not copied,
+          const bool small = !longrow && !(g.dbg & 32);      //  32 = nor are the row extents and epilogue operands)
+          if (lane == 0) {
+            acquire();
+            if (alive) {
+              if (!longrow) meta[s] = CbMeta{cnt, E0 - ea, R0, R1 - R0, R0 - pa, ea, R0 - oa, 0};
+              else meta[s] = CbMeta{cnt, E0 + cb - ea, R0, 1, 0, nlong++, 0, 1 | (cb + kCbCap >= total ? 2 : 0)};
+              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)((stream ? na * 12 : 0) + (small ? np * 4 + no * 8 * cb_nops(OPS) : 0)));
+            }
+          }
+          alive = __shfl_sync(0xffffffffu, (int)alive, 0) != 0;
+          if (!alive) break;
+          const int one = (g.dbg & 64) ? 0 : 1;              // (timing experiment 64: lane 0 issues all copies)
+          if (lane == 0 && stream) bulk_g2s(slot_val(s, 0), A.val + ea, (uint32_t)na * 8, &full_bar[s]);
+          if (lane == 1 * one && stream) bulk_g2s(slot_col(s), A.idx + ea, (uint32_t)na * 4, &full_bar[s]);
+          if (lane == 2 * one && small) bulk_g2s(slot_ptr(s), A.ptr + pa, (uint32_t)np * 4, &full_bar[s]);
+          if constexpr (kEpP) { if (lane == 3 * one && small) bulk_g2s(slot_op(s, 0), in0.v + oa, (uint32_t)no * 8, &full_bar[s]); }
+          if constexpr (kEpR) {
+            if (lane == 4 * one && small) bulk_g2s(slot_op(s, kEpP ? 1 : 0), (MODE == SP_RESID ? g.b : g.r) + oa, (uint32_t)no * 8, &full_bar[s]);
+          }
+          if constexpr (kEpD) { if (lane == 5 * one && small) bulk_g2s(slot_op(s, 2), g.dinv + oa, (uint32_t)no * 8, &full_bar[s]); }
+          ++it;
+        }
+        if (!alive) { done = true; break; }
+      }
+      if (done) break;
+    }
+    if (lane == 0) {                                       // end markers: one for every summing warp
+      for (int e = 0; e < nsum && alive; ++e, ++it) {
+        const int s = acquire();
+        if (alive) {
+          meta[s] = CbMeta{-1, 0, 0, 0, 0, 0, 0, 0};
+          mbar_arrive(&full_bar[s]);
+        }
+      }
+      if (stamp) { g.dbg_t[10] = (u64)(clock64() - t_begin); g.dbg_t[11] = (u64)t_blocked; }
+    }
+  } else if (tid < kCbGather) {
+    // ------------------------------------------------------------------ gather warps
+    if constexpr (GHOST) {
+      if (tid == 0 && g.d.world > 1) {
+        for (int c = 0; c < NV; ++c) csr_wait_channel(g, g.hin_ch + c, g.hin_par, g.hin_epoch);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kCbGather) : "memory");
+    }
+    const int nloc = (int)g.n;
+    auto ld0 = [&](int cj) { if constexpr (GHOST) return (cj < nloc ? in0.v : in0.lo - nloc)[cj]; else return in0.v[cj]; };
+    auto ld1 = [&](int cj) { if constexpr (GHOST) return (cj < nloc ? in1.v : in1.lo - nloc)[cj]; else return in1.v[cj]; };
+    struct GSet { double x[NV][kCbUL]; int cnt, off; };
+    auto gissue = [&](uint32_t it, GSet& S) {               // false: end marker
+      const int s = it % R;
+      if (!wait(&full_bar[s], (it / R) & 1u)) { S.cnt = -1; return false; }
+      S.cnt = meta[s].cnt; S.off = meta[s].off;
+      const int* col = slot_col(s) + S.off;
+#pragma unroll
+      for (int u = 0; u < kCbUL; ++u) {
+        const int j = tid + u * kCbGather;
+        const int cj = j < S.cnt ? col[j] : 0;
+        if (g.dbg & 4) { S.x[0][u] = 1.0; if constexpr (NV == 2) S.x[NV - 1][u] = 1.0; continue; }   // (timing experiment: no gathers)
+        S.x[0][u] = ld0(cj);
+        if constexpr (NV == 2) S.x[NV - 1][u] = ld1(cj);
+      }
+      return S.cnt >= 0;
+    };
+    auto gfinish = [&](uint32_t it, const GSet& S) {
+      const int s = it % R;
+      double* v0 = slot_val(s, 0) + S.off;
+      double* v1 = slot_val(s, NV - 1) + S.off;
+#pragma unroll
+      for (int u = 0; u < kCbUL; ++u) {
+        const int j = tid + u * kCbGather;
+        if (j < S.cnt) {
+          const double a = v0[j];
+          v0[j] = mul_(a, S.x[0][u]);
+          if constexpr (NV == 2) v1[j] = mul_(a, S.x[NV - 1][u]);
+        }
+      }
+      if (g.dbg & 128) fence_proxy_async_smem();            // (timing experiment 128: proxy fence in every gather thread)
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&prod_bar[s]);
+    };
+    GSet SA, SB;
+    uint32_t it = 0;
+    bool more = gissue(it, SA);
+    while (more) {
+      const bool more2 = gissue(it + 1, SB);
+      gfinish(it, SA);
+      if (!more2) break;
+      more = gissue(it + 2, SA);
+      gfinish(it + 1, SB);
+      it += 2;
+    }
+    if (stamp && tid == 0) { g.dbg_t[12] = (u64)(clock64() - t_begin); g.dbg_t[13] = (u64)t_blocked; }
+  } else if (tid >= kCbSum0) {
+    // ------------------------------------------------------------------ summing warps
+    const int lane = tid & 31, sw = (tid - kCbSum0) >> 5;
+    auto epilogue = [&](int row, double pv, double rv, double dv, const double (&y)[NV]) {   // the statements of sp_epilogue
+      if constexpr (MODE == SP_PIPE_R) { g.u[row] = y[0]; g.w[row] = y[NV - 1]; }
+      else if constexpr (MODE == SP_PLAIN) vout[row] = y[0];
+      else if constexpr (MODE == SP_RESID) vout[row] = sub_(rv, y[0]);
+      else if constexpr (MODE == SP_HS) { g.s[row] = y[0]; red[0] = fma(pv, y[0], red[0]); }
+      else if constexpr (MODE == SP_CG) { g.w[row] = y[0]; red[0] = fma(rv, pv, red[0]); red[1] = fma(y[0], pv, red[1]); }
+      else if constexpr (MODE == SP_GV) g.t[row] = y[0];
+      else if constexpr (MODE == SP_PR) {
+        g.s[row] = y[0];
+        const double sti = PM == 1 ? mul_(dv, y[0]) : (PM == 2 ? mul_(g.dinv_s, y[0]) : y[0]);
+        red[0] = fma(pv, y[0], red[0]);
+        red[1] = fma(rv, sti, red[1]);
+        red[2] = fma(sti, y[0], red[2]);
+      } else g.u[row] = y[0];                                  // SP_PIPE_N
+      (void)pv; (void)rv; (void)dv;
+    };
+    constexpr int kStride = (int)(cb_val_bytes() / 8);          // second right-hand side's products
+    for (uint32_t it = (uint32_t)sw;; it += (uint32_t)nsum) {
+      const int s = it % R;
+      if (!wait(&full_bar[s], (it / R) & 1u)) break;          // (the metadata; the products follow)
+      const CbMeta m = meta[s];
+      if (m.cnt < 0) break;
+      if (!wait(&prod_bar[s], (it / R) & 1u)) break;
+      const double* prod = slot_val(s, 0);
+      if (!(m.flags & 1)) {
+        const int* rps = slot_ptr(s) + m.poff;
+        for (int t = lane; t < ((g.dbg & 32) ? 0 : m.nrows); t += 32) {
+          const int b0 = rps[t] - m.pbase, b1 = (g.dbg & 8) ? b0 + 1 : rps[t + 1] - m.pbase;   // (timing experiment: no row sums)
+          double y[NV];
+#pragma unroll
+          for (int c = 0; c < NV; ++c) y[c] = 0.0;
+          // products fetched a batch (KB per right-hand side) at a time, one batch ahead of the additions
+          // (two register sets); the additions run in stored order: the chain the hardware must serialise
+          // is theirs alone
+          constexpr int KB = NV == 2 ? 4 : 8;
+          typedef double Batch[NV][KB];
+          auto fetch = [&](Batch& B, int j) {
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+#pragma unroll
+              for (int q = 0; q < KB; ++q) B[c][q] = prod[c * kStride + j + q];
+          };
+          auto addup = [&](const Batch& B) {
+#pragma unroll
+            for (int q = 0; q < KB; ++q)
+#pragma unroll
+              for (int c = 0; c < NV; ++c) y[c] = add_(y[c], B[c][q]);
+          };
+          Batch BA, BB;
+          int j = b0;
+          if (j + KB <= b1) fetch(BA, j);
+          while (j + KB <= b1) {
+            if (j + 2 * KB <= b1) fetch(BB, j + KB);
+            addup(BA);
+            j += KB;
+            if (j + KB > b1) break;
+            if (j + 2 * KB <= b1) fetch(BA, j + KB);
+            addup(BB);
+            j += KB;
+          }
+          for (; j < b1; ++j) {
+#pragma unroll
+            for (int c = 0; c < NV; ++c) y[c] = add_(y[c], prod[c * kStride + j]);
+          }
+          double pv = 0.0, rv = 0.0, dv = 0.0;
+          int q = 0;
+          if constexpr (kEpP) pv = slot_op(s, q++)[m.ooff + t];
+          if constexpr (kEpR) rv = slot_op(s, q++)[m.ooff + t];
+          if constexpr (kEpD) dv = slot_op(s, q++)[m.ooff + t];
+          epilogue(m.r0 + t, pv, rv, dv, y);
+        }
+      } else if (lane == 0) {
+        // chunk of a long row: continue the running sum where the previous chunk (maybe another warp's) left it
+        volatile int* done = &sh_long_done;
+        volatile double* run = sh_ylong;
+        const long long t0 = clock64();
+        bool ok = true;
+        for (uint32_t spins = 1; *done != m.pbase; ++spins) {
+          if ((spins & 255u) == 0 && (clock64() - t0 > 3000000000ll || *reinterpret_cast<volatile int*>(g.errflag) != 0)) {
+            atomicExch(g.errflag, 1); ok = false; break;
+          }
+        }
+        double yl[NV];
+#pragma unroll
+        for (int c = 0; c < NV; ++c) yl[c] = run[c];
+        for (int j = 0; j < m.cnt; ++j) {
+#pragma unroll
+          for (int c = 0; c < NV; ++c) yl[c] = add_(yl[c], prod[c * kStride + m.off + j]);
+        }
+        if (m.flags & 2) {
+          double pv = 0.0, rv = 0.0, dv = 0.0;
+          if constexpr (kEpP) pv = in0.v[m.r0];
+          if constexpr (kEpR) rv = (MODE == SP_RESID) ? g.b[m.r0] : g.r[m.r0];
+          if constexpr (kEpD) dv = g.dinv[m.r0];
+          epilogue(m.r0, pv, rv, dv, yl);
+#pragma unroll
+          for (int c = 0; c < NV; ++c) yl[c] = 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < NV; ++c) run[c] = yl[c];
+        __threadfence_block();
+        if (ok) *done = m.pbase + 1;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+    if (stamp && tid == kCbSum0) { g.dbg_t[14] = (u64)(clock64() - t_begin); g.dbg_t[15] = (u64)t_blocked; }
+  }
+  spmv_close<MODE, MEURANT>(g, red);
+}
+
+}  // namespace cgx

@@ -21,6 +21,7 @@
 #include "../../include/cgx.h"
 #include "cgx_kernels.cuh"
 #include "cgx_stencil_tma.cuh"
+#include "cgx_csr_bulk.cuh"
 #include "cgx_persistent.cuh"
 
 using namespace cgx;
@@ -56,6 +57,7 @@ extern const char* const kVecNames[];
 struct cgx_ctx {
   int device = 0;
   int sm_count = 148;
+  int smem_per_sm = 233472;         // cudaDevAttrMaxSharedMemoryPerMultiprocessor
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   // operator
@@ -72,6 +74,13 @@ struct cgx_ctx {
   int* d_rowblk = nullptr;         // CSR-stream row blocks (cgx_kernels.cuh)
   int* d_rowblk_e0 = nullptr;      // first non-zero of every row block (= indptr[row_blocks[b]])
   int n_rowblk = 0;
+  int* d_rowblk_b = nullptr;       // the same for the bulk-copy CSR kernel (kCbRows / kCbCap: cgx_csr_bulk.cuh)
+  int* d_rowblk_b_e0 = nullptr;
+  int n_rowblk_b = 0;
+  int csr_bulk = 0;                // option "csr_bulk": 1 = csr_bulk_kernel (cgx_csr_bulk.cuh), 0 = csr_stream_kernel
+  int csr_bulk_ring = 0;           // option "csr_bulk_ring": slots per CTA (0 = what csr_bulk_ctas resident CTAs per SM allow)
+  int csr_bulk_sum = 2;            // option "csr_bulk_sum": summing warps per CTA (1 .. kCbMaxSum)
+  int csr_bulk_ctas = 2;           // option "csr_bulk_ctas": resident CTAs per SM the ring is sized for
   i64 n = 0, nnz = 0;
   // preconditioner: pm = 0 identity, 1 Jacobi vector, 2 Jacobi with a constant diagonal
   double* d_dinv = nullptr;

@@ -15,6 +15,23 @@ template <> struct SpInput<SP_PIPE_R> { static constexpr int v0 = V_ST, v1 = V_R
 template <> struct SpInput<SP_PIPE_N> { static constexpr int v0 = V_ST, v1 = -1; };
 
 
+// CSR pass through csr_bulk_kernel: the ring takes what `csr_bulk_ctas` resident CTAs per SM leave of the SM's
+// shared memory (1 KB per CTA is the system's, ~2 KB static: barriers, slot metadata, reduction scratch).
+template <int MODE, int PM, bool MEUR, bool GHOST>
+static void launch_csr_bulk(cgx_ctx* c, const Args& g, const VecIn& in0, const VecIn& in1, double* vout) {
+  constexpr int nv = SpTraits<MODE>::NV;
+  const size_t slot = cb_slot_bytes(nv, cb_ops(MODE, PM));
+  const size_t per_cta = (size_t)c->smem_per_sm / (size_t)c->csr_bulk_ctas - 1024 - 2560;
+  int ring = c->csr_bulk_ring > 0 ? c->csr_bulk_ring : (int)(per_cta / slot);
+  ring = std::max(2, std::min(ring, (int)kCbMaxRing));
+  const size_t sm = (size_t)ring * slot + 128;
+  const int threads = kCbSum0 + 32 * std::max(1, std::min(c->csr_bulk_sum, (int)kCbMaxSum));
+  const int per_sm = ctx_occupancy(c, (const void*)csr_bulk_kernel<MODE, PM, MEUR, GHOST>, threads, sm);
+  const int grid = std::max(1, std::min(c->n_rowblk_b, c->sm_count * per_sm));
+  csr_bulk_kernel<MODE, PM, MEUR, GHOST><<<grid, threads, sm, c->stream>>>(c->csr, c->d_rowblk_b, c->d_rowblk_b_e0, c->n_rowblk_b, ring,
+                                                                            g, in0, in1, vout);
+}
+
 // Fused SpMV pass of stage MODE (vin/vout only for SP_PLAIN / SP_RESID).
 template <int MODE, int PM, bool MEUR>
 static void launch_spmv(cgx_ctx* c, Args g, const double* vin, double* vout) {
@@ -48,8 +65,10 @@ static void launch_spmv(cgx_ctx* c, Args g, const double* vin, double* vout) {
       const double* a1 = v1 >= 0 ? c->vec[v1 < 0 ? 0 : v1] : nullptr;
       const VecIn in0 = vec_in(c, a0, 0, g), in1 = vec_in(c, a1, 1, g);
       if (c->op_kind == 1) {
-        if (!c->no_csr_stream) {
-          const int grid = std::max(1, std::min(c->n_rowblk, c->sm_count * 8));
+        if (!c->no_csr_stream && c->csr_bulk) {
+          if (csr_dist(c)) launch_csr_bulk<MODE, PM, MEUR, true>(c, g, in0, in1, vout);
+          else launch_csr_bulk<MODE, PM, MEUR, false>(c, g, in0, in1, vout);
+        } else if (!c->no_csr_stream) {
           const size_t sm = csr_stream_smem_bytes(nv);
           if (csr_dist(c)) {
             const int per_sm = ctx_occupancy(c, (const void*)csr_stream_kernel<MODE, PM, MEUR, true>, kBlock, sm);

@@ -373,6 +373,60 @@ def test_csr_stream_kernel_equals_row_kernel(name):
                                        atol=1e-13 * res[(0, tag)][1][h][0], err_msg=f"{tag}/{h}")    # (diagonal matrices converge at once)
 
 
+def _ragged_long_rows():
+    """Rows of 0, 1, 1119, 1120 (= one work item of the bulk kernel exactly), 1121 and 3000 non-zeros
+    between short ones; diagonally dominant where a diagonal exists."""
+    import scipy.sparse as sps
+    rng = np.random.default_rng(11)
+    n = 3200
+    lens = rng.integers(1, 9, n)
+    for r, ln in ((5, 1120), (6, 1121), (7, 1119), (900, 3000), (901, 0), (902, 0), (2500, 2241), (n - 1, 1500)):
+        lens[r] = ln
+    rows, cols, vals = [], [], []
+    for r in range(n):
+        c = np.sort(rng.choice(n, size=lens[r], replace=False)) if lens[r] else np.zeros(0, int)
+        rows.append(np.full(lens[r], r)); cols.append(c); vals.append(rng.standard_normal(lens[r]))
+    return sps.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+
+
+@pytest.mark.parametrize("name", ["bcsstk16", "bcsstk18", "nos7", "bcsstm24", "model_48_8_3", "494_bus", "ragged_long"])
+def test_csr_bulk_kernel_equals_stream_kernel(name):
+    """csr_bulk_kernel (matrix stream staged by cp.async.bulk, ring of slots) against csr_stream_kernel
+    and scipy: bit-identical products for several ring depths, solves equal to rounding (the fused
+    dots are summed over other work items)."""
+    if name == "ragged_long":
+        A = _ragged_long_rows()
+        with Session(A) as s:
+            s.set_option("csr_bulk", 1)
+            for ring in (0, 2, 3, 7):
+                s.set_option("csr_bulk_ring", ring)
+                for seed in (1, 2):
+                    v = np.random.default_rng(seed).standard_normal(A.shape[0])
+                    assert np.array_equal(s.spmv(v), A @ v), f"ring {ring}"
+            s.set_option("csr_bulk", 0)
+            assert np.array_equal(s.spmv(v), A @ v)
+        return
+    A = helpers.load_matrix(name)
+    x_true, b, x0 = orc.setup_problem(A)
+    dinv = orc.jacobi_dinv(A)
+    res = {}
+    for flag, ring in ((1, 0), (1, 2), (1, 5), (0, 0)):
+        with Session(A, dinv=dinv) as s:
+            s.set_option("csr_bulk", flag)
+            s.set_option("csr_bulk_ring", ring)
+            for tag in ("hs", "cg", "pr", "pipe_pr", "gv", "m", "pipe_p"):
+                x, hist, _ = s.solve(tag, b, x0, 10, x_true=x_true, path="stream")
+                res[(flag, ring, tag)] = (x, hist)
+            v = np.random.default_rng(3).standard_normal(A.shape[0])
+            assert np.array_equal(s.spmv(v), A @ v)            # scipy's csr_matvec, bit for bit
+    for tag in ("hs", "cg", "pr", "pipe_pr", "gv", "m", "pipe_p"):
+        for h in orc.HISTORIES:
+            assert np.array_equal(res[(1, 0, tag)][1][h], res[(1, 2, tag)][1][h]), f"{tag}/{h}: ring depth changed the bits"
+            assert np.array_equal(res[(1, 0, tag)][1][h], res[(1, 5, tag)][1][h]), f"{tag}/{h}: ring depth changed the bits"
+            np.testing.assert_allclose(res[(1, 0, tag)][1][h][:6], res[(0, 0, tag)][1][h][:6], rtol=1e-9,
+                                       atol=1e-13 * res[(0, 0, tag)][1][h][0], err_msg=f"{tag}/{h}")
+
+
 # ------------------------------------------------ callers either side of the path (SURVEY 8f)
 def test_figure_gen_style_driver_end_to_end(tmp_path):
     """experiments.test_matrix / parse_convergence_data (figure_gen.py:21-124 restated) on the

@@ -34,35 +34,42 @@ def main():
     ap.add_argument("--n", type=int, default=650000)
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--iters", type=int, default=500)
+    ap.add_argument("--variants", default="hs,cg,pr,gv,pipe_pr")
+    ap.add_argument("--sweep", default="", help="';'-separated option sets, each 'name=value,name=value' (cgx_set_option); "
+                    "one JSON object per set, e.g. 'csr_bulk=0;csr_bulk=1,csr_bulk_ctas=3'")
     args = ap.parse_args()
     t0 = time.time()
     A = model_matrix(args.n, args.k)
     n, nnz = A.shape[0], A.nnz
     x_true = np.ones(n)
     b, x0 = A @ x_true, np.zeros(n)
-    out = {"workload": f"banded model problem n={n} k={args.k} nnz={nnz} unpreconditioned, {args.iters} iterations",
-           "build_s": round(time.time() - t0, 1), "variants": {}}
+    workload = f"banded model problem n={n} k={args.k} nnz={nnz} unpreconditioned, {args.iters} iterations"
+    sets = [dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in st.split(",") if kv) for st in args.sweep.split(";")]
     with Session(A) as s:
         s.load_problem(b, x0, None)
-        for v in ("hs", "cg", "pr", "gv", "pipe_pr"):
-            best = min(s.run(v, args.iters + 1, histories=(), path="stream")["loop_ms"] for _ in range(3))
-            x, _ = s.fetch(want_hist=False)
-            s.set_profile(True)
-            s.run(v, args.iters + 1, histories=(), path="stream")
-            prof = s.get_profile()
-            s.set_profile(False)
-            row = {"us_per_iteration": round(1e3 * best / args.iters, 2),
-                   "rel_error": float(np.linalg.norm(x - x_true) / np.sqrt(n)), "kernels": {}}
-            for kname, (ms, cnt) in prof.items():
-                us = 1e3 * ms / cnt
-                row["kernels"][kname] = {"us": round(us, 2)}
-                if kname in SP_WORDS:
-                    bytes_ = 12.0 * nnz + 4.0 * (n + 1) + 8.0 * n * SP_WORDS[kname]
-                    row["kernels"][kname]["GBps"] = round(bytes_ / (us * 1e-6) / 1e9)
-                    row["kernels"][kname]["algorithmic_bytes"] = bytes_
-            out["variants"][v] = row
-            print(v, row, file=sys.stderr, flush=True)
-    print(json.dumps(out))
+        for opts in sets:
+            for name, value in opts.items():
+                s.set_option(name, value)
+            out = {"workload": workload, "options": opts, "build_s": round(time.time() - t0, 1), "variants": {}}
+            for v in args.variants.split(","):
+                best = min(s.run(v, args.iters + 1, histories=(), path="stream")["loop_ms"] for _ in range(3))
+                x, _ = s.fetch(want_hist=False)
+                s.set_profile(True)
+                s.run(v, args.iters + 1, histories=(), path="stream")
+                prof = s.get_profile()
+                s.set_profile(False)
+                row = {"us_per_iteration": round(1e3 * best / args.iters, 2),
+                       "rel_error": float(np.linalg.norm(x - x_true) / np.sqrt(n)), "kernels": {}}
+                for kname, (ms, cnt) in prof.items():
+                    us = 1e3 * ms / cnt
+                    row["kernels"][kname] = {"us": round(us, 2)}
+                    if kname in SP_WORDS:
+                        bytes_ = 12.0 * nnz + 4.0 * (n + 1) + 8.0 * n * SP_WORDS[kname]
+                        row["kernels"][kname]["GBps"] = round(bytes_ / (us * 1e-6) / 1e9)
+                        row["kernels"][kname]["algorithmic_bytes"] = bytes_
+                out["variants"][v] = row
+                print(opts, v, row, file=sys.stderr, flush=True)
+            print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":
