@@ -5,24 +5,34 @@
 // row); every product a_ij * v_j is rounded on its own and a row's products are added in stored
 // order, so the result equals scipy's csr_matvec bit for bit.  What changed is who moves the bytes:
 //
-//   producer warp   one lane issues `cp.async.bulk` (SASS UBLKCP) copies of the item's values,
-//                   columns, row extents and the epilogue operands of its rows (contiguous ranges of
-//                   the SpMV input, r or b, the Jacobi diagonal) into one slot of a ring in shared
-//                   memory; they complete on the slot's transaction mbarrier.  No register is held
-//                   for a byte in flight, so the ring depth -- not the register file -- sets how
-//                   much of the matrix stream a CTA keeps in flight.  The block metadata of 32 items
-//                   is fetched by the 32 lanes at once.
-//   7 gather warps  read the columns from the slot, gather v_j (L1/L2), multiply with the values
+//   producer warp   issues `cp.async.bulk` (SASS UBLKCP) copies of the item's values, columns, row
+//                   extents and the epilogue operands of its rows (contiguous ranges of the SpMV
+//                   input, r or b, the Jacobi diagonal) into one slot of a ring in shared memory; they
+//                   complete on the slot's transaction mbarrier.  No register is held for a byte in
+//                   flight, so the ring depth -- not the register file -- sets how much of the matrix
+//                   stream a CTA keeps in flight.  Lane l owns the l-th block of a batch of 32 (metadata
+//                   in its own registers, slot and phase computed by all lanes at once) and issues that
+//                   block's copies when its turn comes: no shuffles, no divisions per item.
+//   14 gather warps read the columns from the slot, gather v_j (L1/L2), multiply with the values
 //                   and write the products over the values (in place; second right-hand side into
-//                   an array of its own).  The gathers of item i+1 are issued before the products of
-//                   item i are written.
+//                   an array of its own).  The gathers of items i+1 and i+2 are issued before the
+//                   products of item i are written.
 //   summing warps   (blockDim.x / 32 - 8 of them, items dealt round robin) lane l adds up the products of
 //                   rows l, l+32, ... of the item in stored order and applies the stage's epilogue, all
 //                   from shared memory, then frees the slot.  A row sum is one dependent chain of
-//                   additions (that is what "stored order" means), so what this stage needs is rows in
-//                   flight: with one summing warp per CTA the kernel was bound by that chain (banded
-//                   model problem, 17 rows of 65 per item: 154 us per pass; csr_stream_kernel 108 us).
-//                   The chunks of a row longer than an item are chained through shared memory.
+//                   additions (8.2 cycles each on B200: tools/dadd_probe.cu), so what this stage needs is
+//                   rows in flight.  The chunks of a row longer than an item are chained through shared
+//                   memory.
+//
+// Measured on the way (banded model problem, 65 non-zeros per row; tools/csr_bench.py, csr_stamp_probe.py):
+// the per-item cost of the CONTROL code is what bounds such a pipeline, not memory.  A single producer thread
+// that recomputed slot = it % ring and shuffled the block metadata per item was busy 95 % of the time at
+// ~1000-1650 cycles per 1120-element item (even with every copy, gather and sum switched off); a variant in
+// which every warp was a complete pipeline of its own (352-element items) spent ~400 instructions per item
+// per warp and was bound by instruction issue (163 us per pass against 108 us of csr_stream_kernel).
+// cp.async.bulk itself sustains 7.0 TB/s from 1 KB copies upward once 64 KB per SM are in flight
+// (tools/bulk_probe.cu).  Hence: items as large as the ring allows and a producer without per-item
+// arithmetic.
 //
 // Bulk copies need 16-byte aligned addresses and sizes: a range is widened to the enclosing aligned
 // range (at most 3 elements before and after), which is why the host pads every array the copies
@@ -32,9 +42,9 @@
 
 namespace cgx {
 
-constexpr int kCbCap = 1120;                         // non-zeros per work item (5 per gather thread)
+constexpr int kCbCap = 1792;                         // non-zeros per work item (4 per gather thread)
 constexpr int kCbRows = 159;                         // rows per block at most
-constexpr int kCbGather = 224;                       // gather threads (7 warps)
+constexpr int kCbGather = 448;                       // gather threads (14 warps)
 constexpr int kCbProducer = kCbGather;               // first thread of the producer warp
 constexpr int kCbSum0 = kCbGather + 32;              // first thread of the summing warps
 constexpr int kCbMaxSum = 4;
@@ -92,7 +102,7 @@ __device__ __forceinline__ bool cb_wait(uint64_t* bar, uint32_t parity, int* err
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int MODE, int PM, bool MEURANT, bool GHOST>
-__global__ void __launch_bounds__(kCbMaxThreads, 2)
+__global__ void __launch_bounds__(kCbMaxThreads, 1)
 csr_bulk_kernel(const CsrOp A, const int* __restrict__ row_blocks, const int* __restrict__ blk_e0, int nblocks, int ring,
                 const Args g, const VecIn in0, const VecIn in1, double* vout) {
   constexpr int NV = SpTraits<MODE>::NV;
@@ -138,68 +148,80 @@ csr_bulk_kernel(const CsrOp A, const int* __restrict__ row_blocks, const int* __
   if (tid >= kCbProducer && tid < kCbSum0) {
     // ------------------------------------------------------------------ producer warp
     const int lane = tid & 31;
-    uint32_t it = 0;
-    int nlong = 0;
+    const int G = (int)gridDim.x;
+    uint32_t it = 0;                                       // items handed out so far (uniform)
+    int nlong = 0;                                         // chunks of long rows handed out so far (uniform)
     bool alive = true;
-    auto acquire = [&]() {                                 // lane 0: the slot of item `it` is free again
-      const int s = it % R;
-      if (alive && it >= (uint32_t)R) alive = wait(&empty_bar[s], ((it / R) - 1) & 1u);
-      return s;
+    // the copies of one item into slot s (executed by ONE lane)
+    auto copy_block = [&](int s, int R0, int R1, int E0, int total) {
+      const int ea = E0 & ~3, na = (E0 - ea + total + 3) & ~3;
+      const int pa = R0 & ~3, np = (R0 - pa + (R1 - R0) + 1 + 3) & ~3;
+      const int oa = R0 & ~1, no = (R0 - oa + (R1 - R0) + 1) & ~1;
+      const bool stream = na > 0 && !(g.dbg & 16);       // (timing experiment 16: the matrix stream is not copied)
+      meta[s] = CbMeta{total, E0 - ea, R0, R1 - R0, R0 - pa, ea, R0 - oa, 0};
+      uint64_t* bar = &full_bar[s];
+      mbar_arrive_expect_tx(bar, (uint32_t)((stream ? na * 12 : 0) + np * 4 + no * 8 * cb_nops(OPS)));
+      if (stream) {
+        bulk_g2s(slot_val(s, 0), A.val + ea, (uint32_t)na * 8, bar);
+        bulk_g2s(slot_col(s), A.idx + ea, (uint32_t)na * 4, bar);
+      }
+      bulk_g2s(slot_ptr(s), A.ptr + pa, (uint32_t)np * 4, bar);
+      int q = 0;
+      if constexpr (kEpP) bulk_g2s(slot_op(s, q++), in0.v + oa, (uint32_t)no * 8, bar);
+      if constexpr (kEpR) bulk_g2s(slot_op(s, q++), (MODE == SP_RESID ? g.b : g.r) + oa, (uint32_t)no * 8, bar);
+      if constexpr (kEpD) bulk_g2s(slot_op(s, q++), g.dinv + oa, (uint32_t)no * 8, bar);
     };
-    (void)nlong;
-    for (int b0 = blockIdx.x;; b0 += 32 * (int)gridDim.x) {
-      const int blk = b0 + lane * (int)gridDim.x;
+    for (int b0 = blockIdx.x; b0 < nblocks && alive; b0 += 32 * G) {
+      const int blk = b0 + lane * G;
       int r0 = 0, r1 = 0, e0 = 0, e1 = 0;
       if (blk < nblocks) {
         r0 = __ldg(row_blocks + blk); r1 = __ldg(row_blocks + blk + 1);
         e0 = __ldg(blk_e0 + blk); e1 = __ldg(blk_e0 + blk + 1);
       }
-      bool done = false;
-      for (int l = 0; l < 32; ++l) {
-        const int bl = __shfl_sync(0xffffffffu, blk, l);
-        const int R0 = __shfl_sync(0xffffffffu, r0, l), R1 = __shfl_sync(0xffffffffu, r1, l);
-        const int E0 = __shfl_sync(0xffffffffu, e0, l), E1 = __shfl_sync(0xffffffffu, e1, l);
-        if (bl >= nblocks) { done = true; break; }
-        const int total = E1 - E0;
-        const bool longrow = total > kCbCap;                 // one long row, chunk after chunk
-        for (int cb = 0; cb == 0 || cb < total; cb += kCbCap) {
-          // lane 0 claims the slot, describes the item and announces the bytes; then lanes 0..5 issue one
-          // copy each (a single thread issuing them back to back was the slowest stage of the pipeline)
-          const int s = it % R;
-          const int cnt = longrow ? min(kCbCap, total - cb) : total;
-          const int ea = (E0 + cb) & ~3, na = (E0 + cb - ea + cnt + 3) & ~3;
-          const int pa = R0 & ~3, np = (R0 - pa + (R1 - R0) + 1 + 3) & ~3;
-          const int oa = R0 & ~1, no = (R0 - oa + (R1 - R0) + 1) & ~1;
-          const bool stream = na > 0 && !(g.dbg & 16);       // (timing experiments: 16 = the matrix stream is not copied,
-          const bool small = !longrow && !(g.dbg & 32);      //  32 = nor are the row extents and epilogue operands)
+      const int nb = min(32, (nblocks - b0 + G - 1) / G);  // blocks of this batch
+      if (!__any_sync(0xffffffffu, e1 - e0 > kCbCap)) {
+        // every block is one item: lane l's item number, slot and phase follow from l alone
+        const uint32_t my = it + (uint32_t)lane, q = my / (uint32_t)R;
+        const int s = (int)(my - q * (uint32_t)R);
+        for (int l = 0; l < nb; ++l) {
+          if (lane == l) {
+            if (my >= (uint32_t)R) alive = wait(&empty_bar[s], (q - 1u) & 1u);
+            if (alive) copy_block(s, r0, r1, e0, e1 - e0);
+          }
+          __syncwarp();                                    // one lane after the other, in item order
+        }
+        it += (uint32_t)nb;
+        alive = __all_sync(0xffffffffu, alive);
+      } else {
+        // a batch with a row longer than an item (rare): one block after the other, metadata by shuffle
+        for (int l = 0; l < nb && alive; ++l) {
+          const int R0 = __shfl_sync(0xffffffffu, r0, l), R1 = __shfl_sync(0xffffffffu, r1, l);
+          const int E0 = __shfl_sync(0xffffffffu, e0, l), E1 = __shfl_sync(0xffffffffu, e1, l);
+          const int total = E1 - E0;
           if (lane == 0) {
-            acquire();
-            if (alive) {
-              if (!longrow) meta[s] = CbMeta{cnt, E0 - ea, R0, R1 - R0, R0 - pa, ea, R0 - oa, 0};
-              else meta[s] = CbMeta{cnt, E0 + cb - ea, R0, 1, 0, nlong++, 0, 1 | (cb + kCbCap >= total ? 2 : 0)};
-              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)((stream ? na * 12 : 0) + (small ? np * 4 + no * 8 * cb_nops(OPS) : 0)));
+            for (int cb = 0; (cb == 0 || cb < total) && alive; cb += kCbCap, ++it) {
+              const int s = (int)(it % (uint32_t)R);
+              if (it >= (uint32_t)R) alive = wait(&empty_bar[s], ((it / (uint32_t)R) - 1u) & 1u);
+              if (!alive) break;
+              if (total <= kCbCap) { copy_block(s, R0, R1, E0, total); continue; }
+              const int cnt = min(kCbCap, total - cb);
+              const int ea = (E0 + cb) & ~3, na = (E0 + cb - ea + cnt + 3) & ~3;
+              meta[s] = CbMeta{cnt, E0 + cb - ea, R0, 1, 0, nlong++, 0, 1 | (cb + kCbCap >= total ? 2 : 0)};
+              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)na * 12);
+              bulk_g2s(slot_val(s, 0), A.val + ea, (uint32_t)na * 8, &full_bar[s]);
+              bulk_g2s(slot_col(s), A.idx + ea, (uint32_t)na * 4, &full_bar[s]);
             }
           }
+          it = __shfl_sync(0xffffffffu, it, 0);
+          nlong = __shfl_sync(0xffffffffu, nlong, 0);
           alive = __shfl_sync(0xffffffffu, (int)alive, 0) != 0;
-          if (!alive) break;
-          const int one = (g.dbg & 64) ? 0 : 1;              // (timing experiment 64: lane 0 issues all copies)
-          if (lane == 0 && stream) bulk_g2s(slot_val(s, 0), A.val + ea, (uint32_t)na * 8, &full_bar[s]);
-          if (lane == 1 * one && stream) bulk_g2s(slot_col(s), A.idx + ea, (uint32_t)na * 4, &full_bar[s]);
-          if (lane == 2 * one && small) bulk_g2s(slot_ptr(s), A.ptr + pa, (uint32_t)np * 4, &full_bar[s]);
-          if constexpr (kEpP) { if (lane == 3 * one && small) bulk_g2s(slot_op(s, 0), in0.v + oa, (uint32_t)no * 8, &full_bar[s]); }
-          if constexpr (kEpR) {
-            if (lane == 4 * one && small) bulk_g2s(slot_op(s, kEpP ? 1 : 0), (MODE == SP_RESID ? g.b : g.r) + oa, (uint32_t)no * 8, &full_bar[s]);
-          }
-          if constexpr (kEpD) { if (lane == 5 * one && small) bulk_g2s(slot_op(s, 2), g.dinv + oa, (uint32_t)no * 8, &full_bar[s]); }
-          ++it;
         }
-        if (!alive) { done = true; break; }
       }
-      if (done) break;
     }
     if (lane == 0) {                                       // end markers: one for every summing warp
       for (int e = 0; e < nsum && alive; ++e, ++it) {
-        const int s = acquire();
+        const int s = (int)(it % (uint32_t)R);
+        if (it >= (uint32_t)R) alive = wait(&empty_bar[s], ((it / (uint32_t)R) - 1u) & 1u);
         if (alive) {
           meta[s] = CbMeta{-1, 0, 0, 0, 0, 0, 0, 0};
           mbar_arrive(&full_bar[s]);
@@ -219,9 +241,11 @@ csr_bulk_kernel(const CsrOp A, const int* __restrict__ row_blocks, const int* __
     auto ld0 = [&](int cj) { if constexpr (GHOST) return (cj < nloc ? in0.v : in0.lo - nloc)[cj]; else return in0.v[cj]; };
     auto ld1 = [&](int cj) { if constexpr (GHOST) return (cj < nloc ? in1.v : in1.lo - nloc)[cj]; else return in1.v[cj]; };
     struct GSet { double x[NV][kCbUL]; int cnt, off; };
-    auto gissue = [&](uint32_t it, GSet& S) {               // false: end marker
-      const int s = it % R;
-      if (!wait(&full_bar[s], (it / R) & 1u)) { S.cnt = -1; return false; }
+    struct Pos { int s; uint32_t par; };                   // slot and phase parity of an item
+    auto next = [&](Pos p) { if (++p.s == R) { p.s = 0; p.par ^= 1u; } return p; };
+    auto gissue = [&](Pos p, GSet& S) {                     // false: end marker
+      const int s = p.s;
+      if (!wait(&full_bar[s], p.par)) { S.cnt = -1; return false; }
       S.cnt = meta[s].cnt; S.off = meta[s].off;
       const int* col = slot_col(s) + S.off;
 #pragma unroll
@@ -234,8 +258,8 @@ csr_bulk_kernel(const CsrOp A, const int* __restrict__ row_blocks, const int* __
       }
       return S.cnt >= 0;
     };
-    auto gfinish = [&](uint32_t it, const GSet& S) {
-      const int s = it % R;
+    auto gfinish = [&](Pos p, const GSet& S) {
+      const int s = p.s;
       double* v0 = slot_val(s, 0) + S.off;
       double* v1 = slot_val(s, NV - 1) + S.off;
 #pragma unroll
@@ -251,16 +275,25 @@ csr_bulk_kernel(const CsrOp A, const int* __restrict__ row_blocks, const int* __
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(&prod_bar[s]);
     };
-    GSet SA, SB;
-    uint32_t it = 0;
-    bool more = gissue(it, SA);
-    while (more) {
-      const bool more2 = gissue(it + 1, SB);
-      gfinish(it, SA);
-      if (!more2) break;
-      more = gissue(it + 2, SA);
-      gfinish(it + 1, SB);
-      it += 2;
+    // three items deep: the gathers of items k+1 and k+2 are in flight while the products of item k are
+    // written (an L2 round trip under load is longer than one item's worth of work); needs ring >= 3
+    GSet S0, S1, S2;
+    Pos p0{0, 0u};
+    bool m0 = gissue(p0, S0);
+    Pos p1 = next(p0);
+    bool m1 = m0 && gissue(p1, S1);
+    while (m0) {
+      Pos p2 = next(p1);
+      const bool m2 = m1 && gissue(p2, S2);
+      gfinish(p0, S0);
+      if (!m1) break;
+      p0 = next(p2);
+      m0 = m2 && gissue(p0, S0);
+      gfinish(p1, S1);
+      if (!m2) break;
+      p1 = next(p0);
+      m1 = m0 && gissue(p1, S1);
+      gfinish(p2, S2);
     }
     if (stamp && tid == 0) { g.dbg_t[12] = (u64)(clock64() - t_begin); g.dbg_t[13] = (u64)t_blocked; }
   } else if (tid >= kCbSum0) {
@@ -283,17 +316,19 @@ csr_bulk_kernel(const CsrOp A, const int* __restrict__ row_blocks, const int* __
       (void)pv; (void)rv; (void)dv;
     };
     constexpr int kStride = (int)(cb_val_bytes() / 8);          // second right-hand side's products
-    for (uint32_t it = (uint32_t)sw;; it += (uint32_t)nsum) {
-      const int s = it % R;
-      if (!wait(&full_bar[s], (it / R) & 1u)) break;          // (the metadata; the products follow)
+    int s = sw % R;
+    uint32_t par = (uint32_t)(sw / R) & 1u;
+    for (;; s += nsum) {
+      while (s >= R) { s -= R; par ^= 1u; }
+      if (!wait(&full_bar[s], par)) break;          // (the metadata; the products follow)
       const CbMeta m = meta[s];
       if (m.cnt < 0) break;
-      if (!wait(&prod_bar[s], (it / R) & 1u)) break;
+      if (!wait(&prod_bar[s], par)) break;
       const double* prod = slot_val(s, 0);
       if (!(m.flags & 1)) {
         const int* rps = slot_ptr(s) + m.poff;
         for (int t = lane; t < ((g.dbg & 32) ? 0 : m.nrows); t += 32) {
-          const int b0 = rps[t] - m.pbase, b1 = (g.dbg & 8) ? b0 + 1 : rps[t + 1] - m.pbase;   // (timing experiment: no row sums)
+          const int b0 = rps[t] - m.pbase, b1 = (g.dbg & 8) ? b0 + 1 : rps[t + 1] - m.pbase;   // (timing experiment 8: no row sums)
           double y[NV];
 #pragma unroll
           for (int c = 0; c < NV; ++c) y[c] = 0.0;

@@ -77,10 +77,10 @@ struct cgx_ctx {
   int* d_rowblk_b = nullptr;       // the same for the bulk-copy CSR kernel (kCbRows / kCbCap: cgx_csr_bulk.cuh)
   int* d_rowblk_b_e0 = nullptr;
   int n_rowblk_b = 0;
-  int csr_bulk = 0;                // option "csr_bulk": 1 = csr_bulk_kernel (cgx_csr_bulk.cuh), 0 = csr_stream_kernel
+  int csr_bulk = 1;                // option "csr_bulk": 0 = csr_stream_kernel, 1 = csr_bulk_kernel (cgx_csr_bulk.cuh) for one right-hand side, 2 = for both
   int csr_bulk_ring = 0;           // option "csr_bulk_ring": slots per CTA (0 = what csr_bulk_ctas resident CTAs per SM allow)
-  int csr_bulk_sum = 2;            // option "csr_bulk_sum": summing warps per CTA (1 .. kCbMaxSum)
-  int csr_bulk_ctas = 2;           // option "csr_bulk_ctas": resident CTAs per SM the ring is sized for
+  int csr_bulk_sum = 4;            // option "csr_bulk_sum": summing warps per CTA (1 .. kCbMaxSum)
+  int csr_bulk_ctas = 1;           // option "csr_bulk_ctas": resident CTAs per SM the ring is sized for
   i64 n = 0, nnz = 0;
   // preconditioner: pm = 0 identity, 1 Jacobi vector, 2 Jacobi with a constant diagonal
   double* d_dinv = nullptr;

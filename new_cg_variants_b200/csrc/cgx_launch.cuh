@@ -23,9 +23,10 @@ static void launch_csr_bulk(cgx_ctx* c, const Args& g, const VecIn& in0, const V
   const size_t slot = cb_slot_bytes(nv, cb_ops(MODE, PM));
   const size_t per_cta = (size_t)c->smem_per_sm / (size_t)c->csr_bulk_ctas - 1024 - 2560;
   int ring = c->csr_bulk_ring > 0 ? c->csr_bulk_ring : (int)(per_cta / slot);
-  ring = std::max(2, std::min(ring, (int)kCbMaxRing));
+  ring = std::max(3, std::min(ring, (int)kCbMaxRing));       // (the gather warps work three items deep)
   const size_t sm = (size_t)ring * slot + 128;
-  const int threads = kCbSum0 + 32 * std::max(1, std::min(c->csr_bulk_sum, (int)kCbMaxSum));
+  // (summing warps <= ring: a warp may only wait for the NEXT phase of a slot's barriers)
+  const int threads = kCbSum0 + 32 * std::max(1, std::min(std::min(c->csr_bulk_sum, (int)kCbMaxSum), ring));
   const int per_sm = ctx_occupancy(c, (const void*)csr_bulk_kernel<MODE, PM, MEUR, GHOST>, threads, sm);
   const int grid = std::max(1, std::min(c->n_rowblk_b, c->sm_count * per_sm));
   csr_bulk_kernel<MODE, PM, MEUR, GHOST><<<grid, threads, sm, c->stream>>>(c->csr, c->d_rowblk_b, c->d_rowblk_b_e0, c->n_rowblk_b, ring,
@@ -65,7 +66,8 @@ static void launch_spmv(cgx_ctx* c, Args g, const double* vin, double* vout) {
       const double* a1 = v1 >= 0 ? c->vec[v1 < 0 ? 0 : v1] : nullptr;
       const VecIn in0 = vec_in(c, a0, 0, g), in1 = vec_in(c, a1, 1, g);
       if (c->op_kind == 1) {
-        if (!c->no_csr_stream && c->csr_bulk) {
+        // (the two-right-hand-side pass stays on csr_stream_kernel unless csr_bulk = 2: measured 155 vs 121 us)
+        if (!c->no_csr_stream && (c->csr_bulk >= 2 || (c->csr_bulk == 1 && nv == 1))) {
           if (csr_dist(c)) launch_csr_bulk<MODE, PM, MEUR, true>(c, g, in0, in1, vout);
           else launch_csr_bulk<MODE, PM, MEUR, false>(c, g, in0, in1, vout);
         } else if (!c->no_csr_stream) {
