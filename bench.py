@@ -602,7 +602,7 @@ def run_banded(args, rank, world, local_rank):
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"banded model problem (ex2b.c:86-97) n={n} k={args.banded_k} nnz={nnz}, {its} iterations",
                            "l2": "matrix + vectors = %.2f GB per iteration >> 126 MB L2" % ((12.0 * nnz + 8.0 * n * 12) / 1e9)},
-                "roofline": {"bound": "hbm", "kernel": "csr_stream<%s>" % spk, "achieved": kk["GBps"], "peak": peak, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": ("csr_stream<%s>" if spk == "sp_pipe_r" else "csr_bulk<%s>") % spk, "achieved": kk["GBps"], "peak": peak, "unit": "GB/s",
                              "frac": kk["frac"], "traffic": traffic if world == 1 else None, "traffic_source": traffic_note,
                              "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": kk["algorithmic_bytes"], "avg_launch_ms": kk["us"] / 1e3},

@@ -70,7 +70,8 @@ KERNEL_SOURCES = {
     "pr_fused": _COMMON_CUH + ["cgx_stencil_tma.cuh", "cgx_stencil_fused.cuh"],
     "ew_": _COMMON_CUH,
     "sp_": _COMMON_CUH + ["cgx_stencil_tma.cuh"],
-    "csr_": _COMMON_CUH + ["cgx_csr_bulk.cuh"],
+    "csr_sp_pipe_r": _COMMON_CUH,                       # two right-hand sides: csr_stream_kernel (cgx_kernels.cuh)
+    "csr_": _COMMON_CUH + ["cgx_csr_bulk.cuh"],         # one right-hand side: csr_bulk_kernel
 }
 
 

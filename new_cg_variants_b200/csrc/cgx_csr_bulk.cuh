@@ -17,7 +17,7 @@
 //                   and write the products over the values (in place; second right-hand side into
 //                   an array of its own).  The gathers of items i+1 and i+2 are issued before the
 //                   products of item i are written.
-//   summing warps   (blockDim.x / 32 - 8 of them, items dealt round robin) lane l adds up the products of
+//   summing warps   (blockDim.x / 32 - 15 of them, items dealt round robin) lane l adds up the products of
 //                   rows l, l+32, ... of the item in stored order and applies the stage's epilogue, all
 //                   from shared memory, then frees the slot.  A row sum is one dependent chain of
 //                   additions (8.2 cycles each on B200: tools/dadd_probe.cu), so what this stage needs is
@@ -271,7 +271,10 @@ csr_bulk_kernel(const CsrOp A, const int* __restrict__ row_blocks, const int* __
           if constexpr (NV == 2) v1[j] = mul_(a, S.x[NV - 1][u]);
         }
       }
-      if (g.dbg & 128) fence_proxy_async_smem();            // (timing experiment 128: proxy fence in every gather thread)
+      // (the proxy fence that orders the generic-proxy accesses to this slot before the producer's next
+      // async-proxy copy into it is executed by the summing warp, after it has observed these writes
+      // through prod_bar; timing experiment 128 adds one in every gather thread: no measurable difference)
+      if (g.dbg & 128) fence_proxy_async_smem();
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(&prod_bar[s]);
     };

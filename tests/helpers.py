@@ -13,7 +13,7 @@ section "Parity"):
       end where a further summation order has an even chance of having crossed the line: the
       measured first-deviation index kd of every device run is logged next to all four numbers
       (gpurun_out/parity_kd.jsonl -> profiles/parity_r02.md);
-  P2  attainable accuracy: log10(min_k rel. A-norm error) within log10(2) of the band the
+  P2  attainable accuracy: log10(min_k rel. A-norm error) not worse than log10(2) above the band the
       reference itself spans under those summation orders, widened by the band's width;
   P3  iterations to rel. A-norm error <= 1e-5 within max(1, 1 %) of that band, widened by
       the band's width.
@@ -140,7 +140,13 @@ def check_metrics(dev, band, label=""):
     floor = math.log10(2.0 ** -52)
     acc, lo, hi = max(acc, floor), max(lo, floor), max(hi, floor)
     width = hi - lo
-    assert lo - width - math.log10(2) <= acc <= hi + width + math.log10(2), \
+    # Worse than the band by more than x2 (+ the band's own width) fails.  BETTER than the band is allowed
+    # ("higher-accuracy device dots are allowed and help"): min_k of a quantity that
+    # fluctuates around the rounding floor dips below the five-order band for some summation orders
+    # (nos1_jacobi / m, n = 237: 1e-13.58 against [-12.96, -12.83] with csr_bulk_kernel's order, 1e-12.93 with
+    # csr_stream_kernel's, 1e-13.07 on the persistent path) -- but more than a decade below it would mean the
+    # error is not being measured.
+    assert lo - width - 1.0 <= acc <= hi + width + math.log10(2), \
         f"{label}: attainable accuracy 1e{acc:.2f} outside reference band [{lo:.2f}, {hi:.2f}]"
     ilo, ihi = band["iters_band"]
     iw = ihi - ilo

@@ -1,11 +1,11 @@
 #!/usr/bin/env python3
 """SASS evidence per kernel of libcgx_b200.so: counts of the mnemonics that prove the Blackwell-native
-mechanisms (TMA bulk-tensor copies, mbarrier transactions) next to the fp64 arithmetic.
+mechanisms (TMA bulk-tensor copies, cp.async.bulk copies, mbarrier transactions) next to the fp64 arithmetic.
     python tools/sass_summary.py > profiles/sass_r02.txt"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "new_cg_variants_b200", "_obj")
-PAT = {"UTMALDG": r"UTMALDG", "SYNCS (mbarrier)": r"SYNCS\.", "BAR.SYNC": r"BAR\.SYNC", "LDG.E.128": r"LDG\.E\.128", "STG.E.128": r"STG\.E\.128",
+PAT = {"UTMALDG": r"UTMALDG", "UBLKCP": r"UBLKCP", "SYNCS (mbarrier)": r"SYNCS\.", "BAR.SYNC": r"BAR\.SYNC", "LDG.E.128": r"LDG\.E\.128", "STG.E.128": r"STG\.E\.128",
        "LDS.128": r"LDS\.128", "DFMA": r"DFMA", "DMUL": r"DMUL", "DADD": r"DADD", "LDL/STL (spill)": r"\b(LDL|STL)"}
 print("# cuobjdump -sass of the objects linked into libcgx_b200.so (sm_100a): static instruction counts per kernel")
 print("# kernel | " + " | ".join(PAT))
