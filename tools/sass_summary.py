@@ -25,5 +25,5 @@ for obj in sorted(os.listdir(OBJ)):
                 if re.search(p, line):
                     counts[cur][k] += 1
     for k, c in counts.items():
-        if any(s in k for s in ("stencil_tma", "pr_fused", "csr_stream", "ew_kernel<4", "ew_kernel<3", "ew_kernel<5")) and "<" in k:
+        if any(s in k for s in ("stencil_tma", "pr_fused", "csr_stream", "csr_bulk", "ew_kernel<4", "ew_kernel<3", "ew_kernel<5")) and "<" in k:
             print(f"{obj}: {k[:90]} | " + " | ".join(str(c[p]) for p in PAT))
