@@ -143,7 +143,11 @@ int cgx_get_scalars(cgx_ctx* ctx, double* out9);
 
 /* ---- tuning/testing switches.  "tma" = 0 forces the generic (non-TMA) stencil kernel and
  *      "csr_stream" = 0 the thread-per-row CSR kernel, so that two SpMV implementations can
- *      be compared bit for bit; "persistent_threshold" = rows below which CGX_PATH_AUTO
+ *      be compared bit for bit; "csr_bulk" selects the warp-specialised CSR kernel: 1 (default)
+ *      = matrix stream staged by cp.async.bulk for passes with one right-hand side, 2 = for the
+ *      two-right-hand-side pass too, 0 = the register-staged csr_stream_kernel everywhere
+ *      ("csr_bulk_ring" / "csr_bulk_sum" / "csr_bulk_ctas": slots per CTA, summing warps per CTA,
+ *      resident CTAs per SM the ring is sized for); "persistent_threshold" = rows below which CGX_PATH_AUTO
  *      takes the persistent kernel ("pers_threads" / "pers_ctas" override its CTA shape);
  *      "csr_slab" = 0 keeps the persistent kernel's matrix in L2 instead of shared memory;
  *      "cg_elide" = 0 makes CG-CG / GV stream r~ / w~ on the TMA stencil path instead of
