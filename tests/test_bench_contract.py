@@ -35,3 +35,23 @@ def test_our_arm_fails_loudly_without_a_gpu():
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0                           # no CPU fallback: the product path needs the GPU
     assert out.stdout.strip() == ""                      # and never prints a number it did not measure
+
+
+def test_traffic_stamps_match_the_kernel_sources():
+    """profiles/traffic.json holds ncu-measured DRAM bytes per launch; bench.py echoes an entry as
+    `roofline.traffic` only while it is stamped with the fingerprint of the device headers its kernel
+    class is compiled from.  A header edited after the capture (even a comment) makes the bench line
+    report `traffic: null` -- this test says so before the round ends."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from new_cg_variants_b200 import build as b
+    t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    assert "pr_fused" in t and "csr_sp_pr" in t
+    for cls, ent in t.items():
+        assert ent["kernel_sources_sha"] == b.kernel_fingerprint(cls), f"{cls}: captured for other kernel sources"
+        assert all(os.path.exists(os.path.join(b.CSRC, f)) for p, lst in b.KERNEL_SOURCES.items() if cls.startswith(p) for f in lst)
+    val, note = bench.read_traffic("pr_fused")
+    assert val == t["pr_fused"]["dram_bytes_per_launch"] and "ncu" in note
+    assert bench.read_traffic("no_such_kernel")[0] is None
+    # a class's stamp ignores headers its kernel is not compiled from
+    assert b.kernel_fingerprint("pr_fused") != b.kernel_fingerprint("csr_sp_pr") != b.kernel_fingerprint()
