@@ -66,7 +66,7 @@ static void launch_spmv(cgx_ctx* c, Args g, const double* vin, double* vout) {
       const double* a1 = v1 >= 0 ? c->vec[v1 < 0 ? 0 : v1] : nullptr;
       const VecIn in0 = vec_in(c, a0, 0, g), in1 = vec_in(c, a1, 1, g);
       if (c->op_kind == 1) {
-        // (the two-right-hand-side pass stays on csr_stream_kernel unless csr_bulk = 2: measured 155 vs 121 us)
+        // (the two-right-hand-side pass stays on csr_stream_kernel unless csr_bulk = 2: measured 138 vs 121 us per pass)
         if (!c->no_csr_stream && (c->csr_bulk >= 2 || (c->csr_bulk == 1 && nv == 1))) {
           if (csr_dist(c)) launch_csr_bulk<MODE, PM, MEUR, true>(c, g, in0, in1, vout);
           else launch_csr_bulk<MODE, PM, MEUR, false>(c, g, in0, in1, vout);
